@@ -1,0 +1,186 @@
+"""Generate tests/golden/*.npz by executing the UNMODIFIED reference (TEST INFRASTRUCTURE).
+
+Run in the authoring container only (needs /root/reference):  ``python oracle/make_golden.py``
+
+Fixtures written (all small, committed):
+
+* ``scaler_DCASE20xx.npz``  — the reference's shipped ``data/DCASE20xx_SELD/scaler_wts.pkl``
+  statistics (real fixtures, inputs to standardisation), converted to npz.
+* ``features_foa.npz``      — int16 clips + the outputs of the reference's own
+  ``FeatureLabelProcessor.get_feature`` / ``utility.audio2stft|stft2melscale|stft2iv`` executed
+  over the librosa-0.8.1 restatement (see oracle/ref_shims.py; librosa itself is absent here).
+* ``assign_cells.npz``      — reference ``get_yolo_label`` + ``collate_fn`` on a label dict, and
+  the responsible-cell bitmask of every integer (azi, ele) on the sphere plus boundary values.
+* ``loss_ref.npz``          — reference ``ADYOLOloss`` (device='cpu', the only device it runs on
+  under torch>=2) loss value and d loss / d logit on seeded inputs that include the
+  pole/threshold cases of SURVEY F9; D from the reference's own
+  ``distance_between_polar_coordinates``.
+"""
+from __future__ import annotations
+
+import copy
+import os
+import pickle
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from oracle import ref_shims  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def synth_clip(seed: int, seconds: float, kind: str) -> np.ndarray:
+    """Synthetic (N,4) int16 FOA clip. kind: 'noise' (~-20 dBFS white) | 'bursts' (sinusoid
+    bursts + 0.5 s of digital silence: exercises amin, the 1e-8 offset and the top_db clamp)."""
+    rng = np.random.default_rng(seed)
+    n = int(24000 * seconds)
+    if kind == "noise":
+        x = rng.standard_normal((n, 4)) * 3000.0
+    else:
+        t = np.arange(n) / 24000.0
+        x = np.zeros((n, 4))
+        for c in range(4):
+            for _ in range(3):
+                f = rng.uniform(100, 11000)
+                t0 = rng.uniform(0, seconds * 0.6)
+                env = ((t > t0) & (t < t0 + 0.25 * seconds)).astype(np.float64)
+                x[:, c] += env * rng.uniform(500, 12000) * np.sin(2 * np.pi * f * t + rng.uniform(0, 6.28))
+        x += rng.standard_normal((n, 4)) * 2.0
+        s0 = int(n * 0.7)
+        x[s0:s0 + 12000] = 0.0  # digital silence
+    return np.clip(np.round(x), -32768, 32767).astype(np.int16)
+
+
+def synth_labels(seed: int, nb_label_frames: int, nb_classes: int, max_events=3):
+    """label dict {frame: [[cls, src, azi, ele], ...]} with integer degrees incl. F9 cases."""
+    rng = np.random.default_rng(seed)
+    special_el = [90, -90, 65, -65, 45, -45, 80, -80, 67, -68, 0, 22, -23]
+    special_az = [180, -180, 179, -179, 0, 135, -135, 157, -158]
+    label = {}
+    for f in range(nb_label_frames + 3):  # a few frames past the end (must be dropped)
+        k = int(rng.integers(0, max_events + 1))
+        if k == 0:
+            continue
+        evs = []
+        same_cls = int(rng.integers(0, nb_classes))
+        for e in range(k):
+            cls = same_cls if rng.random() < 0.5 else int(rng.integers(0, nb_classes))
+            az = float(rng.choice(special_az)) if rng.random() < 0.3 else float(rng.integers(-180, 181))
+            el = float(rng.choice(special_el)) if rng.random() < 0.3 else float(rng.integers(-90, 91))
+            evs.append([cls, e, az, el])
+        label[f] = evs
+    return label
+
+
+def main():
+    ref_shims.install()
+    import torch
+    import datasets as ref_datasets
+    import models.loss as ref_loss
+    import utils.utility as ref_utility
+    from oracle import features_np as F
+    from oracle.loss_torch import ADYOLOlossOracle
+
+    os.makedirs(GOLD, exist_ok=True)
+
+    # ---- scaler fixtures
+    for year in (2020, 2021, 2022):
+        with open(f"/root/reference/data/DCASE{year}_SELD/scaler_wts.pkl", "rb") as f:
+            sc = pickle.load(f)
+        np.savez(os.path.join(GOLD, f"scaler_DCASE{year}.npz"),
+                 **{f"{k}_{kk}": vv for k, v in sc.items() for kk, vv in v.items()})
+
+    # ---- features through the reference's own class / functions
+    params = ref_shims.ref_params(12)
+    flp = ref_datasets.FeatureLabelProcessor(params)
+    out = {}
+    for name, kind, secs, seed in (("noise", "noise", 2.0, 1), ("bursts", "bursts", 3.0, 2)):
+        clip = synth_clip(seed, secs, kind)
+        audio = clip / 32768.0 + 1e-8                                   # datasets.py:147
+        (MEL, IV), nlf = flp.get_feature(audio)                          # datasets.py:281-292
+        T = int(len(audio) / 600.0)
+        spec = ref_utility.audio2stft(audio, T, 1200, 600, 1200, "han")  # utility.py:142
+        mel_raw = ref_utility.stft2melscale(spec, 24000, 1200, 64)       # utility.py:168
+        iv_raw = ref_utility.stft2iv(spec, 24000, 1200, 64)              # utility.py:194
+        out[f"{name}_audio"] = clip
+        out[f"{name}_MEL"] = MEL
+        out[f"{name}_IV"] = IV
+        out[f"{name}_mel_raw"] = mel_raw
+        out[f"{name}_iv_raw"] = iv_raw
+        out[f"{name}_nlf"] = np.int64(nlf)
+        out[f"{name}_spec_probe"] = spec[::17, ::13, :].copy()          # sparse probe of the STFT
+    np.savez_compressed(os.path.join(GOLD, "features_foa.npz"), **out)
+
+    # ---- grid-cell assignment
+    nlf = 50
+    label = synth_labels(3, nlf, 12)
+    label_in = copy.deepcopy(label)
+    rows = flp.get_yolo_label(copy.deepcopy(label), nlf)                 # datasets.py:457-482
+    feat_dummy = torch.zeros(1)
+    batch = [(feat_dummy, flp.get_yolo_label(copy.deepcopy(label), nlf)),
+             (feat_dummy, []),
+             (feat_dummy, flp.get_yolo_label(synth_labels(4, nlf, 12), nlf))]
+    _, tgt = ref_datasets.collate_fn(batch)                              # datasets.py:164-184
+    # sphere sweep: every integer (azi, ele) + multiples of 22.5 and their float neighbours
+    az = np.concatenate([np.arange(-180, 181, dtype=np.float64), np.arange(-202.5, 203, 22.5),
+                         np.nextafter(np.arange(-180, 181, 22.5), 1e9), np.nextafter(np.arange(-180, 181, 22.5), -1e9)])
+    el = np.concatenate([np.arange(-90, 91, dtype=np.float64), np.arange(-90, 91, 22.5),
+                         np.nextafter(np.arange(-90, 91, 22.5), 1e9), np.nextafter(np.arange(-90, 91, 22.5), -1e9)])
+    AZ, EL = np.meshgrid(az, el, indexing="ij")
+    AZ, EL = AZ.ravel(), EL.ravel()
+    masks = np.zeros(len(AZ), dtype=np.uint32)
+    for i, (a, e) in enumerate(zip(AZ, EL)):
+        r = flp.get_yolo_label({0: [[0, 0, float(a), float(e)]]}, 1)
+        m = 0
+        for row in r:
+            m |= 1 << (int(row[1]) * 4 + int(row[2]))
+        masks[i] = m
+    ev_frames, ev_rows = [], []
+    for fr, evs in label_in.items():
+        for ev in evs:
+            ev_frames.append(fr)
+            ev_rows.append(ev)
+    np.savez_compressed(os.path.join(GOLD, "assign_cells.npz"),
+                        label_frames=np.asarray(ev_frames, np.int64), label_events=np.asarray(ev_rows, np.float64),
+                        nlf=np.int64(nlf), rows=np.asarray(rows, np.float64), collate_target=tgt.numpy(),
+                        label2_frames=np.asarray([fr for fr, evs in synth_labels(4, nlf, 12).items() for _ in evs], np.int64),
+                        label2_events=np.asarray([ev for fr, evs in synth_labels(4, nlf, 12).items() for ev in evs], np.float64),
+                        sweep_az=AZ, sweep_el=EL, sweep_mask=masks)
+
+    # ---- loss (reference class on CPU)
+    lo = {}
+    for C, seed in ((12, 10), (13, 11), (14, 12)):
+        p = ref_shims.ref_params(C)
+        crit = ref_loss.ADYOLOloss(p)
+        orc = ADYOLOlossOracle(p)
+        B, T = 3, 12
+        flpC = ref_datasets.FeatureLabelProcessor(p)
+        batch = [(feat_dummy, flpC.get_yolo_label(synth_labels(seed * 7 + b, T, C), T)) for b in range(B)]
+        _, target = ref_datasets.collate_fn(batch)
+        g = torch.Generator().manual_seed(seed)
+        logit = torch.randn(B, T, 160 * (C + 3), generator=g)
+        logit.requires_grad_(True)
+        loss = crit(logit, target)                                       # loss.py:189-251
+        loss.backward()
+        with torch.no_grad():
+            dec = orc.decode(logit)
+            bi, ti, gi, gj = (target[:, k].long() for k in range(4))
+            D = crit.distance_between_polar_coordinates(dec[bi, ti, gi, gj][..., -2:],
+                                                        target[:, None, -2:].repeat(1, 5, 1))  # loss.py:182-187
+        lo[f"C{C}_logit"] = logit.detach().numpy()
+        lo[f"C{C}_target"] = target.numpy()
+        lo[f"C{C}_loss"] = loss.detach().numpy()
+        lo[f"C{C}_grad"] = logit.grad.numpy()
+        lo[f"C{C}_D"] = D.numpy()
+    np.savez_compressed(os.path.join(GOLD, "loss_ref.npz"), **lo)
+    print("golden fixtures written to", GOLD)
+    for fn in sorted(os.listdir(GOLD)):
+        print(" ", fn, os.path.getsize(os.path.join(GOLD, fn)))
+
+
+if __name__ == "__main__":
+    main()
