@@ -1,0 +1,339 @@
+// AD-YOLO angular-distance responsibility assignment + loss (forward and backward) on sm_100a.
+//
+// Reference behaviour replaced: /root/reference/src/models/loss.py:156-251 (ADYOLOloss):
+//   :193-213 decode (sigmoid / tanh, scale, offset, clamp V, wrap U)
+//   :182-187 distance_between_polar_coordinates (great-circle distance in degrees)
+//   :222-226 responsibility masks D < {45,25,10} + forced argmin
+//   :227-249 obj / class label scatter, 3 x BCE(mean) x 3 thresholds, angular term
+//
+// Bit-exactness: the mask decisions sit on FP32 rounding noise, so the decode and
+// distance chain reproduces torch's *eager op sequence* with individually rounded FP32 ops
+// (__fmul_rn/__fadd_rn, never contracted into FMAs) and the same libdevice functions torch's CUDA
+// kernels call (tanhf, sinf, cosf, acosf, expf).  Everything downstream of the masks (BCE sums,
+// gradients) only has to match to ~1e-5 and is accumulated in FP64.
+//
+// Three launches per call, no host synchronisation:
+//   assign_rows_kernel  : 1 thread / target row  -> D, masks, argmin; atomicOr label bits into a
+//                         per-anchor 64-bit state word; unnormalised angular gradients
+//   loss_anchor_kernel  : 1 thread / anchor (warp-staged, coalesced) -> BCE sums + d loss/d logit
+//   loss_finalize_kernel: scalar loss
+#include "assign_host.h"
+#include "common.cuh"
+
+namespace ady {
+
+__device__ __forceinline__ float sigmoid_torch(float x) {
+    // ATen sigmoid_kernel_cuda: 1 / (1 + exp(-x)) in float
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+}
+__device__ __forceinline__ float clamp_torch(float v, float lo, float hi) {
+    // ATen clamp: NaN-propagating min(max(v, lo), hi)
+    return (v != v) ? v : fminf(fmaxf(v, lo), hi);
+}
+
+struct RowGeom {
+    int b, t, gi, gj, cls;
+    float tu, tv;
+    bool ok;
+};
+
+__device__ __forceinline__ RowGeom read_row(const float* __restrict__ target, long long m, const AssignCfg& c,
+                                            int B, int T) {
+    const float* r = target + m * 7;
+    RowGeom g;
+    g.b = (int)r[0]; g.t = (int)r[1]; g.gi = (int)r[2]; g.gj = (int)r[3]; g.cls = (int)r[4];
+    g.tu = r[5]; g.tv = r[6];
+    g.ok = g.b >= 0 && g.b < B && g.t >= 0 && g.t < T && g.gi >= 0 && g.gi < c.ga && g.gj >= 0 && g.gj < c.ge &&
+           g.cls >= 0 && g.cls < c.nb_classes;
+    return g;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+assign_rows_kernel(const float* __restrict__ logit, const float* __restrict__ target, long long M, int B, int T,
+                   AssignCfg cfg, float* __restrict__ D_out, uint8_t* __restrict__ mask_out,
+                   int32_t* __restrict__ argmin_out, unsigned long long* __restrict__ state,
+                   float2* __restrict__ ang_grad, LossAccum* __restrict__ acc) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int A = cfg.nb_anchors, CH = cfg.nb_classes + 3;
+    double ang_sum = 0.0;
+    int ang_cnt = 0, newpos[ADY_MAX_THR] = {0, 0, 0, 0}, bad = 0;
+    if (m < M) {
+        const RowGeom g = read_row(target, m, cfg, B, T);
+        if (!g.ok) {
+            bad = 1;
+            for (int a = 0; a < A; ++a) {
+                if (D_out) D_out[m * A + a] = __int_as_float(0x7fc00000);
+                if (mask_out) for (int i = 0; i < cfg.n_thr; ++i) mask_out[((long long)i * M + m) * A + a] = 0;
+            }
+            if (argmin_out) argmin_out[m] = -1;
+        } else {
+            const long long cell = (((long long)g.b * T + g.t) * cfg.ga + g.gi) * cfg.ge + g.gj;
+            const float* lp = logit + cell * A * CH + (cfg.nb_classes + 1);
+            const float off_u = cfg.off_u[g.gi], off_v = cfg.off_v[g.gj];
+            // target side of loss.py:184-186 (deg2rad, sin, cos) — computed once per row
+            const float tur = __fmul_rn(g.tu, cfg.deg2rad), tvr = __fmul_rn(g.tv, cfg.deg2rad);
+            const float stv = sinf(tvr), ctv = cosf(tvr);
+            float Dv[ADY_MAX_ANCHORS], gu[ADY_MAX_ANCHORS], gv[ADY_MAX_ANCHORS];
+            float dmin = 0.f;
+            int amin = 0;
+#pragma unroll
+            for (int a = 0; a < ADY_MAX_ANCHORS; ++a) {
+                if (a >= A) break;
+                const float xu = lp[a * CH], xv = lp[a * CH + 1];
+                // loss.py:196-198 tanh; :203-205 three separately rounded ops
+                const float thu = tanhf(xu), thv = tanhf(xv);
+                float U = __fadd_rn(__fmul_rn(__fmul_rn(thu, cfg.ovl_scale), cfg.gs_u), off_u);
+                float Vp = __fadd_rn(__fmul_rn(__fmul_rn(thv, cfg.ovl_scale), cfg.gs_v), off_v);
+                const float V = clamp_torch(Vp, -90.f, 90.f);       // :208
+                if (U >= 180.f) U = __fadd_rn(U, -360.f);            // :209-210
+                if (U < -180.f) U = __fadd_rn(U, 360.f);             // :211-212
+                // :184-187
+                const float our = __fmul_rn(U, cfg.deg2rad), ovr = __fmul_rn(V, cfg.deg2rad);
+                const float sov = sinf(ovr), cov = cosf(ovr);
+                const float du = __fadd_rn(our, -tur);
+                const float adu = fabsf(du);
+                const float cdu = cosf(adu);
+                const float dist = __fadd_rn(__fmul_rn(sov, stv), __fmul_rn(__fmul_rn(cov, ctv), cdu));
+                const float cl = clamp_torch(dist, cfg.clip_lo, cfg.clip_hi);
+                const float Dd = __fmul_rn(acosf(cl), cfg.rad2deg);
+                Dv[a] = Dd;
+                if (a == 0 || Dd < dmin) { dmin = Dd; amin = a; }   // first minimum (torch.min)
+                // ---- backward of the chain (only needs ~1e-5): dD/d(xu), dD/d(xv)
+                const float pass = (dist >= cfg.clip_lo && dist <= cfg.clip_hi) ? 1.f : 0.f;
+                const float dD_ddist = -cfg.rad2deg * rsqrtf(fmaxf(1.f - cl * cl, 1e-30f)) * pass;
+                const float sgn = du > 0.f ? 1.f : (du < 0.f ? -1.f : 0.f);
+                const float ddist_dou = -(cov * ctv) * sinf(adu) * sgn;
+                const float ddist_dov = cov * stv - sov * ctv * cdu;
+                const float vpass = (Vp >= -90.f && Vp <= 90.f) ? 1.f : 0.f;
+                const float k = cfg.deg2rad * cfg.ovl_scale;
+                gu[a] = dD_ddist * ddist_dou * k * cfg.gs_u * (1.f - thu * thu);
+                gv[a] = dD_ddist * ddist_dov * k * cfg.gs_v * vpass * (1.f - thv * thv);
+            }
+            if (argmin_out) argmin_out[m] = amin;
+#pragma unroll
+            for (int a = 0; a < ADY_MAX_ANCHORS; ++a) {
+                if (a >= A) break;
+                if (D_out) D_out[m * A + a] = Dv[a];
+                unsigned long long bits = 0ull;
+                for (int i = 0; i < cfg.n_thr; ++i) {
+                    const bool resp = (Dv[a] < cfg.thr[i]) || (a == amin);   // :223-224
+                    if (mask_out) mask_out[((long long)i * M + m) * A + a] = resp ? 1 : 0;
+                    if (resp) bits |= (1ull | (2ull << g.cls)) << (16 * i);
+                    if (i == 0 && resp) {                                    // :244-246 angular term
+                        ang_sum += (double)Dv[a];
+                        ang_cnt += 1;
+                        if (ang_grad) {
+                            atomicAdd(&ang_grad[cell * A + a].x, gu[a]);
+                            atomicAdd(&ang_grad[cell * A + a].y, gv[a]);
+                        }
+                    }
+                }
+                if (bits && state) {
+                    const unsigned long long old = atomicOr(&state[cell * A + a], bits);
+                    const unsigned long long fresh = bits & ~old;
+                    for (int i = 0; i < cfg.n_thr; ++i) newpos[i] += (int)((fresh >> (16 * i)) & 1ull);
+                }
+            }
+        }
+    }
+    if (!acc) return;
+    // block reduction of the few counters (warp shuffle, then one atomic per warp)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        ang_sum += __shfl_xor_sync(0xffffffffu, ang_sum, o);
+        ang_cnt += __shfl_xor_sync(0xffffffffu, ang_cnt, o);
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+#pragma unroll
+        for (int i = 0; i < ADY_MAX_THR; ++i) newpos[i] += __shfl_xor_sync(0xffffffffu, newpos[i], o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (ang_cnt) { atomicAdd(&acc->ang_sum, ang_sum); atomicAdd(&acc->ang_cnt, (unsigned long long)ang_cnt); }
+        if (bad) atomicAdd(&acc->bad_rows, bad);
+        for (int i = 0; i < cfg.n_thr; ++i)
+            if (newpos[i]) atomicAdd(&acc->n_pos[i], (unsigned long long)newpos[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BCE pieces exactly as ATen (Loss.cu binary_cross_entropy_out_cuda / _backward):
+//   loss = (t-1) * max(log1p(-p), -100) - t * max(log(p), -100)
+//   dL/dp = (p - t) / max((1-p) p, 1e-12);   dp/dx = (1-p) p
+__device__ __forceinline__ float bce_fwd(float p, float t) {
+    const float lp = fmaxf(logf(p), -100.f), l1 = fmaxf(log1pf(-p), -100.f);
+    return (t - 1.f) * l1 - t * lp;
+}
+__device__ __forceinline__ float bce_bwd_logit(float p, float t) {
+    const float q = (1.f - p) * p;
+    return (p - t) / fmaxf(q, 1e-12f) * q;
+}
+
+constexpr int LA_WARPS = 4;
+
+__global__ void __launch_bounds__(LA_WARPS * 32)
+loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCfg cfg,
+                   const unsigned long long* __restrict__ state, const float2* __restrict__ ang_grad,
+                   LossAccum* __restrict__ acc, float* __restrict__ grad) {
+    extern __shared__ float sh[];
+    const int CH = cfg.nb_classes + 3, C = cfg.nb_classes;
+    const int stride = CH | 1;  // odd -> conflict-free per-thread rows
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* tile = sh + warp * 32 * stride;
+
+    // per-threshold normalisers (counts are final: assign_rows_kernel has completed)
+    float w_pos[ADY_MAX_THR], w_neg[ADY_MAX_THR], w_cls[ADY_MAX_THR];
+    for (int i = 0; i < ADY_MAX_THR; ++i) {
+        const double np_ = i < cfg.n_thr ? (double)acc->n_pos[i] : 0.0;
+        const double nn_ = (double)n_anchor - np_;
+        w_pos[i] = i < cfg.n_thr ? (float)(cfg.gain_obj / (cfg.n_thr * np_)) : 0.f;
+        w_neg[i] = i < cfg.n_thr ? (float)(cfg.gain_nonobj / (cfg.n_thr * nn_)) : 0.f;
+        w_cls[i] = i < cfg.n_thr ? (float)(cfg.gain_cls / (cfg.n_thr * np_ * C)) : 0.f;
+    }
+    const double n_ang = (double)acc->ang_cnt;
+    const float w_ang = (float)(cfg.gain_ang / (180.0 * n_ang));
+
+    double s_pos[ADY_MAX_THR] = {0, 0, 0, 0}, s_neg[ADY_MAX_THR] = {0, 0, 0, 0}, s_cls[ADY_MAX_THR] = {0, 0, 0, 0};
+
+    const long long n_groups = (n_anchor + 31) / 32;
+    for (long long grp = (long long)blockIdx.x * LA_WARPS + warp; grp < n_groups; grp += (long long)gridDim.x * LA_WARPS) {
+        const long long a0 = grp * 32;
+        const int na = (int)min(32LL, n_anchor - a0);
+        const float* src = logit + a0 * CH;
+        for (int i = lane; i < na * CH; i += 32) tile[(i / CH) * stride + (i % CH)] = src[i];
+        __syncwarp();
+        if (lane < na) {
+            float* row = tile + lane * stride;
+            const unsigned long long st = state[a0 + lane];
+            const float p = sigmoid_torch(row[0]);
+            const float l_pos = bce_fwd(p, 1.f), l_neg = bce_fwd(p, 0.f);
+            const float g_pos = bce_bwd_logit(p, 1.f), g_neg = bce_bwd_logit(p, 0.f);
+            float g_obj = 0.f;
+            bool any = false;
+#pragma unroll
+            for (int i = 0; i < ADY_MAX_THR; ++i) {
+                if (i >= cfg.n_thr) break;
+                const bool pos = (st >> (16 * i)) & 1ull;
+                any |= pos;
+                if (pos) { s_pos[i] += l_pos; g_obj += w_pos[i] * g_pos; }
+                else     { s_neg[i] += l_neg; g_obj += w_neg[i] * g_neg; }
+            }
+            row[0] = g_obj;
+            if (any) {
+                for (int c = 0; c < C; ++c) {
+                    const float pc = sigmoid_torch(row[1 + c]);
+                    const float l1 = bce_fwd(pc, 1.f), l0 = bce_fwd(pc, 0.f);
+                    const float g1 = bce_bwd_logit(pc, 1.f), g0 = bce_bwd_logit(pc, 0.f);
+                    float gc = 0.f;
+#pragma unroll
+                    for (int i = 0; i < ADY_MAX_THR; ++i) {
+                        if (i >= cfg.n_thr) break;
+                        if ((st >> (16 * i)) & 1ull) {
+                            const bool t = (st >> (16 * i + 1 + c)) & 1ull;
+                            s_cls[i] += t ? l1 : l0;
+                            gc += w_cls[i] * (t ? g1 : g0);
+                        }
+                    }
+                    row[1 + c] = gc;
+                }
+            } else {
+                for (int c = 0; c < C; ++c) row[1 + c] = 0.f;
+            }
+            const float2 ag = ang_grad[a0 + lane];
+            row[C + 1] = ag.x * w_ang;
+            row[C + 2] = ag.y * w_ang;
+        }
+        __syncwarp();
+        if (grad) {
+            float* dst = grad + a0 * CH;
+            for (int i = lane; i < na * CH; i += 32) dst[i] = tile[(i / CH) * stride + (i % CH)];
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < ADY_MAX_THR; ++i) {
+            s_pos[i] += __shfl_xor_sync(0xffffffffu, s_pos[i], o);
+            s_neg[i] += __shfl_xor_sync(0xffffffffu, s_neg[i], o);
+            s_cls[i] += __shfl_xor_sync(0xffffffffu, s_cls[i], o);
+        }
+    if (lane == 0)
+        for (int i = 0; i < cfg.n_thr; ++i) {
+            atomicAdd(&acc->s_pos[i], s_pos[i]);
+            atomicAdd(&acc->s_neg[i], s_neg[i]);
+            atomicAdd(&acc->s_cls[i], s_cls[i]);
+        }
+}
+
+__global__ void loss_finalize_kernel(long long n_anchor, AssignCfg cfg, const LossAccum* __restrict__ acc,
+                                     float* __restrict__ loss_out) {
+    if (threadIdx.x || blockIdx.x) return;
+    // loss.py:219, 244-249 (means of empty sets are NaN exactly like torch)
+    double total = cfg.gain_ang * (acc->ang_sum / 180.0) / (double)acc->ang_cnt;
+    for (int i = 0; i < cfg.n_thr; ++i) {
+        const double np_ = (double)acc->n_pos[i], nn_ = (double)n_anchor - np_;
+        const double pos = acc->s_pos[i] / np_, neg = acc->s_neg[i] / nn_;
+        const double cls = acc->s_cls[i] / (np_ * cfg.nb_classes);
+        total += (pos * cfg.gain_obj + neg * cfg.gain_nonobj + cls * cfg.gain_cls) / cfg.n_thr;
+    }
+    loss_out[0] = (float)total;
+}
+
+// ------------------------------------------------------------------------------------------------
+size_t loss_workspace_bytes(int B, int T, const AssignCfg& cfg) {
+    const size_t n_anchor = (size_t)B * T * cfg.ga * cfg.ge * cfg.nb_anchors;
+    return sizeof(LossAccum) + n_anchor * (sizeof(unsigned long long) + sizeof(float2));
+}
+
+static int check_cfg(const AssignCfg& c) {
+    if (c.nb_anchors < 1 || c.nb_anchors > ADY_MAX_ANCHORS) return set_error(ADY_ERR_INVALID, "nb_anchors must be 1..%d", ADY_MAX_ANCHORS);
+    if (c.n_thr < 1 || c.n_thr > ADY_MAX_THR) return set_error(ADY_ERR_INVALID, "train_unify must have 1..%d entries", ADY_MAX_THR);
+    if (c.nb_classes < 1 || c.nb_classes > 15) return set_error(ADY_ERR_INVALID, "nb_classes must be 1..15");
+    if (c.ga < 1 || c.ga > ADY_MAX_GRID || c.ge < 1 || c.ge > ADY_MAX_GRID) return set_error(ADY_ERR_INVALID, "grid too large");
+    return ADY_OK;
+}
+
+int launch_assign(const float* logit, const float* target, long long M, int B, int T, const AssignCfg& cfg,
+                  float* D, uint8_t* mask, int32_t* argmin, cudaStream_t stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (M <= 0) return ADY_OK;
+    const int blocks = (int)((M + 127) / 128);
+    assign_rows_kernel<<<blocks, 128, 0, stream>>>(logit, target, M, B, T, cfg, D, mask, argmin, nullptr, nullptr, nullptr);
+    ADY_LAUNCH_CHECK("assign_rows_kernel");
+    return ADY_OK;
+}
+
+int launch_loss(const float* logit, const float* target, long long M, int B, int T, const AssignCfg& cfg,
+                float* loss_out, float* grad_out, float* D, uint8_t* mask, int32_t* argmin, void* ws,
+                cudaStream_t stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    const long long n_anchor = (long long)B * T * cfg.ga * cfg.ge * cfg.nb_anchors;
+    if (n_anchor <= 0) return set_error(ADY_ERR_INVALID, "adyolo_loss: empty logit");
+    LossAccum* acc = reinterpret_cast<LossAccum*>(ws);
+    unsigned long long* state = reinterpret_cast<unsigned long long*>(acc + 1);
+    float2* ang = reinterpret_cast<float2*>(state + n_anchor);
+    ADY_CUDA_CHECK(cudaMemsetAsync(ws, 0, loss_workspace_bytes(B, T, cfg), stream));
+    if (M > 0) {
+        const int blocks = (int)((M + 127) / 128);
+        assign_rows_kernel<<<blocks, 128, 0, stream>>>(logit, target, M, B, T, cfg, D, mask, argmin, state, ang, acc);
+        ADY_LAUNCH_CHECK("assign_rows_kernel");
+    }
+    int dev = 0, sms = 0;
+    ADY_CUDA_CHECK(cudaGetDevice(&dev));
+    ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int stride = (cfg.nb_classes + 3) | 1;
+    const size_t shmem = (size_t)LA_WARPS * 32 * stride * sizeof(float);
+    const long long n_groups = (n_anchor + 31) / 32;
+    long long blocks = (n_groups + LA_WARPS - 1) / LA_WARPS;
+    const long long cap = (long long)sms * 16;
+    if (blocks > cap) blocks = cap;
+    loss_anchor_kernel<<<(int)blocks, LA_WARPS * 32, shmem, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out);
+    ADY_LAUNCH_CHECK("loss_anchor_kernel");
+    loss_finalize_kernel<<<1, 32, 0, stream>>>(n_anchor, cfg, acc, loss_out);
+    ADY_LAUNCH_CHECK("loss_finalize_kernel");
+    return ADY_OK;
+}
+
+}  // namespace ady

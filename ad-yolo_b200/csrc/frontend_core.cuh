@@ -1,0 +1,201 @@
+// Per-thread building blocks of the fused SELD front-end kernel (FOA: STFT -> log-mel + IV).
+//
+// Replaces, per tile of TF feature frames of one clip (reference: /root/reference/src/
+// datasets.py:252-292 get_stft_spectrogram / get_logmel_spectrogram /
+// get_melscale_foa_intensity_vectors / get_feature, == utils/utility.py:142-215):
+//
+//   stage 1   : windowed samples (int16 pairs (W,Y) / (Z,X) packed as one complex signal)
+//               -> 25 x DFT-48 per packed FFT            [thread = (fft, n2)]
+//   stage 2a  : 25 x (2 x DFT-25) per packed FFT          [thread = (frame, residue pair t, role)]
+//   stage 2b  : split packed spectra into the two real channels' spectra using the partner
+//               bin N-k held by the SAME thread, |X|^2, FOA intensity (A/B lanes swap W and
+//               energy with one shuffle step), write 7 values per bin to shared memory
+//   mel       : sparse (CSR) mel projection, 10 log10, standardise, store (B,7,T,64)
+//
+// The 1200-point transform is a Good-Thomas prime-factor FFT (48 x 25, coprime): no twiddle
+// factors between the stages, only compile-time index permutations.  All functions are
+// ADY_HD so that tests/emu can run the identical code on the CPU.
+#pragma once
+#include <stdint.h>
+
+#include "fft_codelets.cuh"
+
+namespace ady {
+
+// ---------------------------------------------------------------- fixed geometry (hyp_data_DCASE20xx.yaml:5-12)
+constexpr int NFFT = 1200;
+constexpr int HOP = 600;
+constexpr int NBIN = 601;
+constexpr int NMEL = 64;
+constexpr int NCH_IN = 4;
+constexpr int NCH_FOA = 7;
+
+// ---------------------------------------------------------------- tiling
+constexpr int TF = 3;              // frames per tile
+constexpr int NTHREADS = 160;      // 150 active in the FFT stages (3 frames x 2 packed FFTs x 25)
+constexpr int NFFT_TILE = 2 * TF;  // packed complex FFTs per tile
+
+// sample planes: one per (frame, pair); word(idx) = idx + idx/16  (skew -> conflict-free
+// stride-48 reads); 1275 words per plane == 51*25 so that lane L = 25*fft + n2 reads word
+// 51*L + const.
+constexpr int SPLANE = 1275;
+constexpr int WROW = 49;                 // window table row stride (25 rows x 48 used)
+constexpr int FS = 1208;                 // float2 per packed FFT in the exchange buffer (2416 words == 16 mod 32)
+constexpr int VFRAME = 2 * FS;           // float2 units per frame (V4a + V4b alias the exchange buffer)
+constexpr int MEL_MAXNNZ = 1216;
+
+struct SmemLayout {
+    static constexpr int off_samples = 0;                                   // uint32 [6][1275]
+    static constexpr int off_x1 = ((off_samples + NFFT_TILE * SPLANE * 4 + 15) / 16) * 16;  // float2 [6][1208]
+    static constexpr int off_win = off_x1 + NFFT_TILE * FS * 8;              // float  [25][49]
+    static constexpr int off_melw = off_win + 25 * WROW * 4;                 // float  [1216]
+    static constexpr int off_melidx = off_melw + MEL_MAXNNZ * 4;             // int16  [3][64] start,len,off
+    static constexpr int off_red = off_melidx + 3 * NMEL * 2;                // int32  [8] tile max/min keys
+    static constexpr int total = ((off_red + 8 * 4 + 15) / 16) * 16;
+};
+static_assert(SmemLayout::off_x1 % 16 == 0 && SmemLayout::off_win % 16 == 0, "alignment");
+static_assert(2 * NBIN * 16 <= VFRAME * 8, "V must fit in the exchange buffer of its frame");
+
+// ---------------------------------------------------------------- helpers
+ADY_HD int skew(int idx) { return idx + (idx >> 4); }
+
+// order-preserving float <-> uint key (for atomicMax/Min on floats of any sign)
+ADY_HD uint32_t f2key(float f) {
+    union { float f; uint32_t u; } c; c.f = f;
+    return (c.u & 0x80000000u) ? ~c.u : (c.u | 0x80000000u);
+}
+ADY_HD float key2f(uint32_t k) {
+    union { float f; uint32_t u; } c;
+    c.u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return c.f;
+}
+
+// ---------------------------------------------------------------- stage 1
+// thread (g = packed fft 0..5, n2 = 0..24).  samples: uint32 words (lo int16 = re channel,
+// hi int16 = im channel).  win: row n2 holds w[(25 n1 + 48 n2) mod 1200] * scale.
+ADY_HD void stage1_task(const uint32_t* __restrict__ samples, const float* __restrict__ win,
+                        float2* __restrict__ x1, int g, int n2) {
+    const uint32_t* sp = samples + g * SPLANE + 51 * n2;
+    const float* wp = win + WROW * n2;
+    const int thr = 1200 - 48 * n2;  // wrap when 25*n1 >= thr
+    cx<float> x[48];
+#pragma unroll
+    for (int n1 = 0; n1 < 48; ++n1) {
+        const int c = 25 * n1;
+        const int off = c + (c >> 4);
+        const uint32_t word = sp[off - (c >= thr ? SPLANE : 0)];
+        const float w = wp[n1];
+        const float lo = (float)(int16_t)(word & 0xffffu);
+        const float hi = (float)(int16_t)(word >> 16);
+        x[n1] = {lo * w, hi * w};
+    }
+    dft48(x);
+    float2* xo = x1 + g * FS + n2;
+#pragma unroll
+    for (int k1 = 0; k1 < 48; ++k1) xo[k1 * 25] = make_float2(x[k1].re, x[k1].im);
+}
+
+// ---------------------------------------------------------------- stage 2a
+struct Stage2Regs {
+    cx<float> P[25], Q[25];
+};
+
+// thread (frame f, residue pair t = 0..24 -> rows (t, (48-t)%48), role r: 0 = (W,Y) fft, 1 = (Z,X) fft)
+// dc: analytic contribution of the "+1e-8" DC offset of datasets.py:147 (pre-scaled like the
+// window): bin 0 gets +dc0 on both packed components, bins +-1 get dc1.
+ADY_HD void stage2a_task(const float2* __restrict__ x1, int f, int t, int r, float dc0, float dc1,
+                         Stage2Regs& s) {
+    const int g = 2 * f + r;
+    const float2* pa = x1 + g * FS + t * 25;
+    const float2* pb = x1 + g * FS + ((48 - t) % 48) * 25;
+#pragma unroll
+    for (int n2 = 0; n2 < 25; ++n2) {
+        float2 a = pa[n2], b = pb[n2];
+        s.P[n2] = {a.x, a.y};
+        s.Q[n2] = {b.x, b.y};
+    }
+    dft25(s.P);
+    dft25(s.Q);
+    if (t == 0) {  // bin 0 <-> (k1,k2) = (0,0); P and Q are the same row here
+        s.P[0].re += dc0; s.P[0].im += dc0;
+        s.Q[0].re += dc0; s.Q[0].im += dc0;
+    }
+    if (t == 1) {  // bin 1 <-> (1,1) in P; bin 1199 <-> (47,24) in Q
+        s.P[1].re += dc1; s.P[1].im += dc1;
+        s.Q[24].re += dc1; s.Q[24].im += dc1;
+    }
+}
+
+// ---------------------------------------------------------------- stage 2b (per slot)
+struct SlotOut {          // what a lane sends to its partner lane (role A <-> role B)
+    float s0re, s0im, e;
+};
+struct SlotMine {
+    cx<float> S0, S1;     // role A: (W, Y)   role B: (Z, X)
+    float P0, P1;
+};
+
+ADY_HD void slot_split(const cx<float> a, const cx<float> bq, float c0, SlotMine& m, SlotOut& o) {
+    // a = A[k], bq = A[N-k] of the packed FFT (already halved by the window scale):
+    // S0 = (a + conj bq), S1 = (a - conj bq)/i
+    m.S0 = {a.re + bq.re, a.im - bq.im};
+    m.S1 = {a.im + bq.im, bq.re - a.re};
+    m.P0 = m.S0.re * m.S0.re + m.S0.im * m.S0.im;
+    m.P1 = m.S1.re * m.S1.re + m.S1.im * m.S1.im;
+    o.s0re = m.S0.re;
+    o.s0im = m.S0.im;
+    o.e = c0 * m.P0 + m.P1 * (1.0f / 3.0f);
+}
+
+// E = eps + |W|^2 + (|Y|^2+|Z|^2+|X|^2)/3  (datasets.py:272);  I = Re(conj(W) X_c) / E (:271,274)
+ADY_HD void slot_finish(const SlotMine& m, const SlotOut& mine, const SlotOut& other, int r,
+                        float& iva, float& ivb) {
+    const float wre = r == 0 ? m.S0.re : other.s0re;
+    const float wim = r == 0 ? m.S0.im : other.s0im;
+    const float E = 1e-8f + (mine.e + other.e);
+    const float rE = 1.0f / E;
+    iva = (wre * m.S0.re + wim * m.S0.im) * rE;   // role B: IV_Z        (role A: unused)
+    ivb = (wre * m.S1.re + wim * m.S1.im) * rE;   // role A: IV_Y, role B: IV_X
+}
+
+// bin index (folded to 0..600) of PFA output (k1 = t, k2)
+ADY_HD int slot_bin(int kt /* = 625*t % 1200 */, int k2) {
+    int k = kt + (576 * k2) % 1200;
+    k = k >= 1200 ? k - 1200 : k;
+    return k > 600 ? 1200 - k : k;
+}
+
+// V layout per frame (float4 units): V4a[k] = (|W|^2,|Y|^2,|Z|^2,|X|^2), V4b[k] = (junk, IV_Y, IV_Z, IV_X)
+ADY_HD void slot_store(float2* __restrict__ vframe, int k, int r, float P0, float P1, float iva, float ivb) {
+    vframe[2 * k + r] = make_float2(P0, P1);
+    vframe[2 * NBIN + 2 * k + r] = make_float2(iva, ivb);
+}
+
+// ---------------------------------------------------------------- mel phase
+// task (f, half, j): half 0 -> 4 power channels, half 1 -> IV channels. returns 4 accumulators.
+ADY_HD void mel_task(const float4* __restrict__ vframe4, const float* __restrict__ melw,
+                     const int16_t* __restrict__ melidx, int half, int j, float (&acc)[4]) {
+    const int start = melidx[j], len = melidx[NMEL + j], off = melidx[2 * NMEL + j];
+    const float4* v = vframe4 + half * NBIN + start;
+    const float* w = melw + off;
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+    for (int i = 0; i < len; ++i) {
+        const float4 x = v[i];
+        const float wi = w[i];
+        acc[0] += wi * x.x;
+        acc[1] += wi * x.y;
+        acc[2] += wi * x.z;
+        acc[3] += wi * x.w;
+    }
+}
+
+// librosa.power_to_db(ref=1, amin=1e-10) before the top_db clamp (datasets.py:265)
+ADY_HD float power_to_db_unclamped(float s) {
+#if defined(__CUDA_ARCH__)
+    return 10.0f * log10f(fmaxf(s, 1e-10f));
+#else
+    return 10.0f * __builtin_log10f(s > 1e-10f ? s : 1e-10f);
+#endif
+}
+
+}  // namespace ady

@@ -1,0 +1,31 @@
+// Host-side declarations shared by the front-end translation units and the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace ady {
+
+struct FrontendTables {
+    float win[25 * 49];      // win[n2*49 + n1] = hann[(25 n1 + 48 n2) % 1200] * 2^-16
+    float melw[1216];        // concatenated non-zero runs of the (64 x 601) Slaney mel matrix
+    int16_t melidx[3 * 64];  // [start | len | offset into melw] per mel filter
+    float hann[1200];        // plain periodic Hann (for the float-input / stft paths)
+};
+
+// librosa.filters.mel(sr, n_fft, n_mels) defaults (Slaney scale + norm, float32), row-major
+// (n_mels, 1 + n_fft/2).  Host arithmetic in double, replicating librosa's rounding steps.
+void mel_filterbank_host(int sr, int n_fft, int n_mels, float* out);
+
+// Device-resident constant tables for the fixed DCASE geometry (built once per device).
+int get_frontend_tables(const FrontendTables** dev_tables);
+
+size_t frontend_workspace_bytes(int B, long long N);
+int launch_features_foa(const int16_t* audio, int B, long long N, const float* mean, const float* istd,
+                        float dc_offset, float top_db, int apply_topdb, float* out, void* ws,
+                        cudaStream_t stream);
+
+int launch_features_foa_clamp(float* out, int B, long long N, const float* mean, const float* istd, float top_db,
+                              void* ws, cudaStream_t stream);
+
+}  // namespace ady

@@ -1,0 +1,130 @@
+"""AD-YOLO loss: Python mirror of ``models/loss.py:156-251`` over the CUDA C ABI.
+
+``ADYOLOloss(params)(logit, target) -> tensor[1]`` like the reference, differentiable w.r.t.
+``logit`` through a ``torch.autograd.Function`` whose forward launches the fused
+assignment + loss + gradient kernels (no host synchronisation, unlike the reference's nine).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, require_cuda, stream_ptr
+from .labels import GridSpec
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def _check_inputs(logit, target, grid):
+    require_cuda(logit, "ADYOLOloss")
+    if logit.dim() != 3 or logit.shape[-1] != grid.nb_predicts * grid.nb_channels:
+        raise ValueError(f"logit must be (B, T, {grid.nb_predicts * grid.nb_channels}); got {tuple(logit.shape)}")
+    if target.dim() != 2 or target.shape[-1] != 7:
+        raise ValueError("target must be (M, 7) [batch, frame, Gi, Gj, class, U, V]")
+
+
+def adyolo_assign(logit: torch.Tensor, target: torch.Tensor, grid: GridSpec):
+    """loss.py:193-226 only: -> D (M, A) float32, masks (n_thr, M, A) bool, argmin (M,) int64."""
+    _check_inputs(logit, target, grid)
+    logit = logit.detach().contiguous().float()
+    target = target.to(logit.device, torch.float32).contiguous()
+    B, T, _ = logit.shape
+    M, A, K = target.shape[0], grid.nb_anchors, len(grid.train_unify)
+    with torch.cuda.device(logit.device):
+        D = torch.empty((M, A), dtype=torch.float32, device=logit.device)
+        mask = torch.empty((K, M, A), dtype=torch.uint8, device=logit.device)
+        amin = torch.empty((M,), dtype=torch.int32, device=logit.device)
+        check(_lib.lib().adyolo_assign(ptr(logit), ptr(target), M, B, T, C.byref(grid.c), ptr(D), ptr(mask), ptr(amin),
+                                       stream_ptr()), "adyolo_assign")
+    return D, mask.bool(), amin.long()
+
+
+class _ADYOLOFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logit, target, grid):
+        B, T, _ = logit.shape
+        M = target.shape[0]
+        L = _lib.lib()
+        need_grad = logit.requires_grad
+        with torch.cuda.device(logit.device):
+            loss = torch.empty(1, dtype=torch.float32, device=logit.device)
+            grad = torch.empty_like(logit) if need_grad else None
+            ws = _workspace(L.adyolo_loss_workspace_bytes(B, T, C.byref(grid.c)), logit.device)
+            check(L.adyolo_loss(ptr(logit), ptr(target), M, B, T, C.byref(grid.c), ptr(loss), ptr(grad), None, None,
+                                None, ptr(ws), stream_ptr()), "adyolo_loss")
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        (grad,) = ctx.saved_tensors
+        return (grad * gout.reshape(1, 1, 1) if grad is not None else None), None, None
+
+
+class ADYOLOloss(object):
+    """loss.py:156-251.  Reads the same ``params`` keys as the reference."""
+
+    def __init__(self, params: dict):
+        self.device = torch.device(params["args"]["device"])
+        if self.device.type != "cuda":
+            raise RuntimeError("adyolo_b200.ADYOLOloss needs params['args']['device'] to be a CUDA device "
+                               "(no CPU fallback)")
+        tc = params["train_config"]
+        self.nb_classes = params["data_config"]["nb_classes"]
+        self.nb_anchors = tc["nb_anchors"]
+        self.train_unify = tc["train_unify"]
+        self.g_overlap = tc["g_overlap"]
+        self.loss_gains = tc["loss_gains"]
+        self.grid = GridSpec(self.nb_classes, self.nb_anchors, tc["grid_size"], tc["g_overlap"], tc["train_unify"],
+                             tc["loss_gains"])
+        self.nb_grids = torch.Tensor(self.grid.nb_grids).long()
+        self.nb_predicts = self.grid.nb_predicts
+
+    def distance_between_polar_coordinates(self, output_coord, target_coord):
+        """loss.py:182-187 on already-decoded coordinates (debug/compat surface).  The fused path
+        never materialises decoded outputs; this evaluates the same FP32 op sequence with torch ops
+        on the caller's device."""
+        output_coord, target_coord = torch.deg2rad(output_coord), torch.deg2rad(target_coord)
+        dist = (torch.sin(output_coord[..., 1]) * torch.sin(target_coord[..., 1]) +
+                torch.cos(output_coord[..., 1]) * torch.cos(target_coord[..., 1]) *
+                torch.cos(torch.abs(output_coord[..., 0] - target_coord[..., 0])))
+        return torch.rad2deg(torch.acos(torch.clip(dist, -1 + 1e-7, 1 - 1e-7)))
+
+    def assign(self, logit, target):
+        return adyolo_assign(logit, target, self.grid)
+
+    def __call__(self, logit: torch.Tensor, target: torch.Tensor):
+        _check_inputs(logit, target, self.grid)
+        if logit.dtype != torch.float32:
+            logit = logit.float()
+        logit = logit.contiguous()
+        target = target.to(logit.device, torch.float32).contiguous()   # loss.py:199
+        return _ADYOLOFn.apply(logit, target, self.grid)
+
+
+class WrapperCriterion(object):
+    """wrapper.py:63-88 restricted to the loss on the B200 hot path."""
+
+    def __init__(self, params):
+        self.nb_classes = params["data_config"]["nb_classes"]
+        self.loss_nm = params["args"]["loss"]
+        if self.loss_nm == "adyolo":
+            self.loss = ADYOLOloss(params)
+        elif self.loss_nm in ("seddoa", "masked-seddoa", "accdoa", "adpit"):
+            raise NotImplementedError(f"loss: {self.loss_nm} is outside the B200 hot path (use the reference)")
+        else:
+            raise NotImplementedError("loss: {}".format(self.loss_nm))
+
+    def __call__(self, output, target):
+        return self.loss(output, target)

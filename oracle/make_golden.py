@@ -34,14 +34,33 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 
 def synth_clip(seed: int, seconds: float, kind: str) -> np.ndarray:
-    """Synthetic (N,4) int16 FOA clip. kind: 'noise' (~-20 dBFS white) | 'bursts' (sinusoid
-    bursts + 0.5 s of digital silence: exercises amin, the 1e-8 offset and the top_db clamp)."""
+    """Synthetic (N,4) int16 FOA clip (channel order W,Y,Z,X as in the DCASE foa_dev wavs).
+
+    'noise'  : ~-20 dBFS white noise, independent per channel.
+    'bursts' : three point sources (tone bursts) encoded to FOA by their direction, a -60 dBFS
+               sensor-noise floor and 0.5 s of digital silence (exercises amin, the 1e-8
+               offset and the top_db clamp).
+    'harsh'  : per-channel independent full-scale tone bursts over a 2-LSB dither (channels up
+               to 75 dB apart inside one frame: probes the FP32 dynamic-range floor of a GPU
+               front end; not a realistic FOA signal)."""
     rng = np.random.default_rng(seed)
     n = int(24000 * seconds)
+    t = np.arange(n) / 24000.0
     if kind == "noise":
         x = rng.standard_normal((n, 4)) * 3000.0
+    elif kind == "bursts":
+        x = rng.standard_normal((n, 4)) * 30.0
+        for _ in range(3):
+            f = rng.uniform(150, 9000)
+            t0 = rng.uniform(0, seconds * 0.5)
+            env = ((t > t0) & (t < t0 + 0.3 * seconds)).astype(np.float64)
+            s = env * rng.uniform(2000, 9000) * np.sin(2 * np.pi * f * t + rng.uniform(0, 6.28))
+            az, el = np.deg2rad(rng.uniform(-180, 180)), np.deg2rad(rng.uniform(-60, 60))
+            gains = np.array([1.0, np.sin(az) * np.cos(el), np.sin(el), np.cos(az) * np.cos(el)])
+            x += s[:, None] * gains[None, :]
+        s0 = int(n * 0.75)
+        x[s0:s0 + 12000] = 0.0  # digital silence
     else:
-        t = np.arange(n) / 24000.0
         x = np.zeros((n, 4))
         for c in range(4):
             for _ in range(3):
@@ -50,8 +69,6 @@ def synth_clip(seed: int, seconds: float, kind: str) -> np.ndarray:
                 env = ((t > t0) & (t < t0 + 0.25 * seconds)).astype(np.float64)
                 x[:, c] += env * rng.uniform(500, 12000) * np.sin(2 * np.pi * f * t + rng.uniform(0, 6.28))
         x += rng.standard_normal((n, 4)) * 2.0
-        s0 = int(n * 0.7)
-        x[s0:s0 + 12000] = 0.0  # digital silence
     return np.clip(np.round(x), -32768, 32767).astype(np.int16)
 
 
@@ -98,7 +115,7 @@ def main():
     params = ref_shims.ref_params(12)
     flp = ref_datasets.FeatureLabelProcessor(params)
     out = {}
-    for name, kind, secs, seed in (("noise", "noise", 2.0, 1), ("bursts", "bursts", 3.0, 2)):
+    for name, kind, secs, seed in (("noise", "noise", 2.0, 1), ("bursts", "bursts", 3.0, 2), ("harsh", "harsh", 1.5, 3)):
         clip = synth_clip(seed, secs, kind)
         audio = clip / 32768.0 + 1e-8                                   # datasets.py:147
         (MEL, IV), nlf = flp.get_feature(audio)                          # datasets.py:281-292

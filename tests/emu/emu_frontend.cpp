@@ -1,0 +1,103 @@
+// CPU emulation of frontend_foa_kernel (TEST INFRASTRUCTURE): runs the same per-thread
+// functions (frontend_core.cuh) thread by thread, phase by phase, over a fake shared memory,
+// so the index logic can be checked against the oracle without a GPU.
+#include <math.h>
+#include <string.h>
+#include <vector>
+#include <algorithm>
+#include "../../ad-yolo_b200/csrc/frontend_core.cuh"
+using namespace ady;
+
+extern "C" int emu_features_foa(const int16_t* audio, int B, long long N, const float* mel_dense /*64x601*/,
+                                const float* mean, const float* istd, float dc_offset, float top_db,
+                                float* out /*B,7,T,64*/) {
+  const int T = (int)(N / HOP);
+  const int tpc = (T + TF - 1) / TF;
+  std::vector<unsigned char> smem(SmemLayout::total, 0);
+  uint32_t* s_samples = (uint32_t*)(smem.data() + SmemLayout::off_samples);
+  float2* s_x1 = (float2*)(smem.data() + SmemLayout::off_x1);
+  float* s_win = (float*)(smem.data() + SmemLayout::off_win);
+  float* s_melw = (float*)(smem.data() + SmemLayout::off_melw);
+  int16_t* s_melidx = (int16_t*)(smem.data() + SmemLayout::off_melidx);
+  for (int n2 = 0; n2 < 25; ++n2) for (int n1 = 0; n1 < 48; ++n1) {
+    int n = pfa_in(n1, n2); double w = 0.5 - 0.5 * cos(2.0 * M_PI * n / NFFT);
+    s_win[n2 * WROW + n1] = (float)w * (1.0f / 65536.0f);
+  }
+  int off = 0;
+  for (int j = 0; j < NMEL; ++j) {
+    int first = -1, last = -1;
+    for (int k = 0; k < NBIN; ++k) if (mel_dense[j * NBIN + k] != 0.f) { if (first < 0) first = k; last = k; }
+    int len = last - first + 1;
+    if (off + len > MEL_MAXNNZ) return -1;
+    s_melidx[j] = first; s_melidx[NMEL + j] = len; s_melidx[2 * NMEL + j] = off;
+    for (int i = 0; i < len; ++i) s_melw[off + i] = mel_dense[j * NBIN + first + i];
+    off += len;
+  }
+  const float dc0 = dc_offset * 300.0f, dc1 = -dc_offset * 150.0f;
+  std::vector<float> gmax(B * 4, -INFINITY);
+  for (int tile = 0; tile < B * tpc; ++tile) {
+    const int b = tile / tpc, tb = tile % tpc, t0 = tb * TF, nf = std::min(TF, T - t0);
+    // ---- copy (same element mapping as issue_tile_copy)
+    for (int tid = 0; tid < NTHREADS; ++tid) {
+      const int pair = tid & 1, i0 = tid >> 1;
+      const int16_t* clip = audio + (long long)b * N * 4 + pair * 2;
+      for (int f = 0; f < nf; ++f) {
+        const int t = t0 + f;
+        uint32_t* dst = s_samples + (2 * f + pair) * SPLANE + skew(i0);
+        for (int i = 0; i < 15; ++i) {
+          const int idx = i0 + 80 * i;
+          long long m = t > 0 ? (long long)(t - 1) * HOP + idx : (idx < HOP ? HOP - idx : idx - HOP);
+          memcpy(dst + 85 * i, clip + m * 4, 4);
+        }
+      }
+    }
+    // ---- stage 1
+    for (int tid = 0; tid < 150; ++tid) { int g = tid / 25, n2 = tid % 25; if ((g >> 1) < nf) stage1_task(s_samples, s_win, s_x1, g, n2); }
+    // ---- stage 2a (all threads, then "barrier")
+    std::vector<Stage2Regs> R(NTHREADS);
+    for (int tid = 0; tid < NTHREADS; ++tid) { int L = std::min(tid, 149); stage2a_task(s_x1, L / 50, (L % 50) >> 1, L & 1, dc0, dc1, R[tid]); }
+    // ---- stage 2b: lane pairs exchange
+    for (int tid = 0; tid < NTHREADS; tid += 2) {
+      for (int k2 = 0; k2 < 25; ++k2) {
+        SlotMine m[2]; SlotOut o[2];
+        for (int s = 0; s < 2; ++s) { int L = std::min(tid + s, 149); int r = L & 1; slot_split(R[tid + s].P[k2], R[tid + s].Q[(25 - k2) % 25], r == 0 ? 1.0f : 1.0f / 3.0f, m[s], o[s]); }
+        for (int s = 0; s < 2; ++s) {
+          int L = std::min(tid + s, 149); int f2 = L / 50, t2 = (L % 50) >> 1, r2 = L & 1;
+          float iva, ivb; slot_finish(m[s], o[s], o[1 - s], r2, iva, ivb);
+          if (tid + s < 150 && f2 < nf) slot_store(s_x1 + f2 * VFRAME, slot_bin((625 * t2) % 1200, k2), r2, m[s].P0, m[s].P1, iva, ivb);
+        }
+      }
+    }
+    // ---- mel
+    for (int task = 0; task < TF * 2 * NMEL; ++task) {
+      const int f = task >> 7, half = (task >> 6) & 1, j = task & 63;
+      if (f >= nf) continue;
+      float acc[4];
+      mel_task((const float4*)(s_x1 + f * VFRAME), s_melw, s_melidx, half, j, acc);
+      const long long tt = t0 + f;
+      if (half == 0) {
+        for (int c = 0; c < 4; ++c) {
+          float db = power_to_db_unclamped(acc[c]);
+          gmax[b * 4 + c] = std::max(gmax[b * 4 + c], db);
+          float mu = mean ? mean[c * NMEL + j] : 0.f, is = istd ? istd[c * NMEL + j] : 1.f;
+          out[(((long long)b * 7 + c) * T + tt) * NMEL + j] = (db - mu) * is;
+        }
+      } else {
+        for (int c = 4; c < 7; ++c) {
+          float mu = mean ? mean[c * NMEL + j] : 0.f, is = istd ? istd[c * NMEL + j] : 1.f;
+          out[(((long long)b * 7 + c) * T + tt) * NMEL + j] = (acc[c - 3] - mu) * is;
+        }
+      }
+    }
+  }
+  // ---- top_db clamp
+  for (int b = 0; b < B; ++b) for (int c = 0; c < 4; ++c) {
+    float thr = gmax[b * 4 + c] - top_db;
+    for (int t = 0; t < T; ++t) for (int j = 0; j < NMEL; ++j) {
+      float mu = mean ? mean[c * NMEL + j] : 0.f, is = istd ? istd[c * NMEL + j] : 1.f;
+      float& o = out[(((long long)b * 7 + c) * T + t) * NMEL + j];
+      o = std::max(o, (thr - mu) * is);
+    }
+  }
+  return 0;
+}

@@ -1,0 +1,123 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol (no compute calls
+without a GPU), host helpers match the oracle, and the CPU emulation of the front-end kernel
+(same per-thread code as the CUDA kernel, built with g++) matches the oracle."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import features_np as F
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    import adyolo_b200
+    return adyolo_b200
+
+
+def test_library_exports_every_declared_symbol(built):
+    from adyolo_b200 import _lib
+    L = _lib.lib()
+    syms = _lib.declared_symbols()
+    assert len(syms) >= 15
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+    assert L.adyolo_version() >= 100
+    # every declared symbol has a ctypes signature on the Python side
+    assert not [s for s in syms if s not in _lib._SIGS]
+
+
+def test_sass_is_sm100a(built):
+    from adyolo_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_mel_filterbank_host_is_bitexact(built):
+    m = built.mel_filterbank(24000, 1200, 64)
+    assert np.array_equal(m, F.librosa_mel(24000, 1200, 64))
+    m2 = built.mel_filterbank(16000, 512, 40)
+    assert np.abs(m2 - F.librosa_mel(16000, 512, 40)).max() < 1e-9
+
+
+def test_unsupported_geometry_is_refused(built):
+    from adyolo_b200 import _lib
+    cfg = _lib.FrontendCfg(24000, 1024, 512, 1024, 64, 4, 1e-8, 80.0)
+    assert _lib.lib().adyolo_frontend_workspace_bytes(ctypes.byref(cfg), 1, 24000) == 0
+    assert b"1200" in _lib.lib().adyolo_last_error()
+
+
+def test_no_cpu_fallback(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        built.features_batched(torch.zeros((1, 24000, 4), dtype=torch.int16))
+    with pytest.raises(RuntimeError):
+        built.audio2stft(np.zeros((2400, 4)), 4, 1200, 600, 1200)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "ad-yolo_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, fn)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "/oracle/" not in txt, fn
+
+
+# ---------------------------------------------------------------- kernel logic on the CPU
+def _emu():
+    L = ctypes.CDLL(os.path.join(ROOT, "build", "emu_frontend.so"))
+    L.emu_features_foa.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
+                                   ctypes.c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_void_p]
+    return L
+
+
+@pytest.mark.parametrize("name,tol_iv", [("noise", 1e-3), ("bursts", 1e-3), ("harsh", 5e-3)])
+def test_emulated_kernel_matches_golden(built, gold, scaler2021, name, tol_iv):
+    g = gold("features_foa.npz")
+    clip = np.ascontiguousarray(g[f"{name}_audio"])
+    N = len(clip); T = N // 600
+    mel = built.mel_filterbank(24000, 1200, 64).copy()
+    mean = np.concatenate([scaler2021["MEL"]["mean"][0].T, scaler2021["IV"]["mean"][0].T], 0).astype(np.float32)
+    istd = (1.0 / np.concatenate([scaler2021["MEL"]["std"][0].T, scaler2021["IV"]["std"][0].T], 0)).astype(np.float32)
+    out = np.zeros((1, 7, T, 64), np.float32)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    assert _emu().emu_features_foa(vp(clip), 1, N, vp(mel), vp(mean), vp(istd), 1e-8, 80.0, vp(out)) == 0
+    ref = np.concatenate([g[f"{name}_MEL"].transpose(2, 0, 1), g[f"{name}_IV"].transpose(2, 0, 1)], 0)
+    assert (np.abs(out[0, :4] - ref[:4]) / np.maximum(np.abs(ref[:4]), 1.0)).max() < 1e-4
+    assert np.abs(out[0, 4:] - ref[4:]).max() < tol_iv
+
+
+def test_emulated_kernel_ragged_batch(built):
+    """T not a multiple of the 3-frame tile, several clips, raw (un-standardised) output."""
+    rng = np.random.default_rng(5)
+    B, N = 3, 600 * 7 + 123
+    clips = np.clip(rng.standard_normal((B, N, 4)) * 2000, -32768, 32767).astype(np.int16)
+    T = N // 600
+    mel = built.mel_filterbank(24000, 1200, 64).copy()
+    out = np.zeros((B, 7, T, 64), np.float32)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    assert _emu().emu_features_foa(vp(clips), B, N, vp(mel), None, None, 1e-8, 80.0, vp(out)) == 0
+    for b in range(B):
+        ref = F.features_foa_stack(clips[b])
+        assert ref.shape == (7, T, 64)
+        assert (np.abs(out[b, :4] - ref[:4]) / np.maximum(np.abs(ref[:4]), 1.0)).max() < 1e-4
+        assert np.abs(out[b, 4:] - ref[4:]).max() < 1e-6
+
+
+def test_codelets_against_numpy_fft(built):
+    L = ctypes.CDLL(os.path.join(ROOT, "build", "emu_codelets.so"))
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(1200) + 1j * rng.standard_normal(1200)
+    i = np.stack([x.real, x.imag], 1).astype(np.float32).copy()
+    o = np.zeros_like(i)
+    L.emu_fft1200(i.ctypes.data_as(ctypes.c_void_p), o.ctypes.data_as(ctypes.c_void_p))
+    ref = np.fft.fft(x)
+    assert np.abs((o[:, 0] + 1j * o[:, 1]) - ref).max() / np.abs(ref).max() < 1e-6

@@ -7,7 +7,7 @@ import torch
 from oracle import features_np as F
 
 
-@pytest.mark.parametrize("name", ["noise", "bursts"])
+@pytest.mark.parametrize("name", ["noise", "bursts", "harsh"])
 def test_oracle_matches_reference_golden(gold, scaler2021, name):
     g = gold("features_foa.npz")
     clip = g[f"{name}_audio"]
