@@ -201,4 +201,13 @@ int adyolo_loss(const float* logit, const float* target, int64_t M, int B, int T
                        (cudaStream_t)stream);
 }
 
+int adyolo_loss_backward(const float* logit, int B, int T, const adyolo_grid_cfg* cfg, const void* workspace,
+                         const float* grad_output, float* grad_out, void* stream) {
+    AssignCfg a;
+    int rc = make_cfgs(cfg, &a, nullptr);
+    if (rc) return rc;
+    if (!logit || !workspace || !grad_out) return set_error(ADY_ERR_INVALID, "loss_backward: NULL pointer");
+    return launch_loss_backward(logit, B, T, a, workspace, grad_output, grad_out, (cudaStream_t)stream);
+}
+
 }  // extern "C"

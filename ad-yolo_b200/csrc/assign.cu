@@ -101,7 +101,10 @@ assign_rows_kernel(const float* __restrict__ logit, const float* __restrict__ ta
                 if (a == 0 || Dd < dmin) { dmin = Dd; amin = a; }   // first minimum (torch.min)
                 // ---- backward of the chain (only needs ~1e-5): dD/d(xu), dD/d(xv)
                 const float pass = (dist >= cfg.clip_lo && dist <= cfg.clip_hi) ? 1.f : 0.f;
-                const float dD_ddist = -cfg.rad2deg * rsqrtf(fmaxf(1.f - cl * cl, 1e-30f)) * pass;
+                // acos backward as ATen evaluates it: grad * -rsqrt(-x*x + 1), two roundings (no FMA):
+                // 1 - x^2 cancels badly for small angles, so the op order matters at the 1e-5 level
+                const float om = __fadd_rn(1.f, -__fmul_rn(cl, cl));
+                const float dD_ddist = -cfg.rad2deg * rsqrtf(fmaxf(om, 1e-30f)) * pass;
                 const float sgn = du > 0.f ? 1.f : (du < 0.f ? -1.f : 0.f);
                 const float ddist_dou = -(cov * ctv) * sinf(adu) * sgn;
                 const float ddist_dov = cov * stv - sov * ctv * cdu;
@@ -173,7 +176,8 @@ constexpr int LA_WARPS = 4;
 __global__ void __launch_bounds__(LA_WARPS * 32)
 loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCfg cfg,
                    const unsigned long long* __restrict__ state, const float2* __restrict__ ang_grad,
-                   LossAccum* __restrict__ acc, float* __restrict__ grad) {
+                   LossAccum* __restrict__ acc, float* __restrict__ grad, const float* __restrict__ gscale,
+                   int do_sums) {
     extern __shared__ float sh[];
     const int CH = cfg.nb_classes + 3, C = cfg.nb_classes;
     const int stride = CH | 1;  // odd -> conflict-free per-thread rows
@@ -181,16 +185,17 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
     float* tile = sh + warp * 32 * stride;
 
     // per-threshold normalisers (counts are final: assign_rows_kernel has completed)
+    const double gs = gscale ? (double)gscale[0] : 1.0;   // upstream d(total)/d(loss), device scalar
     float w_pos[ADY_MAX_THR], w_neg[ADY_MAX_THR], w_cls[ADY_MAX_THR];
     for (int i = 0; i < ADY_MAX_THR; ++i) {
         const double np_ = i < cfg.n_thr ? (double)acc->n_pos[i] : 0.0;
         const double nn_ = (double)n_anchor - np_;
-        w_pos[i] = i < cfg.n_thr ? (float)(cfg.gain_obj / (cfg.n_thr * np_)) : 0.f;
-        w_neg[i] = i < cfg.n_thr ? (float)(cfg.gain_nonobj / (cfg.n_thr * nn_)) : 0.f;
-        w_cls[i] = i < cfg.n_thr ? (float)(cfg.gain_cls / (cfg.n_thr * np_ * C)) : 0.f;
+        w_pos[i] = i < cfg.n_thr ? (float)(gs * cfg.gain_obj / (cfg.n_thr * np_)) : 0.f;
+        w_neg[i] = i < cfg.n_thr ? (float)(gs * cfg.gain_nonobj / (cfg.n_thr * nn_)) : 0.f;
+        w_cls[i] = i < cfg.n_thr ? (float)(gs * cfg.gain_cls / (cfg.n_thr * np_ * C)) : 0.f;
     }
     const double n_ang = (double)acc->ang_cnt;
-    const float w_ang = (float)(cfg.gain_ang / (180.0 * n_ang));
+    const float w_ang = (float)(gs * cfg.gain_ang / (180.0 * n_ang));
 
     double s_pos[ADY_MAX_THR] = {0, 0, 0, 0}, s_neg[ADY_MAX_THR] = {0, 0, 0, 0}, s_cls[ADY_MAX_THR] = {0, 0, 0, 0};
 
@@ -257,7 +262,7 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
             s_neg[i] += __shfl_xor_sync(0xffffffffu, s_neg[i], o);
             s_cls[i] += __shfl_xor_sync(0xffffffffu, s_cls[i], o);
         }
-    if (lane == 0)
+    if (lane == 0 && do_sums)
         for (int i = 0; i < cfg.n_thr; ++i) {
             atomicAdd(&acc->s_pos[i], s_pos[i]);
             atomicAdd(&acc->s_neg[i], s_neg[i]);
@@ -329,10 +334,37 @@ int launch_loss(const float* logit, const float* target, long long M, int B, int
     long long blocks = (n_groups + LA_WARPS - 1) / LA_WARPS;
     const long long cap = (long long)sms * 16;
     if (blocks > cap) blocks = cap;
-    loss_anchor_kernel<<<(int)blocks, LA_WARPS * 32, shmem, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out);
+    loss_anchor_kernel<<<(int)blocks, LA_WARPS * 32, shmem, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out,
+                                                                      nullptr, 1);
     ADY_LAUNCH_CHECK("loss_anchor_kernel");
     loss_finalize_kernel<<<1, 32, 0, stream>>>(n_anchor, cfg, acc, loss_out);
     ADY_LAUNCH_CHECK("loss_finalize_kernel");
+    return ADY_OK;
+}
+
+// Backward from the workspace a forward call left behind (label bits, counts, angular partials):
+// grad_out = grad_output[0] * d loss / d logit, one pass over the logits.
+int launch_loss_backward(const float* logit, int B, int T, const AssignCfg& cfg, const void* ws,
+                         const float* grad_output, float* grad_out, cudaStream_t stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    const long long n_anchor = (long long)B * T * cfg.ga * cfg.ge * cfg.nb_anchors;
+    if (n_anchor <= 0) return set_error(ADY_ERR_INVALID, "adyolo_loss_backward: empty logit");
+    LossAccum* acc = const_cast<LossAccum*>(reinterpret_cast<const LossAccum*>(ws));
+    const unsigned long long* state = reinterpret_cast<const unsigned long long*>(acc + 1);
+    const float2* ang = reinterpret_cast<const float2*>(state + n_anchor);
+    int dev = 0, sms = 0;
+    ADY_CUDA_CHECK(cudaGetDevice(&dev));
+    ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int stride = (cfg.nb_classes + 3) | 1;
+    const size_t shmem = (size_t)LA_WARPS * 32 * stride * sizeof(float);
+    const long long n_groups = (n_anchor + 31) / 32;
+    long long blocks = (n_groups + LA_WARPS - 1) / LA_WARPS;
+    const long long cap = (long long)sms * 16;
+    if (blocks > cap) blocks = cap;
+    loss_anchor_kernel<<<(int)blocks, LA_WARPS * 32, shmem, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out,
+                                                                      grad_output, 0);
+    ADY_LAUNCH_CHECK("loss_anchor_kernel(backward)");
     return ADY_OK;
 }
 

@@ -40,6 +40,9 @@ int launch_loss(const float* logit, const float* target, long long M, int B, int
                 float* loss_out, float* grad_out, float* D, uint8_t* mask, int32_t* argmin, void* ws,
                 cudaStream_t stream);
 
+int launch_loss_backward(const float* logit, int B, int T, const AssignCfg& cfg, const void* ws,
+                         const float* grad_output, float* grad_out, cudaStream_t stream);
+
 // grid-cell responsibility (datasets.py:457-482): events -> 32-bit cell mask + count, rows
 struct CellCfg {
     int ga, ge;

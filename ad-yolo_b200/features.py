@@ -66,12 +66,15 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 
 def features_batched(audio_i16: torch.Tensor, scaler_dev=None, out: torch.Tensor | None = None,
                      apply_topdb: bool = True, cfg: FrontendCfg | None = None,
-                     check_nan: bool = False) -> torch.Tensor:
+                     check_nan: bool = False, timing_events: list | None = None) -> torch.Tensor:
     """int16 PCM (B, N, 4) on a CUDA device -> features (B, 7, T, 64) float32 on the same device.
 
     Equivalent to, per clip: ``audio/32768.0 + 1e-8`` -> ``FeatureLabelProcessor.get_feature`` ->
     ``permute(2,0,1)`` + ``cat`` (datasets.py:147-160) without augmentation.  ``scaler_dev`` is the
     ``(mean, inv_std)`` pair from ``FeatureLabelProcessor.scaler_device`` or None (raw dB / IV).
+    ``timing_events``: when a list is given, a (start, end) pair of CUDA events bracketing the fused
+    front-end kernel alone is appended (bench.py's roofline measurement); the top_db pass is then
+    issued through ``adyolo_features_foa_clamp``.
     """
     require_cuda(audio_i16, "features_batched")
     if audio_i16.dtype != torch.int16 or audio_i16.dim() != 3 or audio_i16.shape[-1] != 4:
@@ -89,8 +92,19 @@ def features_batched(audio_i16: torch.Tensor, scaler_dev=None, out: torch.Tensor
         nbytes = L.adyolo_frontend_workspace_bytes(C.byref(cfg), B, N)
         ws = _workspace(nbytes, audio_i16.device)
         mean, istd = scaler_dev if scaler_dev is not None else (None, None)
-        check(L.adyolo_features_foa(ptr(audio_i16), B, N, C.byref(cfg), ptr(mean), ptr(istd), ptr(out), ptr(ws),
-                                    1 if apply_topdb else 0, stream_ptr()), "adyolo_features_foa")
+        if timing_events is None:
+            check(L.adyolo_features_foa(ptr(audio_i16), B, N, C.byref(cfg), ptr(mean), ptr(istd), ptr(out), ptr(ws),
+                                        1 if apply_topdb else 0, stream_ptr()), "adyolo_features_foa")
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            check(L.adyolo_features_foa(ptr(audio_i16), B, N, C.byref(cfg), ptr(mean), ptr(istd), ptr(out), ptr(ws),
+                                        0, stream_ptr()), "adyolo_features_foa")
+            e1.record()
+            timing_events.append((e0, e1))
+            if apply_topdb:
+                check(L.adyolo_features_foa_clamp(ptr(out), B, N, C.byref(cfg), ptr(mean), ptr(istd), ptr(ws),
+                                                  stream_ptr()), "adyolo_features_foa_clamp")
         if check_nan and int(ws[:4].view(torch.int32).item()) & 1:
             raise FloatingPointError("Feature extraction is generating nan outputs")  # datasets.py:277
     return out

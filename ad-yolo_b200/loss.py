@@ -59,17 +59,25 @@ class _ADYOLOFn(torch.autograd.Function):
         need_grad = logit.requires_grad
         with torch.cuda.device(logit.device):
             loss = torch.empty(1, dtype=torch.float32, device=logit.device)
-            grad = torch.empty_like(logit) if need_grad else None
-            ws = _workspace(L.adyolo_loss_workspace_bytes(B, T, C.byref(grid.c)), logit.device)
-            check(L.adyolo_loss(ptr(logit), ptr(target), M, B, T, C.byref(grid.c), ptr(loss), ptr(grad), None, None,
+            nbytes = L.adyolo_loss_workspace_bytes(B, T, C.byref(grid.c))
+            # the workspace carries label bits / counts to backward: private per call when needed
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=logit.device) if need_grad else _workspace(nbytes, logit.device)
+            check(L.adyolo_loss(ptr(logit), ptr(target), M, B, T, C.byref(grid.c), ptr(loss), None, None, None,
                                 None, ptr(ws), stream_ptr()), "adyolo_loss")
-        ctx.save_for_backward(grad)
+        ctx.grid = grid
+        ctx.save_for_backward(logit, ws)
         return loss
 
     @staticmethod
     def backward(ctx, gout):
-        (grad,) = ctx.saved_tensors
-        return (grad * gout.reshape(1, 1, 1) if grad is not None else None), None, None
+        logit, ws = ctx.saved_tensors
+        B, T, _ = logit.shape
+        gout = gout.to(torch.float32).contiguous()
+        with torch.cuda.device(logit.device):
+            grad = torch.empty_like(logit)
+            check(_lib.lib().adyolo_loss_backward(ptr(logit), B, T, C.byref(ctx.grid.c), ptr(ws), ptr(gout), ptr(grad),
+                                                  stream_ptr()), "adyolo_loss_backward")
+        return grad, None, None
 
 
 class ADYOLOloss(object):

@@ -132,13 +132,21 @@ int adyolo_label_rows(const double* events, int64_t E, const adyolo_grid_cfg* cf
 int adyolo_assign(const float* logit, const float* target, int64_t M, int B, int T,
                   const adyolo_grid_cfg* cfg, float* D, uint8_t* mask, int32_t* argmin, void* stream);
 
-/* ADYOLOloss.__call__ (loss.py:189-251) forward AND d loss / d logit in one pass.
- *   loss_out device float32[1];  grad_out device float32 like logit or NULL (forward only)
- *   stats_out optional device pointer to 16 doubles (see adyolo_loss_stats_layout in DESIGN.md) */
+/* ADYOLOloss.__call__ (loss.py:189-251).
+ *   loss_out device float32[1]
+ *   grad_out device float32 like logit: d loss / d logit written in the same pass (upstream
+ *            gradient 1), or NULL for forward only — then adyolo_loss_backward produces
+ *            grad_output[0] * d loss / d logit later from the same `workspace` (which keeps the
+ *            label bits, counts and angular partials of the forward call; do not reuse it in
+ *            between).  D / mask / argmin as in adyolo_assign, may be NULL.                     */
 size_t adyolo_loss_workspace_bytes(int B, int T, const adyolo_grid_cfg* cfg);
 int adyolo_loss(const float* logit, const float* target, int64_t M, int B, int T,
                 const adyolo_grid_cfg* cfg, float* loss_out, float* grad_out, float* D, uint8_t* mask,
                 int32_t* argmin, void* workspace, void* stream);
+
+int adyolo_loss_backward(const float* logit, int B, int T, const adyolo_grid_cfg* cfg, const void* workspace,
+                         const float* grad_output /* device float32[1] or NULL (= 1) */, float* grad_out,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,199 @@
+"""GPU parity of the AD-YOLO label assignment and loss.
+
+Bit-exact gates (integer results):
+  * grid cells / target rows  vs the numpy restatement of get_yolo_label + collate_fn
+  * D, the three responsibility masks and argmin vs the torch oracle executed ON THE SAME GPU
+    (the reference's own eager op sequence) for every entry
+Float gates: loss value and d loss / d logit vs the reference run on the CPU (golden) <= 1e-5 rel.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import assign_np
+from oracle.loss_torch import ADYOLOlossOracle, default_params
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def A():
+    import __graft_entry__ as g
+    g.build()
+    import adyolo_b200
+    assert torch.cuda.is_available()
+    return adyolo_b200
+
+
+def _grid(A, C=12):
+    return A.labels.GridSpec(C, 5, [45, 45], 0.5)
+
+
+def _events(rng, B, T, C, max_ev=3, p_special=0.3, same_class=False):
+    special_el = np.array([90, -90, 65, -65, 45, -45, 80, -80, 67, -68, 0, 22, -23], np.float64)
+    special_az = np.array([180, -180, 179, -179, 0, 135, -135, 157, -158], np.float64)
+    n = rng.integers(0, max_ev + 1, size=(B, T))
+    b, t = np.nonzero(n)
+    reps = n[b, t]
+    b, t = np.repeat(b, reps), np.repeat(t, reps)
+    E = len(b)
+    same = rng.integers(0, C, size=(B, T))[b, t]
+    cls = same if same_class else np.where(rng.random(E) < 0.5, same, rng.integers(0, C, size=E))
+    az = np.where(rng.random(E) < p_special, rng.choice(special_az, E), rng.integers(-180, 181, E).astype(np.float64))
+    el = np.where(rng.random(E) < p_special, rng.choice(special_el, E), rng.integers(-90, 91, E).astype(np.float64))
+    return np.stack([b, t, cls, az, el], 1).astype(np.float64)
+
+
+def test_cells_golden_sweep_and_dict_api(A, gold):
+    g = gold("assign_cells.npz")
+    grid = _grid(A)
+    az, el = g["sweep_az"], g["sweep_el"]
+    ev = np.stack([np.zeros_like(az), np.zeros_like(az), np.zeros_like(az), az, el], 1)
+    rows, cm = A.label_rows_batched(torch.from_numpy(ev).cuda(), 1, grid, return_cellmask=True)
+    assert np.array_equal(cm.cpu().numpy().astype(np.uint32), g["sweep_mask"])
+    assert np.array_equal(rows.cpu().numpy(), assign_np.events_to_rows(ev, 1).astype(np.float32))
+    # dict API (reference signature) against the reference's own output
+    lab = {}
+    for f, e in zip(g["label_frames"], g["label_events"]):
+        lab.setdefault(int(f), []).append([int(e[0]), int(e[1]), float(e[2]), float(e[3])])
+    import copy
+    lab0 = copy.deepcopy(lab)
+    got = A.get_yolo_label(lab, int(g["nlf"]), grid)
+    assert lab == lab0                                     # caller's dict is not mutated
+    assert np.array_equal(np.asarray(got, np.float64), g["rows"])
+    lab2 = {}
+    for f, e in zip(g["label2_frames"], g["label2_events"]):
+        lab2.setdefault(int(f), []).append([int(e[0]), int(e[1]), float(e[2]), float(e[3])])
+    feat = torch.zeros(1)
+    _, tgt = A.collate_fn([(feat, got), (feat, []), (feat, A.get_yolo_label(lab2, int(g["nlf"]), grid))])
+    assert np.array_equal(tgt.numpy(), g["collate_target"])
+    assert A.get_yolo_label({}, 10, grid) == []
+    with pytest.raises((RuntimeError, ValueError)):
+        A.collate_fn([(feat, []), (feat, [])])           # reference: torch.cat of an empty list raises
+
+
+@pytest.mark.parametrize("C", [12, 13, 14])
+def test_assign_bitexact_vs_torch_on_gpu(A, C):
+    rng = np.random.default_rng(100 + C)
+    B, T = 64, 50
+    grid = _grid(A, C)
+    ev = _events(rng, B, T, C)
+    rows = A.label_rows_batched(torch.from_numpy(ev).cuda(), T, grid)
+    assert np.array_equal(rows.cpu().numpy(), assign_np.events_to_rows(ev, T).astype(np.float32))
+    gen = torch.Generator(device="cuda").manual_seed(C)
+    for scale in (1.0, 3.0, 0.1):
+        logit = torch.randn((B, T, 160 * (C + 3)), device="cuda", generator=gen) * scale
+        D, masks, amin = A.adyolo_assign(logit, rows, grid)
+        orc = ADYOLOlossOracle(default_params(C, "cuda:0"))
+        Dr, mr, ar = orc.assign(logit, rows)
+        assert torch.equal(D, Dr), (D - Dr).abs().max()
+        assert torch.equal(masks, mr)
+        assert torch.equal(amin, ar)
+
+
+def test_assign_vs_reference_cpu_golden(A, gold):
+    """Against the unmodified reference on the CPU: D within 2 ulp-ish, masks identical except
+    entries whose D sits within 1e-5 deg of a threshold (CPU SLEEF vs CUDA libdevice)."""
+    g = gold("loss_ref.npz")
+    for C in (12, 13, 14):
+        logit = torch.from_numpy(g[f"C{C}_logit"]).cuda()
+        target = torch.from_numpy(g[f"C{C}_target"]).cuda()
+        D, masks, amin = A.adyolo_assign(logit, target, _grid(A, C))
+        Dref = torch.from_numpy(g[f"C{C}_D"]).cuda()
+        assert (D - Dref).abs().max().item() < 2e-4
+        for i, thr in enumerate((45.0, 25.0, 10.0)):
+            mref = Dref < thr
+            mref[torch.arange(len(Dref)), Dref.argmin(1)] = True
+            rows_bad, _ = torch.nonzero(masks[i] != mref, as_tuple=True)
+            for m in rows_bad.tolist():                       # only threshold / argmin near-ties may differ
+                two = Dref[m].sort()[0][:2]
+                assert ((Dref[m] - thr).abs() < 1e-4).any() or (two[1] - two[0]).abs() < 1e-4
+
+
+@pytest.mark.parametrize("C", [12, 13, 14])
+def test_loss_and_grad_vs_reference_golden_inputs(A, gold, C):
+    """On the reference-generated golden inputs.
+    (a) vs the torch oracle on the same GPU (the declared authority): <= 1e-5.
+    (b) vs the unmodified reference run on the CPU: <= 1e-5 when the CPU and GPU masks agree; the
+        CPU (SLEEF) and CUDA (libdevice) sin/cos/acos differ in the last ulp, so a D that lands
+        exactly on 45/25/10 can flip a mask bit between the two devices - then the
+        loss legitimately differs at the 1e-3 level (one anchor more or less among ~10^2)."""
+    g = gold("loss_ref.npz")
+    logit = torch.from_numpy(g[f"C{C}_logit"]).cuda().requires_grad_(True)
+    target = torch.from_numpy(g[f"C{C}_target"])
+    crit = A.WrapperCriterion(default_params(C, "cuda:0"))
+    loss = crit(logit, target)
+    assert loss.shape == (1,)
+    (loss * 2.0).backward()                                    # non-unit upstream gradient
+    l2 = logit.detach().clone().requires_grad_(True)
+    ref = ADYOLOlossOracle(default_params(C, "cuda:0"))(l2, target)
+    (ref * 2.0).backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert (logit.grad - l2.grad).abs().max().item() <= 1e-5 * l2.grad.abs().max().item()
+    assert ((logit.grad - l2.grad).norm() / l2.grad.norm()).item() < 1e-5
+    # (b) CPU reference
+    ref_loss, ref_grad = float(g[f"C{C}_loss"][0]), torch.from_numpy(g[f"C{C}_grad"]).cuda() * 2.0
+    D, masks, amin = A.adyolo_assign(logit, target.cuda(), _grid(A, C))
+    Dref = torch.from_numpy(g[f"C{C}_D"]).cuda()
+    flips = 0
+    for i, thr in enumerate((45.0, 25.0, 10.0)):
+        mref = Dref < thr
+        mref[torch.arange(len(Dref)), Dref.argmin(1)] = True
+        flips += int((masks[i] != mref).sum())
+    tol = 1e-5 if flips == 0 else 5e-3
+    assert abs(loss.item() - ref_loss) <= tol * abs(ref_loss), (flips, loss.item(), ref_loss)
+    assert ((logit.grad - ref_grad).norm() / ref_grad.norm()).item() < (1e-5 if flips == 0 else 5e-2), flips
+
+
+def test_loss_vs_torch_oracle_on_gpu_config2_shape(A):
+    """BASELINE config 2 loss shape: B=256, T=50, C=12."""
+    C, B, T = 12, 256, 50
+    rng = np.random.default_rng(9)
+    grid = _grid(A, C)
+    rows = A.label_rows_batched(torch.from_numpy(_events(rng, B, T, C)).cuda(), T, grid)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    logit = torch.randn((B, T, 2400), device="cuda", generator=gen).requires_grad_(True)
+    loss = A.ADYOLOloss(default_params(C, "cuda:0"))(logit, rows)
+    loss.backward()
+    l2 = logit.detach().clone().requires_grad_(True)
+    ref = ADYOLOlossOracle(default_params(C, "cuda:0"))(l2, rows)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert (logit.grad - l2.grad).abs().max().item() <= 2e-5 * l2.grad.abs().max().item()
+    assert ((logit.grad - l2.grad).norm() / l2.grad.norm()).item() < 1e-5
+
+
+def test_loss_nan_without_targets_and_bad_shapes(A):
+    crit = A.ADYOLOloss(default_params(12, "cuda:0"))
+    out = crit(torch.zeros(1, 2, 2400, device="cuda"), torch.zeros(0, 7))
+    assert out.shape == (1,) and torch.isnan(out).all()           # reference returns tensor([nan])
+    with pytest.raises(ValueError):
+        crit(torch.zeros(1, 2, 2399, device="cuda"), torch.zeros(1, 7))
+    with pytest.raises(NotImplementedError):
+        p = default_params(12, "cuda:0"); p["args"]["loss"] = "adpit"
+        A.WrapperCriterion(p)
+
+
+@pytest.mark.parametrize("C", [12, 13])
+def test_stress_one_million_frames_bitexact(A, C):
+    """BASELINE config 5: 10^6 label frames, up to 3 same-class overlapping events per frame,
+    logits ~ N(0,1); cells, argmin and all three masks identical to the oracle for every entry.
+    Processed in 10 chunks of 10^5 frames to bound the torch oracle's temporaries."""
+    rng = np.random.default_rng(C)
+    grid = _grid(A, C)
+    orc = ADYOLOlossOracle(default_params(C, "cuda:0"))
+    gen = torch.Generator(device="cuda").manual_seed(1000 + C)
+    B, T = 2000, 50
+    total_rows = 0
+    for chunk in range(10):
+        ev = _events(rng, B, T, C, same_class=True)
+        rows, cm = A.label_rows_batched(torch.from_numpy(ev).cuda(), T, grid, return_cellmask=True)
+        want = assign_np.events_to_rows(ev, T).astype(np.float32)
+        assert np.array_equal(rows.cpu().numpy(), want)
+        logit = torch.randn((B, T, 160 * (C + 3)), device="cuda", generator=gen)
+        D, masks, amin = A.adyolo_assign(logit, rows, grid)
+        Dr, mr, ar = orc.assign(logit, rows)
+        assert torch.equal(D, Dr) and torch.equal(masks, mr) and torch.equal(amin, ar)
+        total_rows += len(rows)
+        del logit, D, Dr, masks, mr
+    assert total_rows > 3_000_000
