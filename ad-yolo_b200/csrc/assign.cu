@@ -15,7 +15,7 @@
 // Three launches per call, no host synchronisation:
 //   assign_rows_kernel  : 1 thread / target row  -> D, masks, argmin; atomicOr label bits into a
 //                         per-anchor 64-bit state word; unnormalised angular gradients
-//   loss_anchor_kernel  : 1 thread / anchor (warp-staged, coalesced) -> BCE sums + d loss/d logit
+//   loss_anchor_kernel  : element-wise float4 pass over the logits -> BCE sums and/or d loss/d logit
 //   loss_finalize_kernel: scalar loss
 #include "assign_host.h"
 #include "common.cuh"
@@ -171,18 +171,20 @@ __device__ __forceinline__ float bce_bwd_logit(float p, float t) {
     return (p - t) / fmaxf(q, 1e-12f) * q;
 }
 
-constexpr int LA_WARPS = 4;
+constexpr int LA_THREADS = 256;
+constexpr int LA_TILE = 256;   // anchors per tile (tile base is 16-byte aligned for any channel count)
 
-__global__ void __launch_bounds__(LA_WARPS * 32)
+// One pass over the logits in memory order (float4, fully coalesced).  Thread = 4 consecutive
+// elements; the anchor's 64-bit label word is re-read (L1 hit) when the element run crosses
+// into the next anchor.  do_sums: accumulate the BCE sums (forward); grad != NULL: write
+// gscale * d loss / d logit (backward, or fused forward+backward with gscale = NULL -> 1).
+__global__ void __launch_bounds__(LA_THREADS)
 loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCfg cfg,
                    const unsigned long long* __restrict__ state, const float2* __restrict__ ang_grad,
                    LossAccum* __restrict__ acc, float* __restrict__ grad, const float* __restrict__ gscale,
                    int do_sums) {
-    extern __shared__ float sh[];
-    const int CH = cfg.nb_classes + 3, C = cfg.nb_classes;
-    const int stride = CH | 1;  // odd -> conflict-free per-thread rows
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* tile = sh + warp * 32 * stride;
+    const unsigned CH = cfg.nb_classes + 3, C = cfg.nb_classes;
+    const int lane = threadIdx.x & 31;
 
     // per-threshold normalisers (counts are final: assign_rows_kernel has completed)
     const double gs = gscale ? (double)gscale[0] : 1.0;   // upstream d(total)/d(loss), device scalar
@@ -196,64 +198,84 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
     }
     const double n_ang = (double)acc->ang_cnt;
     const float w_ang = (float)(gs * cfg.gain_ang / (180.0 * n_ang));
+    const unsigned long long OBJ_ANY = 0x0001000100010001ull;
 
     double s_pos[ADY_MAX_THR] = {0, 0, 0, 0}, s_neg[ADY_MAX_THR] = {0, 0, 0, 0}, s_cls[ADY_MAX_THR] = {0, 0, 0, 0};
 
-    const long long n_groups = (n_anchor + 31) / 32;
-    for (long long grp = (long long)blockIdx.x * LA_WARPS + warp; grp < n_groups; grp += (long long)gridDim.x * LA_WARPS) {
-        const long long a0 = grp * 32;
-        const int na = (int)min(32LL, n_anchor - a0);
-        const float* src = logit + a0 * CH;
-        for (int i = lane; i < na * CH; i += 32) tile[(i / CH) * stride + (i % CH)] = src[i];
-        __syncwarp();
-        if (lane < na) {
-            float* row = tile + lane * stride;
-            const unsigned long long st = state[a0 + lane];
-            const float p = sigmoid_torch(row[0]);
-            const float l_pos = bce_fwd(p, 1.f), l_neg = bce_fwd(p, 0.f);
-            const float g_pos = bce_bwd_logit(p, 1.f), g_neg = bce_bwd_logit(p, 0.f);
-            float g_obj = 0.f;
-            bool any = false;
-#pragma unroll
-            for (int i = 0; i < ADY_MAX_THR; ++i) {
-                if (i >= cfg.n_thr) break;
-                const bool pos = (st >> (16 * i)) & 1ull;
-                any |= pos;
-                if (pos) { s_pos[i] += l_pos; g_obj += w_pos[i] * g_pos; }
-                else     { s_neg[i] += l_neg; g_obj += w_neg[i] * g_neg; }
-            }
-            row[0] = g_obj;
-            if (any) {
-                for (int c = 0; c < C; ++c) {
-                    const float pc = sigmoid_torch(row[1 + c]);
-                    const float l1 = bce_fwd(pc, 1.f), l0 = bce_fwd(pc, 0.f);
-                    const float g1 = bce_bwd_logit(pc, 1.f), g0 = bce_bwd_logit(pc, 0.f);
-                    float gc = 0.f;
-#pragma unroll
-                    for (int i = 0; i < ADY_MAX_THR; ++i) {
-                        if (i >= cfg.n_thr) break;
-                        if ((st >> (16 * i)) & 1ull) {
-                            const bool t = (st >> (16 * i + 1 + c)) & 1ull;
-                            s_cls[i] += t ? l1 : l0;
-                            gc += w_cls[i] * (t ? g1 : g0);
-                        }
-                    }
-                    row[1 + c] = gc;
-                }
+    const long long n_tiles = (n_anchor + LA_TILE - 1) / LA_TILE;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long a_base = tile * LA_TILE;
+        const unsigned na = (unsigned)min((long long)LA_TILE, n_anchor - a_base);
+        const unsigned nel = na * CH;
+        const float* src = logit + a_base * CH;
+        float* dst = grad ? grad + a_base * CH : nullptr;
+        for (unsigned el = threadIdx.x * 4; el < nel; el += LA_THREADS * 4) {
+            float x[4], g[4] = {0.f, 0.f, 0.f, 0.f};
+            const bool full = el + 4 <= nel;
+            if (full) {
+                const float4 v = *reinterpret_cast<const float4*>(src + el);
+                x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
             } else {
-                for (int c = 0; c < C; ++c) row[1 + c] = 0.f;
+#pragma unroll
+                for (unsigned q = 0; q < 4; ++q) x[q] = el + q < nel ? src[el + q] : 0.f;
             }
-            const float2 ag = ang_grad[a0 + lane];
-            row[C + 1] = ag.x * w_ang;
-            row[C + 2] = ag.y * w_ang;
+            unsigned a = el / CH, ch = el - a * CH;
+            unsigned long long st = state[a_base + a];
+#pragma unroll
+            for (unsigned q = 0; q < 4; ++q) {
+                if (el + q < nel) {
+                    if (ch == 0) {
+                        const float p = sigmoid_torch(x[q]);
+                        const float g_pos = bce_bwd_logit(p, 1.f), g_neg = bce_bwd_logit(p, 0.f);
+                        float l_pos = 0.f, l_neg = 0.f;
+                        if (do_sums) { l_pos = bce_fwd(p, 1.f); l_neg = bce_fwd(p, 0.f); }
+                        float go = 0.f;
+#pragma unroll
+                        for (int i = 0; i < ADY_MAX_THR; ++i) {
+                            if (i >= cfg.n_thr) break;
+                            if ((st >> (16 * i)) & 1ull) { s_pos[i] += l_pos; go += w_pos[i] * g_pos; }
+                            else                         { s_neg[i] += l_neg; go += w_neg[i] * g_neg; }
+                        }
+                        g[q] = go;
+                    } else if (ch <= C) {
+                        if (st & OBJ_ANY) {
+                            const float pc = sigmoid_torch(x[q]);
+                            const float g1 = bce_bwd_logit(pc, 1.f), g0 = bce_bwd_logit(pc, 0.f);
+                            float l1 = 0.f, l0 = 0.f;
+                            if (do_sums) { l1 = bce_fwd(pc, 1.f); l0 = bce_fwd(pc, 0.f); }
+                            float gc = 0.f;
+#pragma unroll
+                            for (int i = 0; i < ADY_MAX_THR; ++i) {
+                                if (i >= cfg.n_thr) break;
+                                if ((st >> (16 * i)) & 1ull) {
+                                    const bool t = (st >> (16 * i + ch)) & 1ull;   // class c = ch-1 sits at bit 1+c
+                                    s_cls[i] += t ? l1 : l0;
+                                    gc += w_cls[i] * (t ? g1 : g0);
+                                }
+                            }
+                            g[q] = gc;
+                        }
+                    } else if (dst) {
+                        const float2 ag = ang_grad[a_base + a];
+                        g[q] = (ch == C + 1 ? ag.x : ag.y) * w_ang;
+                    }
+                }
+                if (++ch == CH) {
+                    ch = 0;
+                    ++a;
+                    if (a < na) st = state[a_base + a];
+                }
+            }
+            if (dst) {
+                if (full) *reinterpret_cast<float4*>(dst + el) = make_float4(g[0], g[1], g[2], g[3]);
+                else {
+#pragma unroll
+                    for (unsigned q = 0; q < 4; ++q) if (el + q < nel) dst[el + q] = g[q];
+                }
+            }
         }
-        __syncwarp();
-        if (grad) {
-            float* dst = grad + a0 * CH;
-            for (int i = lane; i < na * CH; i += 32) dst[i] = tile[(i / CH) * stride + (i % CH)];
-        }
-        __syncwarp();
     }
+    if (!do_sums) return;
 #pragma unroll
     for (int o = 16; o; o >>= 1)
 #pragma unroll
@@ -262,7 +284,7 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
             s_neg[i] += __shfl_xor_sync(0xffffffffu, s_neg[i], o);
             s_cls[i] += __shfl_xor_sync(0xffffffffu, s_cls[i], o);
         }
-    if (lane == 0 && do_sums)
+    if (lane == 0)
         for (int i = 0; i < cfg.n_thr; ++i) {
             atomicAdd(&acc->s_pos[i], s_pos[i]);
             atomicAdd(&acc->s_neg[i], s_neg[i]);
@@ -328,14 +350,11 @@ int launch_loss(const float* logit, const float* target, long long M, int B, int
     int dev = 0, sms = 0;
     ADY_CUDA_CHECK(cudaGetDevice(&dev));
     ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int stride = (cfg.nb_classes + 3) | 1;
-    const size_t shmem = (size_t)LA_WARPS * 32 * stride * sizeof(float);
-    const long long n_groups = (n_anchor + 31) / 32;
-    long long blocks = (n_groups + LA_WARPS - 1) / LA_WARPS;
-    const long long cap = (long long)sms * 16;
+    long long blocks = (n_anchor + LA_TILE - 1) / LA_TILE;
+    const long long cap = (long long)sms * 8;
     if (blocks > cap) blocks = cap;
-    loss_anchor_kernel<<<(int)blocks, LA_WARPS * 32, shmem, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out,
-                                                                      nullptr, 1);
+    loss_anchor_kernel<<<(int)blocks, LA_THREADS, 0, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out,
+                                                               nullptr, 1);
     ADY_LAUNCH_CHECK("loss_anchor_kernel");
     loss_finalize_kernel<<<1, 32, 0, stream>>>(n_anchor, cfg, acc, loss_out);
     ADY_LAUNCH_CHECK("loss_finalize_kernel");
@@ -356,14 +375,11 @@ int launch_loss_backward(const float* logit, int B, int T, const AssignCfg& cfg,
     int dev = 0, sms = 0;
     ADY_CUDA_CHECK(cudaGetDevice(&dev));
     ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int stride = (cfg.nb_classes + 3) | 1;
-    const size_t shmem = (size_t)LA_WARPS * 32 * stride * sizeof(float);
-    const long long n_groups = (n_anchor + 31) / 32;
-    long long blocks = (n_groups + LA_WARPS - 1) / LA_WARPS;
-    const long long cap = (long long)sms * 16;
+    long long blocks = (n_anchor + LA_TILE - 1) / LA_TILE;
+    const long long cap = (long long)sms * 8;
     if (blocks > cap) blocks = cap;
-    loss_anchor_kernel<<<(int)blocks, LA_WARPS * 32, shmem, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out,
-                                                                      grad_output, 0);
+    loss_anchor_kernel<<<(int)blocks, LA_THREADS, 0, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out,
+                                                               grad_output, 0);
     ADY_LAUNCH_CHECK("loss_anchor_kernel(backward)");
     return ADY_OK;
 }

@@ -10,8 +10,8 @@
 //   stage 1 (25 x DFT-48 / packed FFT) -> smem exchange -> stage 2 (DFT-25 pairs, channel split,
 //   |X|^2, IV) -> smem V -> sparse mel, log10, standardise -> global (B,7,T,64) f32
 // The per-(clip,channel) global max needed by librosa.power_to_db(top_db=80) (datasets.py:265)
-// is reduced with atomicMax while the unclamped values are written; clamp_topdb_kernel then
-// rewrites only the tiles whose minimum falls below max-80 dB.
+// is taken by clamp_topdb_kernel over the freshly written (L2-resident) log-mel planes, which
+// then rewrites only the rows that fall below max-80 dB.
 #include "common.cuh"
 #include "frontend_core.cuh"
 #include "frontend_host.h"
@@ -52,30 +52,18 @@ __device__ __forceinline__ void issue_tile_copy(uint32_t* samples, const int16_t
     }
 }
 
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ float warp_min(float v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 2)
 frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_per_clip, int ntiles,
                     const FrontendTables* __restrict__ tab, const float* __restrict__ mean,
                     const float* __restrict__ istd, float dc0, float dc1, float* __restrict__ out,
-                    uint32_t* __restrict__ gmax, float* __restrict__ tmin, int* __restrict__ flags) {
+                    int* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t* s_samples = reinterpret_cast<uint32_t*>(smem + SmemLayout::off_samples);
     float2* s_x1 = reinterpret_cast<float2*>(smem + SmemLayout::off_x1);
     float* s_win = reinterpret_cast<float*>(smem + SmemLayout::off_win);
-    float* s_melw = reinterpret_cast<float*>(smem + SmemLayout::off_melw);
+    MelEntry* s_melent = reinterpret_cast<MelEntry*>(smem + SmemLayout::off_melent);
     int16_t* s_melidx = reinterpret_cast<int16_t*>(smem + SmemLayout::off_melidx);
-    uint32_t* s_red = reinterpret_cast<uint32_t*>(smem + SmemLayout::off_red);
 
     const int tid = threadIdx.x;
     int tile = blockIdx.x;
@@ -86,22 +74,21 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
     cp_async_commit();
     // constant tables -> smem (once per persistent CTA)
     for (int i = tid; i < 25 * WROW; i += NTHREADS) s_win[i] = tab->win[i];
-    for (int i = tid; i < MEL_MAXNNZ; i += NTHREADS) s_melw[i] = tab->melw[i];
-    for (int i = tid; i < 3 * NMEL; i += NTHREADS) s_melidx[i] = tab->melidx[i];
+    for (int i = tid; i < MEL_MAXNNZ; i += NTHREADS) s_melent[i] = MelEntry{tab->melent_pos[i], tab->melw[i]};
+    for (int i = tid; i < 2 * NMEL; i += NTHREADS) s_melidx[i] = tab->melidx2[i];
 
     // fixed roles
     const int g1 = tid / 25, n2 = tid - 25 * g1;             // stage 1 (tid < 150)
     const int L = min(tid, 6 * 25 - 1);                      // stage 2: lane pairs (A,B) adjacent
     const int f2 = L / 50, t2 = (L % 50) >> 1, r2 = L & 1;
-    const int kt = (625 * t2) % 1200;
     const float c0 = r2 == 0 ? 1.0f : (1.0f / 3.0f);
+    float2* const vbase = s_x1 + f2 * VFRAME + 50 * t2 + r2;
 
     for (; tile < ntiles; tile += gridDim.x) {
         const int b = tile / tiles_per_clip, tb = tile % tiles_per_clip;
         const int t0 = tb * TF, nf = min(TF, T - t0);
         cp_async_wait_all();
         __syncthreads();
-        if (tid < 8) s_red[tid] = tid < 4 ? 0u : 0xffffffffu;  // max keys, min keys
 
         // ---- stage 1
         if (tid < 150 && (g1 >> 1) < nf) stage1_task(s_samples, s_win, s_x1, g1, n2);
@@ -125,7 +112,6 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
         // ---- stage 2b
         {
             const bool valid = tid < 150 && f2 < nf;
-            float2* vframe = s_x1 + f2 * VFRAME;
 #pragma unroll
             for (int k2 = 0; k2 < 25; ++k2) {
                 SlotMine m;
@@ -136,7 +122,7 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
                 other.e = __shfl_xor_sync(0xffffffffu, mine.e, 1);
                 float iva, ivb;
                 slot_finish(m, mine, other, r2, iva, ivb);
-                if (valid) slot_store(vframe, slot_bin(kt, k2), r2, m.P0, m.P1, iva, ivb);
+                if (valid) slot_store(vbase, k2, m.P0, m.P1, iva, ivb);
             }
         }
         __syncthreads();
@@ -144,77 +130,104 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
         // ---- mel projection + log + standardise + store
 #pragma unroll 1
         for (int rr = 0; rr < 3; ++rr) {
-            const int task = rr * NTHREADS + tid;     // (f, half, j), j fastest; warp-uniform (f, half)
-            if (task >= TF * 2 * NMEL) break;
-            const int f = task >> 7, half = (task >> 6) & 1, j = task & 63;
-            if (f >= nf) continue;
-            float acc[4];
-            mel_task(reinterpret_cast<const float4*>(s_x1 + f * VFRAME), s_melw, s_melidx, half, j, acc);
-            const long long tt = t0 + f;
-            if (half == 0) {
+            const int task = rr * NTHREADS + tid;     // (f, j, part): part fastest -> adjacent lanes
+            if (task >= TF * 2 * NMEL) break;          // warp-uniform (160 and 384 are multiples of 32)
+            const int f = task >> 7, j = (task >> 1) & 63, part = task & 1;
+            if (f >= nf) continue;                     // warp-uniform (128 tasks per frame)
+            float acc[8];
+            mel_task(reinterpret_cast<const float4*>(s_x1 + f * VFRAME), s_melent, s_melidx, j, part, acc);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+            float* o = out + (((long long)b * NCH_FOA) * T + (t0 + f)) * NMEL + j;
+            const long long cs = (long long)T * NMEL;
+            if (part == 0) {                           // lane 0 of the pair: the 4 log-mel channels
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const float db = power_to_db_unclamped(acc[c]);
-                    const float mx = warp_max(db), mn = warp_min(db);
-                    if ((tid & 31) == 0) {
-                        atomicMax(&s_red[c], f2key(mx));
-                        atomicMin(&s_red[4 + c], f2key(mn));
-                    }
                     const float mu = mean ? __ldg(mean + c * NMEL + j) : 0.f;
                     const float is = istd ? __ldg(istd + c * NMEL + j) : 1.f;
-                    out[(((long long)b * NCH_FOA + c) * T + tt) * NMEL + j] = (db - mu) * is;
+                    o[c * cs] = (db - mu) * is;
                 }
-            } else {
+            } else {                                   // lane 1: the 3 intensity channels
                 bool bad = false;
 #pragma unroll
                 for (int c = 4; c < 7; ++c) {
-                    const float v = acc[c - 3];
+                    const float v = acc[c + 1];
                     bad |= !(v == v);
                     const float mu = mean ? __ldg(mean + c * NMEL + j) : 0.f;
                     const float is = istd ? __ldg(istd + c * NMEL + j) : 1.f;
-                    out[(((long long)b * NCH_FOA + c) * T + tt) * NMEL + j] = (v - mu) * is;
+                    o[c * cs] = (v - mu) * is;
                 }
                 if (bad) atomicOr(flags, 1);  // reference prints + exit() on NaN (datasets.py:277)
             }
         }
-        __syncthreads();
-        if (tid < 4) {
-            atomicMax(&gmax[b * 4 + tid], s_red[tid]);
-            tmin[((long long)b * 4 + tid) * tiles_per_clip + tb] = key2f(s_red[4 + tid]);
-        }
+        // the barrier at the top of the next iteration orders these V reads before its stage 1
     }
     cp_async_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------------
-// top_db: out = max(out, standardise(max_db - top_db)) for the tiles that need it.
-// grid = B*4 blocks (one per clip-channel), 8 warps; warp w walks tiles w, w+8, ...
+// librosa.power_to_db top_db (datasets.py:265): out = max(out, max_over_clip_channel - top_db), in
+// the standardised domain (x -> (x-mean)*istd is monotone, so max commutes with it exactly).
+// One block per (clip, log-mel channel): pass 1 takes the max of the (T,64) plane (still L2-resident
+// from the front-end kernel), pass 2 rewrites only the values below the threshold.
 __global__ void __launch_bounds__(256)
-clamp_topdb_kernel(float* __restrict__ out, const uint32_t* __restrict__ gmax, const float* __restrict__ tmin,
-                   const float* __restrict__ mean, const float* __restrict__ istd, int T, int tiles_per_clip,
-                   float top_db) {
+clamp_topdb_kernel(float* __restrict__ out, const float* __restrict__ mean, const float* __restrict__ istd,
+                   int T, float top_db) {
+    __shared__ float s_max[8];
     const int b = blockIdx.x >> 2, c = blockIdx.x & 3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float thr = key2f(gmax[blockIdx.x]) - top_db;
-    const float th0 = (thr - (mean ? mean[c * NMEL + lane] : 0.f)) * (istd ? istd[c * NMEL + lane] : 1.f);
-    const float th1 = (thr - (mean ? mean[c * NMEL + lane + 32] : 0.f)) * (istd ? istd[c * NMEL + lane + 32] : 1.f);
-    float* base = out + ((long long)b * NCH_FOA + c) * T * NMEL;
-    for (int tb = warp; tb < tiles_per_clip; tb += 8) {
-        if (tmin[(long long)blockIdx.x * tiles_per_clip + tb] >= thr) continue;
-        const int t0 = tb * TF, nf = min(TF, T - t0);
-        for (int f = 0; f < nf; ++f) {
-            float* row = base + (long long)(t0 + f) * NMEL;
-            row[lane] = fmaxf(row[lane], th0);
-            row[lane + 32] = fmaxf(row[lane + 32], th1);
+    float4* base = reinterpret_cast<float4*>(out + ((long long)b * NCH_FOA + c) * T * NMEL);
+    const int n4 = T * (NMEL / 4);
+    const int j4 = threadIdx.x & 15;                      // this thread always sees mel bins 4*j4..4*j4+3
+    float mu[4], is[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        mu[q] = mean ? mean[c * NMEL + 4 * j4 + q] : 0.f;
+        is[q] = istd ? istd[c * NMEL + 4 * j4 + q] : 1.f;
+    }
+    // pass 1: max of dB = v/istd + mean  (un-standardise; exact enough: the clamp value itself is
+    // recomputed from the dB max below, and values are compared in the standardised domain)
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < n4; i += 256) {          // 256 % 16 == 0 -> j4 is loop-invariant
+        const float4 v = base[i];
+        mx = fmaxf(mx, fmaxf(fmaxf(v.x / is[0] + mu[0], v.y / is[1] + mu[1]),
+                             fmaxf(v.z / is[2] + mu[2], v.w / is[3] + mu[3])));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_max[warp] = mx;
+    __syncthreads();
+    mx = s_max[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_max[w]);
+    const float thr = mx - top_db;
+    float th[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) th[q] = (thr - mu[q]) * is[q];
+    for (int i = threadIdx.x; i < n4; i += 256) {
+        float4 v = base[i];
+        if (v.x < th[0] || v.y < th[1] || v.z < th[2] || v.w < th[3]) {
+            v.x = fmaxf(v.x, th[0]); v.y = fmaxf(v.y, th[1]); v.z = fmaxf(v.z, th[2]); v.w = fmaxf(v.w, th[3]);
+            base[i] = v;
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 size_t frontend_workspace_bytes(int B, long long N) {
+    (void)B; (void)N;
+    return 64;   // [flags int x4]
+}
+
+int launch_features_foa_clamp(float* out, int B, long long N, const float* mean, const float* istd, float top_db,
+                              void* ws, cudaStream_t stream) {
+    (void)ws;
     const long long T = N / HOP;
-    const long long tpc = (T + TF - 1) / TF;
-    return (size_t)(16 + (long long)B * 4 * 4 + (long long)B * 4 * tpc * 4 + 64);
+    if (B <= 0 || T <= 0) return set_error(ADY_ERR_INVALID, "features_foa_clamp: empty input");
+    clamp_topdb_kernel<<<B * 4, 256, 0, stream>>>(out, mean, istd, (int)T, top_db);
+    ADY_LAUNCH_CHECK("clamp_topdb_kernel");
+    return ADY_OK;
 }
 
 int launch_features_foa(const int16_t* audio, int B, long long N, const float* mean, const float* istd,
@@ -228,11 +241,8 @@ int launch_features_foa(const int16_t* audio, int B, long long N, const float* m
     const long long tpc = (T + TF - 1) / TF;
     const long long ntiles = (long long)B * tpc;
     if (ntiles > 0x7fffffffLL) return set_error(ADY_ERR_INVALID, "features_foa: too many tiles");
-    // workspace: [flags int x4][gmax u32 B*4][tmin f32 B*4*tpc]
     int* flags = reinterpret_cast<int*>(ws);
-    uint32_t* gmax = reinterpret_cast<uint32_t*>(flags + 4);
-    float* tmin = reinterpret_cast<float*>(gmax + (size_t)B * 4);
-    ADY_CUDA_CHECK(cudaMemsetAsync(ws, 0, 16 + (size_t)B * 16, stream));
+    ADY_CUDA_CHECK(cudaMemsetAsync(ws, 0, 16, stream));
 
     static int configured_dev = -1;
     int dev = 0, sms = 0;
@@ -246,26 +256,9 @@ int launch_features_foa(const int16_t* audio, int B, long long N, const float* m
     const int grid = (int)(ntiles < 2LL * sms ? ntiles : 2LL * sms);
     // window scale: 2^-15 (int16 -> [-1,1)) * 1/2 (channel split), DC terms scaled by the same 1/2
     frontend_foa_kernel<<<grid, NTHREADS, SmemLayout::total, stream>>>(
-        audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc_offset * 300.0f, -dc_offset * 150.0f, out,
-        gmax, tmin, flags);
+        audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc_offset * 300.0f, -dc_offset * 150.0f, out, flags);
     ADY_LAUNCH_CHECK("frontend_foa_kernel");
-    if (apply_topdb) {
-        clamp_topdb_kernel<<<B * 4, 256, 0, stream>>>(out, gmax, tmin, mean, istd, (int)T, (int)tpc, top_db);
-        ADY_LAUNCH_CHECK("clamp_topdb_kernel");
-    }
-    return ADY_OK;
-}
-
-int launch_features_foa_clamp(float* out, int B, long long N, const float* mean, const float* istd, float top_db,
-                              void* ws, cudaStream_t stream) {
-    const long long T = N / HOP;
-    if (B <= 0 || T <= 0) return set_error(ADY_ERR_INVALID, "features_foa_clamp: empty input");
-    const long long tpc = (T + TF - 1) / TF;
-    int* flags = reinterpret_cast<int*>(ws);
-    uint32_t* gmax = reinterpret_cast<uint32_t*>(flags + 4);
-    float* tmin = reinterpret_cast<float*>(gmax + (size_t)B * 4);
-    clamp_topdb_kernel<<<B * 4, 256, 0, stream>>>(out, gmax, tmin, mean, istd, (int)T, (int)tpc, top_db);
-    ADY_LAUNCH_CHECK("clamp_topdb_kernel");
+    if (apply_topdb) return launch_features_foa_clamp(out, B, N, mean, istd, top_db, ws, stream);
     return ADY_OK;
 }
 

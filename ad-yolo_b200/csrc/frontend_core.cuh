@@ -40,21 +40,26 @@ constexpr int NFFT_TILE = 2 * TF;  // packed complex FFTs per tile
 // 51*L + const.
 constexpr int SPLANE = 1275;
 constexpr int WROW = 49;                 // window table row stride (25 rows x 48 used)
-constexpr int FS = 1208;                 // float2 per packed FFT in the exchange buffer (2416 words == 16 mod 32)
+constexpr int FS = 1256;                 // float2 per packed FFT in the exchange buffer (2512 words == 16 mod 32)
 constexpr int VFRAME = 2 * FS;           // float2 units per frame (V4a + V4b alias the exchange buffer)
+constexpr int NPOS = 625;                // V is stored in PFA position order p = 25*t + k2 (t, k2 < 25)
 constexpr int MEL_MAXNNZ = 1216;
 
 struct SmemLayout {
     static constexpr int off_samples = 0;                                   // uint32 [6][1275]
     static constexpr int off_x1 = ((off_samples + NFFT_TILE * SPLANE * 4 + 15) / 16) * 16;  // float2 [6][1208]
     static constexpr int off_win = off_x1 + NFFT_TILE * FS * 8;              // float  [25][49]
-    static constexpr int off_melw = off_win + 25 * WROW * 4;                 // float  [1216]
-    static constexpr int off_melidx = off_melw + MEL_MAXNNZ * 4;             // int16  [3][64] start,len,off
-    static constexpr int off_red = off_melidx + 3 * NMEL * 2;                // int32  [8] tile max/min keys
-    static constexpr int total = ((off_red + 8 * 4 + 15) / 16) * 16;
+    static constexpr int off_melent = ((off_win + 25 * WROW * 4 + 7) / 8) * 8;  // MelEntry [1216] (pos, weight)
+    static constexpr int off_melidx = off_melent + MEL_MAXNNZ * 8;           // int16  [2][64] offset, len
+    static constexpr int total = ((off_melidx + 2 * NMEL * 2 + 15) / 16) * 16;
 };
 static_assert(SmemLayout::off_x1 % 16 == 0 && SmemLayout::off_win % 16 == 0, "alignment");
-static_assert(2 * NBIN * 16 <= VFRAME * 8, "V must fit in the exchange buffer of its frame");
+static_assert(2 * NPOS * 16 <= VFRAME * 8, "V must fit in the exchange buffer of its frame");
+
+struct MelEntry {   // one non-zero of the mel matrix: V position of its FFT bin + weight
+    int pos;
+    float w;
+};
 
 // ---------------------------------------------------------------- helpers
 ADY_HD int skew(int idx) { return idx + (idx >> 4); }
@@ -153,7 +158,11 @@ ADY_HD void slot_finish(const SlotMine& m, const SlotOut& mine, const SlotOut& o
     const float wre = r == 0 ? m.S0.re : other.s0re;
     const float wim = r == 0 ? m.S0.im : other.s0im;
     const float E = 1e-8f + (mine.e + other.e);
+#if defined(__CUDA_ARCH__)
+    const float rE = __fdividef(1.0f, E);   // MUFU.RCP (2 ulp) - far inside the 1e-3 tolerance
+#else
     const float rE = 1.0f / E;
+#endif
     iva = (wre * m.S0.re + wim * m.S0.im) * rE;   // role B: IV_Z        (role A: unused)
     ivb = (wre * m.S1.re + wim * m.S1.im) * rE;   // role A: IV_Y, role B: IV_X
 }
@@ -165,34 +174,36 @@ ADY_HD int slot_bin(int kt /* = 625*t % 1200 */, int k2) {
     return k > 600 ? 1200 - k : k;
 }
 
-// V layout per frame (float4 units): V4a[k] = (|W|^2,|Y|^2,|Z|^2,|X|^2), V4b[k] = (junk, IV_Y, IV_Z, IV_X)
-ADY_HD void slot_store(float2* __restrict__ vframe, int k, int r, float P0, float P1, float iva, float ivb) {
-    vframe[2 * k + r] = make_float2(P0, P1);
-    vframe[2 * NBIN + 2 * k + r] = make_float2(iva, ivb);
+// V layout per frame (float4 units, PFA position order p = 25 t + k2):
+//   V4a[p] = (|W|^2,|Y|^2,|Z|^2,|X|^2),  V4b[p] = (junk, IV_Y, IV_Z, IV_X)
+// vbase = frame base + 50 t + r (float2 units): every slot offset is a compile-time constant.
+ADY_HD void slot_store(float2* __restrict__ vbase, int k2, float P0, float P1, float iva, float ivb) {
+    vbase[2 * k2] = make_float2(P0, P1);
+    vbase[2 * NPOS + 2 * k2] = make_float2(iva, ivb);
 }
 
 // ---------------------------------------------------------------- mel phase
-// task (f, half, j): half 0 -> 4 power channels, half 1 -> IV channels. returns 4 accumulators.
-ADY_HD void mel_task(const float4* __restrict__ vframe4, const float* __restrict__ melw,
-                     const int16_t* __restrict__ melidx, int half, int j, float (&acc)[4]) {
-    const int start = melidx[j], len = melidx[NMEL + j], off = melidx[2 * NMEL + j];
-    const float4* v = vframe4 + half * NBIN + start;
-    const float* w = melw + off;
-    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-    for (int i = 0; i < len; ++i) {
-        const float4 x = v[i];
-        const float wi = w[i];
-        acc[0] += wi * x.x;
-        acc[1] += wi * x.y;
-        acc[2] += wi * x.z;
-        acc[3] += wi * x.w;
+// task (f, j, part): half of the non-zeros of mel filter j, all 7(+1) channels.  The two parts
+// of a filter sit in adjacent lanes and are summed with one shuffle step by the caller.
+ADY_HD void mel_task(const float4* __restrict__ vframe4, const MelEntry* __restrict__ ent,
+                     const int16_t* __restrict__ melidx, int j, int part, float (&acc)[8]) {
+    const int off = melidx[j], len = melidx[NMEL + j];
+    const int h = (len + 1) >> 1;
+    const int i0 = part ? h : 0, i1 = part ? len : h;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    for (int i = i0; i < i1; ++i) {
+        const MelEntry e = ent[off + i];
+        const float4 a = vframe4[e.pos], b = vframe4[NPOS + e.pos];
+        acc[0] += e.w * a.x; acc[1] += e.w * a.y; acc[2] += e.w * a.z; acc[3] += e.w * a.w;
+        acc[4] += e.w * b.x; acc[5] += e.w * b.y; acc[6] += e.w * b.z; acc[7] += e.w * b.w;
     }
 }
 
 // librosa.power_to_db(ref=1, amin=1e-10) before the top_db clamp (datasets.py:265)
 ADY_HD float power_to_db_unclamped(float s) {
 #if defined(__CUDA_ARCH__)
-    return 10.0f * log10f(fmaxf(s, 1e-10f));
+    return 3.0102999566398120f * __log2f(fmaxf(s, 1e-10f));   // 10 log10(s); MUFU.LG2 abs err ~1e-6 dB
 #else
     return 10.0f * __builtin_log10f(s > 1e-10f ? s : 1e-10f);
 #endif

@@ -11,6 +11,8 @@ struct FrontendTables {
     float melw[1216];        // concatenated non-zero runs of the (64 x 601) Slaney mel matrix
     int16_t melidx[3 * 64];  // [start | len | offset into melw] per mel filter
     float hann[1200];        // plain periodic Hann (for the float-input / stft paths)
+    int melent_pos[1216];    // fused kernel: V position (25 t + k2) of each non-zero's FFT bin
+    int16_t melidx2[2 * 64]; // fused kernel: [offset | len] per mel filter into melw / melent_pos
 };
 
 // librosa.filters.mel(sr, n_fft, n_mels) defaults (Slaney scale + norm, float32), row-major

@@ -69,6 +69,17 @@ static int build_tables(FrontendTables& t) {
         }
     std::vector<float> mel((size_t)NMEL * NBIN);
     mel_filterbank_host(24000, NFFT, NMEL, mel.data());
+    // V position of every FFT bin: p = 25 t + k2 with folded pfa_out(t, k2) == bin (first wins)
+    int pos_of_bin[NBIN];
+    for (int k = 0; k < NBIN; ++k) pos_of_bin[k] = -1;
+    for (int t = 0; t < 25; ++t)
+        for (int k2 = 0; k2 < 25; ++k2) {
+            int k = pfa_out(t, k2);
+            if (k > 600) k = 1200 - k;
+            if (pos_of_bin[k] < 0) pos_of_bin[k] = 25 * t + k2;
+        }
+    for (int k = 0; k < NBIN; ++k)
+        if (pos_of_bin[k] < 0) return set_error(ADY_ERR_INVALID, "internal: bin %d has no V position", k);
     int off = 0;
     for (int j = 0; j < NMEL; ++j) {
         int first = -1, last = -1;
@@ -83,7 +94,12 @@ static int build_tables(FrontendTables& t) {
         t.melidx[j] = (int16_t)first;
         t.melidx[NMEL + j] = (int16_t)len;
         t.melidx[2 * NMEL + j] = (int16_t)off;
-        for (int i = 0; i < len; ++i) t.melw[off + i] = mel[(size_t)j * NBIN + first + i];
+        t.melidx2[j] = (int16_t)off;
+        t.melidx2[NMEL + j] = (int16_t)len;
+        for (int i = 0; i < len; ++i) {
+            t.melw[off + i] = mel[(size_t)j * NBIN + first + i];
+            t.melent_pos[off + i] = pos_of_bin[first + i];
+        }
         off += len;
     }
     return ADY_OK;

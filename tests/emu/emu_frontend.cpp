@@ -17,8 +17,11 @@ extern "C" int emu_features_foa(const int16_t* audio, int B, long long N, const 
   uint32_t* s_samples = (uint32_t*)(smem.data() + SmemLayout::off_samples);
   float2* s_x1 = (float2*)(smem.data() + SmemLayout::off_x1);
   float* s_win = (float*)(smem.data() + SmemLayout::off_win);
-  float* s_melw = (float*)(smem.data() + SmemLayout::off_melw);
+  MelEntry* s_melent = (MelEntry*)(smem.data() + SmemLayout::off_melent);
   int16_t* s_melidx = (int16_t*)(smem.data() + SmemLayout::off_melidx);
+  int pos_of_bin[NBIN];
+  for (int k = 0; k < NBIN; ++k) pos_of_bin[k] = -1;
+  for (int t = 0; t < 25; ++t) for (int k2 = 0; k2 < 25; ++k2) { int k = pfa_out(t, k2); if (k > 600) k = 1200 - k; if (pos_of_bin[k] < 0) pos_of_bin[k] = 25 * t + k2; }
   for (int n2 = 0; n2 < 25; ++n2) for (int n1 = 0; n1 < 48; ++n1) {
     int n = pfa_in(n1, n2); double w = 0.5 - 0.5 * cos(2.0 * M_PI * n / NFFT);
     s_win[n2 * WROW + n1] = (float)w * (1.0f / 65536.0f);
@@ -29,8 +32,8 @@ extern "C" int emu_features_foa(const int16_t* audio, int B, long long N, const 
     for (int k = 0; k < NBIN; ++k) if (mel_dense[j * NBIN + k] != 0.f) { if (first < 0) first = k; last = k; }
     int len = last - first + 1;
     if (off + len > MEL_MAXNNZ) return -1;
-    s_melidx[j] = first; s_melidx[NMEL + j] = len; s_melidx[2 * NMEL + j] = off;
-    for (int i = 0; i < len; ++i) s_melw[off + i] = mel_dense[j * NBIN + first + i];
+    s_melidx[j] = off; s_melidx[NMEL + j] = len;
+    for (int i = 0; i < len; ++i) s_melent[off + i] = MelEntry{pos_of_bin[first + i], mel_dense[j * NBIN + first + i]};
     off += len;
   }
   const float dc0 = dc_offset * 300.0f, dc1 = -dc_offset * 150.0f;
@@ -64,29 +67,28 @@ extern "C" int emu_features_foa(const int16_t* audio, int B, long long N, const 
         for (int s = 0; s < 2; ++s) {
           int L = std::min(tid + s, 149); int f2 = L / 50, t2 = (L % 50) >> 1, r2 = L & 1;
           float iva, ivb; slot_finish(m[s], o[s], o[1 - s], r2, iva, ivb);
-          if (tid + s < 150 && f2 < nf) slot_store(s_x1 + f2 * VFRAME, slot_bin((625 * t2) % 1200, k2), r2, m[s].P0, m[s].P1, iva, ivb);
+          if (tid + s < 150 && f2 < nf) slot_store(s_x1 + f2 * VFRAME + 50 * t2 + r2, k2, m[s].P0, m[s].P1, iva, ivb);
         }
       }
     }
-    // ---- mel
-    for (int task = 0; task < TF * 2 * NMEL; ++task) {
-      const int f = task >> 7, half = (task >> 6) & 1, j = task & 63;
+    // ---- mel: task pairs (part 0 / part 1) summed like the shuffle in the kernel
+    for (int task = 0; task < TF * 2 * NMEL; task += 2) {
+      const int f = task >> 7, j = (task >> 1) & 63;
       if (f >= nf) continue;
-      float acc[4];
-      mel_task((const float4*)(s_x1 + f * VFRAME), s_melw, s_melidx, half, j, acc);
+      float a0[8], a1[8], acc[8];
+      mel_task((const float4*)(s_x1 + f * VFRAME), s_melent, s_melidx, j, 0, a0);
+      mel_task((const float4*)(s_x1 + f * VFRAME), s_melent, s_melidx, j, 1, a1);
+      for (int c = 0; c < 8; ++c) acc[c] = a0[c] + a1[c];
       const long long tt = t0 + f;
-      if (half == 0) {
-        for (int c = 0; c < 4; ++c) {
-          float db = power_to_db_unclamped(acc[c]);
-          gmax[b * 4 + c] = std::max(gmax[b * 4 + c], db);
-          float mu = mean ? mean[c * NMEL + j] : 0.f, is = istd ? istd[c * NMEL + j] : 1.f;
-          out[(((long long)b * 7 + c) * T + tt) * NMEL + j] = (db - mu) * is;
-        }
-      } else {
-        for (int c = 4; c < 7; ++c) {
-          float mu = mean ? mean[c * NMEL + j] : 0.f, is = istd ? istd[c * NMEL + j] : 1.f;
-          out[(((long long)b * 7 + c) * T + tt) * NMEL + j] = (acc[c - 3] - mu) * is;
-        }
+      for (int c = 0; c < 4; ++c) {
+        float db = power_to_db_unclamped(acc[c]);
+        gmax[b * 4 + c] = std::max(gmax[b * 4 + c], db);
+        float mu = mean ? mean[c * NMEL + j] : 0.f, is = istd ? istd[c * NMEL + j] : 1.f;
+        out[(((long long)b * 7 + c) * T + tt) * NMEL + j] = (db - mu) * is;
+      }
+      for (int c = 4; c < 7; ++c) {
+        float mu = mean ? mean[c * NMEL + j] : 0.f, is = istd ? istd[c * NMEL + j] : 1.f;
+        out[(((long long)b * 7 + c) * T + tt) * NMEL + j] = (acc[c + 1] - mu) * is;
       }
     }
   }
