@@ -172,23 +172,30 @@ __device__ __forceinline__ float bce_bwd_logit(float p, float t) {
 }
 
 constexpr int LA_THREADS = 256;
-constexpr int LA_TILE = 256;   // anchors per tile (tile base is 16-byte aligned for any channel count)
+constexpr int LA_TILE = 256;   // anchors per tile == threads (tile base is 16-byte aligned for any channel count)
 
-// One pass over the logits in memory order (float4, fully coalesced).  Thread = 4 consecutive
-// elements; the anchor's 64-bit label word is re-read (L1 hit) when the element run crosses
-// into the next anchor.  do_sums: accumulate the BCE sums (forward); grad != NULL: write
-// gscale * d loss / d logit (backward, or fused forward+backward with gscale = NULL -> 1).
+// Per tile of 256 anchors, three divergence-free passes:
+//   1. thread = anchor: objectness logit -> sigmoid, BCE sums, objectness gradient (smem);
+//      positive anchors (any threshold) are appended to a compact list
+//   2. (grad only) thread = 4 consecutive elements, float4 coalesced: objectness gradient from
+//      smem, zeros for the class channels, scaled angular partials for (u, v)
+//   3. work item = (positive anchor, class): class BCE sums / gradients (few items, uniform work)
+// do_sums: accumulate the BCE sums (forward); grad != NULL: write gscale * d loss / d logit.
 __global__ void __launch_bounds__(LA_THREADS)
 loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCfg cfg,
                    const unsigned long long* __restrict__ state, const float2* __restrict__ ang_grad,
                    LossAccum* __restrict__ acc, float* __restrict__ grad, const float* __restrict__ gscale,
                    int do_sums) {
+    __shared__ float s_go[LA_TILE];
+    __shared__ int s_pos_list[LA_TILE];
+    __shared__ int s_npos;
     const unsigned CH = cfg.nb_classes + 3, C = cfg.nb_classes;
     const int lane = threadIdx.x & 31;
 
     // per-threshold normalisers (counts are final: assign_rows_kernel has completed)
     const double gs = gscale ? (double)gscale[0] : 1.0;   // upstream d(total)/d(loss), device scalar
     float w_pos[ADY_MAX_THR], w_neg[ADY_MAX_THR], w_cls[ADY_MAX_THR];
+#pragma unroll
     for (int i = 0; i < ADY_MAX_THR; ++i) {
         const double np_ = i < cfg.n_thr ? (double)acc->n_pos[i] : 0.0;
         const double nn_ = (double)n_anchor - np_;
@@ -201,6 +208,8 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
     const unsigned long long OBJ_ANY = 0x0001000100010001ull;
 
     double s_pos[ADY_MAX_THR] = {0, 0, 0, 0}, s_neg[ADY_MAX_THR] = {0, 0, 0, 0}, s_cls[ADY_MAX_THR] = {0, 0, 0, 0};
+    if (threadIdx.x == 0) s_npos = 0;
+    __syncthreads();
 
     const long long n_tiles = (n_anchor + LA_TILE - 1) / LA_TILE;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -209,71 +218,76 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
         const unsigned nel = na * CH;
         const float* src = logit + a_base * CH;
         float* dst = grad ? grad + a_base * CH : nullptr;
-        for (unsigned el = threadIdx.x * 4; el < nel; el += LA_THREADS * 4) {
-            float x[4], g[4] = {0.f, 0.f, 0.f, 0.f};
-            const bool full = el + 4 <= nel;
-            if (full) {
-                const float4 v = *reinterpret_cast<const float4*>(src + el);
-                x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-            } else {
+
+        // ---- pass 1: objectness, one anchor per thread
+        if (threadIdx.x < na) {
+            const unsigned long long st = state[a_base + threadIdx.x];
+            const float p = sigmoid_torch(src[threadIdx.x * CH]);
+            const float g_pos = bce_bwd_logit(p, 1.f), g_neg = bce_bwd_logit(p, 0.f);
+            float l_pos = 0.f, l_neg = 0.f;
+            if (do_sums) { l_pos = bce_fwd(p, 1.f); l_neg = bce_fwd(p, 0.f); }
+            float go = 0.f;
 #pragma unroll
-                for (unsigned q = 0; q < 4; ++q) x[q] = el + q < nel ? src[el + q] : 0.f;
+            for (int i = 0; i < ADY_MAX_THR; ++i) {
+                if (i >= cfg.n_thr) break;
+                if ((st >> (16 * i)) & 1ull) { s_pos[i] += l_pos; go += w_pos[i] * g_pos; }
+                else                         { s_neg[i] += l_neg; go += w_neg[i] * g_neg; }
             }
-            unsigned a = el / CH, ch = el - a * CH;
-            unsigned long long st = state[a_base + a];
+            s_go[threadIdx.x] = go;
+            if (st & OBJ_ANY) s_pos_list[atomicAdd(&s_npos, 1)] = threadIdx.x;
+        }
+        __syncthreads();
+
+        // ---- pass 2: coalesced gradient write (objectness, zeroed classes, angular u/v)
+        if (dst) {
+            for (unsigned el = threadIdx.x * 4; el < nel; el += LA_THREADS * 4) {
+                unsigned a = el / CH, ch = el - a * CH;
+                float g[4];
 #pragma unroll
-            for (unsigned q = 0; q < 4; ++q) {
-                if (el + q < nel) {
-                    if (ch == 0) {
-                        const float p = sigmoid_torch(x[q]);
-                        const float g_pos = bce_bwd_logit(p, 1.f), g_neg = bce_bwd_logit(p, 0.f);
-                        float l_pos = 0.f, l_neg = 0.f;
-                        if (do_sums) { l_pos = bce_fwd(p, 1.f); l_neg = bce_fwd(p, 0.f); }
-                        float go = 0.f;
-#pragma unroll
-                        for (int i = 0; i < ADY_MAX_THR; ++i) {
-                            if (i >= cfg.n_thr) break;
-                            if ((st >> (16 * i)) & 1ull) { s_pos[i] += l_pos; go += w_pos[i] * g_pos; }
-                            else                         { s_neg[i] += l_neg; go += w_neg[i] * g_neg; }
-                        }
-                        g[q] = go;
-                    } else if (ch <= C) {
-                        if (st & OBJ_ANY) {
-                            const float pc = sigmoid_torch(x[q]);
-                            const float g1 = bce_bwd_logit(pc, 1.f), g0 = bce_bwd_logit(pc, 0.f);
-                            float l1 = 0.f, l0 = 0.f;
-                            if (do_sums) { l1 = bce_fwd(pc, 1.f); l0 = bce_fwd(pc, 0.f); }
-                            float gc = 0.f;
-#pragma unroll
-                            for (int i = 0; i < ADY_MAX_THR; ++i) {
-                                if (i >= cfg.n_thr) break;
-                                if ((st >> (16 * i)) & 1ull) {
-                                    const bool t = (st >> (16 * i + ch)) & 1ull;   // class c = ch-1 sits at bit 1+c
-                                    s_cls[i] += t ? l1 : l0;
-                                    gc += w_cls[i] * (t ? g1 : g0);
-                                }
-                            }
-                            g[q] = gc;
-                        }
-                    } else if (dst) {
+                for (unsigned q = 0; q < 4; ++q) {
+                    float v = 0.f;
+                    if (ch == 0) v = s_go[a < na ? a : 0];
+                    else if (ch > C && a < na) {
                         const float2 ag = ang_grad[a_base + a];
-                        g[q] = (ch == C + 1 ? ag.x : ag.y) * w_ang;
+                        v = (ch == C + 1 ? ag.x : ag.y) * w_ang;
                     }
+                    g[q] = v;
+                    if (++ch == CH) { ch = 0; ++a; }
                 }
-                if (++ch == CH) {
-                    ch = 0;
-                    ++a;
-                    if (a < na) st = state[a_base + a];
-                }
-            }
-            if (dst) {
-                if (full) *reinterpret_cast<float4*>(dst + el) = make_float4(g[0], g[1], g[2], g[3]);
+                if (el + 4 <= nel) *reinterpret_cast<float4*>(dst + el) = make_float4(g[0], g[1], g[2], g[3]);
                 else {
 #pragma unroll
                     for (unsigned q = 0; q < 4; ++q) if (el + q < nel) dst[el + q] = g[q];
                 }
             }
+            __syncthreads();   // class gradients of positive anchors overwrite the zeros below
         }
+
+        // ---- pass 3: (positive anchor, class) items
+        const unsigned n_items = (unsigned)s_npos * C;
+        for (unsigned it = threadIdx.x; it < n_items; it += LA_THREADS) {
+            const unsigned pi = it / C, c = it - pi * C;
+            const unsigned a = s_pos_list[pi];
+            const unsigned long long st = state[a_base + a];
+            const float pc = sigmoid_torch(src[a * CH + 1 + c]);
+            const float g1 = bce_bwd_logit(pc, 1.f), g0 = bce_bwd_logit(pc, 0.f);
+            float l1 = 0.f, l0 = 0.f;
+            if (do_sums) { l1 = bce_fwd(pc, 1.f); l0 = bce_fwd(pc, 0.f); }
+            float gc = 0.f;
+#pragma unroll
+            for (int i = 0; i < ADY_MAX_THR; ++i) {
+                if (i >= cfg.n_thr) break;
+                if ((st >> (16 * i)) & 1ull) {
+                    const bool t = (st >> (16 * i + 1 + c)) & 1ull;
+                    s_cls[i] += t ? l1 : l0;
+                    gc += w_cls[i] * (t ? g1 : g0);
+                }
+            }
+            if (dst) dst[a * CH + 1 + c] = gc;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_npos = 0;
+        __syncthreads();
     }
     if (!do_sums) return;
 #pragma unroll
@@ -284,12 +298,15 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
             s_neg[i] += __shfl_xor_sync(0xffffffffu, s_neg[i], o);
             s_cls[i] += __shfl_xor_sync(0xffffffffu, s_cls[i], o);
         }
-    if (lane == 0)
-        for (int i = 0; i < cfg.n_thr; ++i) {
-            atomicAdd(&acc->s_pos[i], s_pos[i]);
-            atomicAdd(&acc->s_neg[i], s_neg[i]);
-            atomicAdd(&acc->s_cls[i], s_cls[i]);
-        }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < ADY_MAX_THR; ++i)
+            if (i < cfg.n_thr) {
+                atomicAdd(&acc->s_pos[i], s_pos[i]);
+                atomicAdd(&acc->s_neg[i], s_neg[i]);
+                atomicAdd(&acc->s_cls[i], s_cls[i]);
+            }
+    }
 }
 
 __global__ void loss_finalize_kernel(long long n_anchor, AssignCfg cfg, const LossAccum* __restrict__ acc,

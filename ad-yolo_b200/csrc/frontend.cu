@@ -36,7 +36,7 @@ __device__ __forceinline__ void issue_tile_copy(uint32_t* samples, const int16_t
     const int16_t* clip = audio + (long long)b * N * 4 + pair * 2;
     for (int f = 0; f < nf; ++f) {
         const int t = t0 + f;
-        uint32_t* dst = samples + (2 * f + pair) * SPLANE + skew(i0);  // skew(i0 + 80 i) = skew(i0) + 85 i
+        uint32_t* dst = samples + q_of_g(2 * f + pair) * SPLANE + skew(i0);  // skew(i0 + 80 i) = skew(i0) + 85 i
         if (t > 0) {
             const int16_t* src = clip + ((long long)(t - 1) * HOP + i0) * 4;
 #pragma unroll
@@ -61,9 +61,8 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t* s_samples = reinterpret_cast<uint32_t*>(smem + SmemLayout::off_samples);
     float2* s_x1 = reinterpret_cast<float2*>(smem + SmemLayout::off_x1);
-    float* s_win = reinterpret_cast<float*>(smem + SmemLayout::off_win);
     MelEntry* s_melent = reinterpret_cast<MelEntry*>(smem + SmemLayout::off_melent);
-    int16_t* s_melidx = reinterpret_cast<int16_t*>(smem + SmemLayout::off_melidx);
+    int* s_melhdr = reinterpret_cast<int*>(smem + SmemLayout::off_melhdr);
 
     const int tid = threadIdx.x;
     int tile = blockIdx.x;
@@ -73,16 +72,18 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
     }
     cp_async_commit();
     // constant tables -> smem (once per persistent CTA)
-    for (int i = tid; i < 25 * WROW; i += NTHREADS) s_win[i] = tab->win[i];
-    for (int i = tid; i < MEL_MAXNNZ; i += NTHREADS) s_melent[i] = MelEntry{tab->melent_pos[i], tab->melw[i]};
-    for (int i = tid; i < 2 * NMEL; i += NTHREADS) s_melidx[i] = tab->melidx2[i];
+    for (int i = tid; i < MEL_MAXROWS * 32; i += NTHREADS) s_melent[i] = MelEntry{tab->mel_pos[i], tab->mel_w[i]};
+    if (tid < 8) s_melhdr[tid] = tab->mel_hdr[tid];
 
     // fixed roles
-    const int g1 = tid / 25, n2 = tid - 25 * g1;             // stage 1 (tid < 150)
+    const int q1 = tid / 25, n2 = tid - 25 * q1;             // stage 1 (tid < 150): lane group q1 -> fft g_of_q(q1)
+    const int f1 = q1 < 3 ? q1 : q1 - 3;                     // its frame
+    const float cB = tab->wcs[2 * (n2 % 25)], sB = tab->wcs[2 * (n2 % 25) + 1];
     const int L = min(tid, 6 * 25 - 1);                      // stage 2: lane pairs (A,B) adjacent
     const int f2 = L / 50, t2 = (L % 50) >> 1, r2 = L & 1;
     const float c0 = r2 == 0 ? 1.0f : (1.0f / 3.0f);
-    float2* const vbase = s_x1 + f2 * VFRAME + 50 * t2 + r2;
+    float2* const vbase = s_x1 + v_base(f2) + 50 * t2 + r2;
+    const int warp = tid >> 5, lane = tid & 31;
 
     for (; tile < ntiles; tile += gridDim.x) {
         const int b = tile / tiles_per_clip, tb = tile % tiles_per_clip;
@@ -91,7 +92,7 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
         __syncthreads();
 
         // ---- stage 1
-        if (tid < 150 && (g1 >> 1) < nf) stage1_task(s_samples, s_win, s_x1, g1, n2);
+        if (tid < 150 && f1 < nf) stage1_task(s_samples, s_x1, q1, n2, cB, sB);
         __syncthreads();
 
         // samples are free: prefetch the next tile while stage 2 / mel run
@@ -127,17 +128,19 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
         }
         __syncthreads();
 
-        // ---- mel projection + log + standardise + store
+        // ---- mel projection + log + standardise + store (static schedule, balanced over warps)
 #pragma unroll 1
-        for (int rr = 0; rr < 3; ++rr) {
-            const int task = rr * NTHREADS + tid;     // (f, j, part): part fastest -> adjacent lanes
-            if (task >= TF * 2 * NMEL) break;          // warp-uniform (160 and 384 are multiples of 32)
-            const int f = task >> 7, j = (task >> 1) & 63, part = task & 1;
-            if (f >= nf) continue;                     // warp-uniform (128 tasks per frame)
+        for (int qq = 0; qq < 3; ++qq) {
+            const int code = mel_assign(warp, qq);
+            if (code < 0) break;
+            const int f = code >> 2, wt = code & 3;
+            if (f >= nf) continue;
             float acc[8];
-            mel_task(reinterpret_cast<const float4*>(s_x1 + f * VFRAME), s_melent, s_melidx, j, part, acc);
+            mel_task(reinterpret_cast<const float4*>(s_x1 + v_base(f)), s_melent + s_melhdr[wt] * 32 + lane,
+                     s_melhdr[4 + wt], acc);
 #pragma unroll
             for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+            const int j = 16 * wt + (lane >> 1), part = lane & 1;
             float* o = out + (((long long)b * NCH_FOA) * T + (t0 + f)) * NMEL + j;
             const long long cs = (long long)T * NMEL;
             if (part == 0) {                           // lane 0 of the pair: the 4 log-mel channels

@@ -39,22 +39,32 @@ constexpr int NFFT_TILE = 2 * TF;  // packed complex FFTs per tile
 // stride-48 reads); 1275 words per plane == 51*25 so that lane L = 25*fft + n2 reads word
 // 51*L + const.
 constexpr int SPLANE = 1275;
-constexpr int WROW = 49;                 // window table row stride (25 rows x 48 used)
-constexpr int FS = 1256;                 // float2 per packed FFT in the exchange buffer (2512 words == 16 mod 32)
-constexpr int VFRAME = 2 * FS;           // float2 units per frame (V4a + V4b alias the exchange buffer)
+constexpr int FS = 1256;                 // float2 per packed FFT in the exchange buffer (== 8 mod 16)
+constexpr int XFRAME = 2 * FS + 25;      // float2 per frame block (2537 == 9 mod 16, see x1_base)
 constexpr int NPOS = 625;                // V is stored in PFA position order p = 25*t + k2 (t, k2 < 25)
+constexpr int MEL_MAXROWS = 56;          // rows of 32 lanes in the static mel schedule
 constexpr int MEL_MAXNNZ = 1216;
+
+// Stage 1 walks the packed FFTs in the lane-group order g = 0,2,4,1,3,5 (the three (W,Y) FFTs,
+// then the three (Z,X) FFTs) and sample planes are stored in that order, so that lane L of the CTA
+// reads sample word 51*L + const and writes exchange word 2*(25*k1) + 2*L' + const with the bank
+// sequence continuing across lane groups:
+//   x1_base(g+2) - x1_base(g) == 9 (mod 16 float2)   [25 float2 of the previous group]
+//   x1_base(2f+1) - x1_base(2f) == 8 (mod 16 float2) [stage 2a: adjacent A/B lanes, disjoint banks]
+ADY_HD constexpr int g_of_q(int q) { return q < 3 ? 2 * q : 2 * (q - 3) + 1; }
+ADY_HD constexpr int q_of_g(int g) { return (g & 1) ? 3 + (g >> 1) : (g >> 1); }
+ADY_HD constexpr int x1_base(int g) { return (g >> 1) * XFRAME + (g & 1) * FS; }
+ADY_HD constexpr int v_base(int f) { return ((f * XFRAME + 1) >> 1) << 1; }   // float2 units, 16-byte aligned
 
 struct SmemLayout {
     static constexpr int off_samples = 0;                                   // uint32 [6][1275]
-    static constexpr int off_x1 = ((off_samples + NFFT_TILE * SPLANE * 4 + 15) / 16) * 16;  // float2 [6][1208]
-    static constexpr int off_win = off_x1 + NFFT_TILE * FS * 8;              // float  [25][49]
-    static constexpr int off_melent = ((off_win + 25 * WROW * 4 + 7) / 8) * 8;  // MelEntry [1216] (pos, weight)
-    static constexpr int off_melidx = off_melent + MEL_MAXNNZ * 8;           // int16  [2][64] offset, len
-    static constexpr int total = ((off_melidx + 2 * NMEL * 2 + 15) / 16) * 16;
+    static constexpr int off_x1 = ((off_samples + NFFT_TILE * SPLANE * 4 + 15) / 16) * 16;  // float2 [TF][XFRAME]
+    static constexpr int off_melent = ((off_x1 + TF * XFRAME * 8 + 15) / 16) * 16;  // MelEntry [56][32]
+    static constexpr int off_melhdr = off_melent + MEL_MAXROWS * 32 * 8;     // int32 [8]: it0[4], nit[4]
+    static constexpr int total = ((off_melhdr + 8 * 4 + 15) / 16) * 16;
 };
-static_assert(SmemLayout::off_x1 % 16 == 0 && SmemLayout::off_win % 16 == 0, "alignment");
-static_assert(2 * NPOS * 16 <= VFRAME * 8, "V must fit in the exchange buffer of its frame");
+static_assert(SmemLayout::off_x1 % 16 == 0 && SmemLayout::off_melent % 16 == 0, "alignment");
+static_assert(v_base(0) + 2 * NPOS * 2 <= XFRAME && x1_base(1) + 1200 <= XFRAME, "V / FFT data must fit in a frame block");
 
 struct MelEntry {   // one non-zero of the mel matrix: V position of its FFT bin + weight
     int pos;
@@ -76,12 +86,19 @@ ADY_HD float key2f(uint32_t k) {
 }
 
 // ---------------------------------------------------------------- stage 1
-// thread (g = packed fft 0..5, n2 = 0..24).  samples: uint32 words (lo int16 = re channel,
-// hi int16 = im channel).  win: row n2 holds w[(25 n1 + 48 n2) mod 1200] * scale.
-ADY_HD void stage1_task(const uint32_t* __restrict__ samples, const float* __restrict__ win,
-                        float2* __restrict__ x1, int g, int n2) {
-    const uint32_t* sp = samples + g * SPLANE + 51 * n2;
-    const float* wp = win + WROW * n2;
+// Periodic Hann window at n = (25 n1 + 48 n2) mod 1200, scaled by 2^-16 (int16 -> [-1,1) and the
+// 1/2 of the channel split):  w = 2^-16 (0.5 - 0.5 cos(2 pi n1/48 + 2 pi n2/25))
+//                               = W0 + CA[n1] * cos(2 pi n2/25) + SA[n1] * sin(2 pi n2/25)
+// CA/SA are compile-time immediates, (cB, sB) two per-thread registers: two FMAs replace a
+// shared-memory table lookup (shared-memory bandwidth is the scarcer resource in this kernel).
+// thread (q = lane group 0..5 -> packed fft g = g_of_q(q), n2 = 0..24).  samples: uint32 words
+// (lo int16 = re channel, hi int16 = im channel), plane q.
+ADY_HD void stage1_task(const uint32_t* __restrict__ samples, float2* __restrict__ x1, int q, int n2,
+                        float cB, float sB) {
+    constexpr float WIN_W0 = 0.5f / 65536.0f;
+    constexpr float WIN_CA[48] = {-7.6293945312e-06f, -7.5641240034e-06f, -7.3694292167e-06f, -7.0486414529e-06f, -6.6072494796e-06f, -6.0528056358e-06f, -5.3947966094e-06f, -4.6444811173e-06f, -3.8146972656e-06f, -2.9196428861e-06f, -1.9746326073e-06f, -9.9583581711e-07f, -4.6716567961e-22f, 9.9583581711e-07f, 1.9746326073e-06f, 2.9196428861e-06f, 3.8146972656e-06f, 4.6444811173e-06f, 5.3947966094e-06f, 6.0528056358e-06f, 6.6072494796e-06f, 7.0486414529e-06f, 7.3694292167e-06f, 7.5641240034e-06f, 7.6293945312e-06f, 7.5641240034e-06f, 7.3694292167e-06f, 7.0486414529e-06f, 6.6072494796e-06f, 6.0528056358e-06f, 5.3947966094e-06f, 4.6444811173e-06f, 3.8146972656e-06f, 2.9196428861e-06f, 1.9746326073e-06f, 9.9583581711e-07f, 1.4014970388e-21f, -9.9583581711e-07f, -1.9746326073e-06f, -2.9196428861e-06f, -3.8146972656e-06f, -4.6444811173e-06f, -5.3947966094e-06f, -6.0528056358e-06f, -6.6072494796e-06f, -7.0486414529e-06f, -7.3694292167e-06f, -7.5641240034e-06f};
+    constexpr float WIN_SA[48] = {0.0000000000e+00f, 9.9583581711e-07f, 1.9746326073e-06f, 2.9196428861e-06f, 3.8146972656e-06f, 4.6444811173e-06f, 5.3947966094e-06f, 6.0528056358e-06f, 6.6072494796e-06f, 7.0486414529e-06f, 7.3694292167e-06f, 7.5641240034e-06f, 7.6293945312e-06f, 7.5641240034e-06f, 7.3694292167e-06f, 7.0486414529e-06f, 6.6072494796e-06f, 6.0528056358e-06f, 5.3947966094e-06f, 4.6444811173e-06f, 3.8146972656e-06f, 2.9196428861e-06f, 1.9746326073e-06f, 9.9583581711e-07f, 9.3433135921e-22f, -9.9583581711e-07f, -1.9746326073e-06f, -2.9196428861e-06f, -3.8146972656e-06f, -4.6444811173e-06f, -5.3947966094e-06f, -6.0528056358e-06f, -6.6072494796e-06f, -7.0486414529e-06f, -7.3694292167e-06f, -7.5641240034e-06f, -7.6293945312e-06f, -7.5641240034e-06f, -7.3694292167e-06f, -7.0486414529e-06f, -6.6072494796e-06f, -6.0528056358e-06f, -5.3947966094e-06f, -4.6444811173e-06f, -3.8146972656e-06f, -2.9196428861e-06f, -1.9746326073e-06f, -9.9583581711e-07f};
+    const uint32_t* sp = samples + q * SPLANE + 51 * n2;
     const int thr = 1200 - 48 * n2;  // wrap when 25*n1 >= thr
     cx<float> x[48];
 #pragma unroll
@@ -89,13 +106,13 @@ ADY_HD void stage1_task(const uint32_t* __restrict__ samples, const float* __res
         const int c = 25 * n1;
         const int off = c + (c >> 4);
         const uint32_t word = sp[off - (c >= thr ? SPLANE : 0)];
-        const float w = wp[n1];
+        const float w = WIN_W0 + WIN_CA[n1] * cB + WIN_SA[n1] * sB;
         const float lo = (float)(int16_t)(word & 0xffffu);
         const float hi = (float)(int16_t)(word >> 16);
         x[n1] = {lo * w, hi * w};
     }
     dft48(x);
-    float2* xo = x1 + g * FS + n2;
+    float2* xo = x1 + x1_base(q < 3 ? 2 * q : 2 * (q - 3) + 1) + n2;
 #pragma unroll
     for (int k1 = 0; k1 < 48; ++k1) xo[k1 * 25] = make_float2(x[k1].re, x[k1].im);
 }
@@ -111,8 +128,8 @@ struct Stage2Regs {
 ADY_HD void stage2a_task(const float2* __restrict__ x1, int f, int t, int r, float dc0, float dc1,
                          Stage2Regs& s) {
     const int g = 2 * f + r;
-    const float2* pa = x1 + g * FS + t * 25;
-    const float2* pb = x1 + g * FS + ((48 - t) % 48) * 25;
+    const float2* pa = x1 + x1_base(g) + t * 25;
+    const float2* pb = x1 + x1_base(g) + ((48 - t) % 48) * 25;
 #pragma unroll
     for (int n2 = 0; n2 < 25; ++n2) {
         float2 a = pa[n2], b = pb[n2];
@@ -183,21 +200,29 @@ ADY_HD void slot_store(float2* __restrict__ vbase, int k2, float P0, float P1, f
 }
 
 // ---------------------------------------------------------------- mel phase
-// task (f, j, part): half of the non-zeros of mel filter j, all 7(+1) channels.  The two parts
-// of a filter sit in adjacent lanes and are summed with one shuffle step by the caller.
-ADY_HD void mel_task(const float4* __restrict__ vframe4, const MelEntry* __restrict__ ent,
-                     const int16_t* __restrict__ melidx, int j, int part, float (&acc)[8]) {
-    const int off = melidx[j], len = melidx[NMEL + j];
-    const int h = (len + 1) >> 1;
-    const int i0 = part ? h : 0, i1 = part ? len : h;
+// warp-task wt (16 filters x 2 parts = 32 lanes): lane walks its column of the static schedule
+// ent[it0 + it][lane]; every lane of the warp runs nit iterations (zero-weight padding).
+ADY_HD void mel_task(const float4* __restrict__ vframe4, const MelEntry* __restrict__ ent_col, int nit,
+                     float (&acc)[8]) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-    for (int i = i0; i < i1; ++i) {
-        const MelEntry e = ent[off + i];
+#pragma unroll 2
+    for (int it = 0; it < nit; ++it) {
+        const MelEntry e = ent_col[it * 32];
         const float4 a = vframe4[e.pos], b = vframe4[NPOS + e.pos];
         acc[0] += e.w * a.x; acc[1] += e.w * a.y; acc[2] += e.w * a.z; acc[3] += e.w * a.w;
         acc[4] += e.w * b.x; acc[5] += e.w * b.y; acc[6] += e.w * b.z; acc[7] += e.w * b.w;
     }
+}
+
+// Balanced assignment of the 12 (frame, warp-task) pairs of a tile to the 5 warps (iteration
+// counts ~ 3 / 6 / 14 / 31): code = 4*frame + warp-task, -1 = none.  Makespan 34 vs 51 round-robin.
+// 15 nibbles [warp][slot], 15 = none:  w0: (f0,wt3) (f0,wt0) | w1: (f1,wt3) (f1,wt0) | w2: (f2,wt3) (f2,wt0)
+//                                      | w3: (f0,wt2) (f1,wt2) (f0,wt1) | w4: (f2,wt2) (f1,wt1) (f2,wt1)
+constexpr unsigned long long MEL_ASSIGN_PACK = 0x95a162f8bf47f03ull;
+ADY_HD int mel_assign(int warp, int slot) {
+    const int v = (int)((MEL_ASSIGN_PACK >> (4 * (warp * 3 + slot))) & 15ull);
+    return v == 15 ? -1 : v;
 }
 
 // librosa.power_to_db(ref=1, amin=1e-10) before the top_db clamp (datasets.py:265)

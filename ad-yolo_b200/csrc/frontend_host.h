@@ -7,12 +7,13 @@
 namespace ady {
 
 struct FrontendTables {
-    float win[25 * 49];      // win[n2*49 + n1] = hann[(25 n1 + 48 n2) % 1200] * 2^-16
     float melw[1216];        // concatenated non-zero runs of the (64 x 601) Slaney mel matrix
     int16_t melidx[3 * 64];  // [start | len | offset into melw] per mel filter
     float hann[1200];        // plain periodic Hann (for the float-input / stft paths)
-    int melent_pos[1216];    // fused kernel: V position (25 t + k2) of each non-zero's FFT bin
-    int16_t melidx2[2 * 64]; // fused kernel: [offset | len] per mel filter into melw / melent_pos
+    float wcs[25 * 2];       // fused kernel: cos / sin (2 pi n2 / 25) of the window factorisation
+    int mel_hdr[8];          // fused kernel: static mel schedule, it0[4] | nit[4]
+    int mel_pos[56 * 32];    // fused kernel: schedule entries [row][lane]: V position ...
+    float mel_w[56 * 32];    //               ... and weight (0 = padding)
 };
 
 // librosa.filters.mel(sr, n_fft, n_mels) defaults (Slaney scale + norm, float32), row-major

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "frontend_core.cuh"
 #include "frontend_host.h"
+#include "frontend_tables.h"
 
 namespace ady {
 
@@ -61,25 +62,8 @@ void mel_filterbank_host(int sr, int n_fft, int n_mels, float* out) {
 static int build_tables(FrontendTables& t) {
     memset(&t, 0, sizeof(t));
     for (int n = 0; n < NFFT; ++n) t.hann[n] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * n / NFFT));
-    for (int n2 = 0; n2 < 25; ++n2)
-        for (int n1 = 0; n1 < 48; ++n1) {
-            const int n = pfa_in(n1, n2);
-            const double w = 0.5 - 0.5 * cos(2.0 * M_PI * n / NFFT);
-            t.win[n2 * WROW + n1] = (float)w * (1.0f / 65536.0f);
-        }
     std::vector<float> mel((size_t)NMEL * NBIN);
     mel_filterbank_host(24000, NFFT, NMEL, mel.data());
-    // V position of every FFT bin: p = 25 t + k2 with folded pfa_out(t, k2) == bin (first wins)
-    int pos_of_bin[NBIN];
-    for (int k = 0; k < NBIN; ++k) pos_of_bin[k] = -1;
-    for (int t = 0; t < 25; ++t)
-        for (int k2 = 0; k2 < 25; ++k2) {
-            int k = pfa_out(t, k2);
-            if (k > 600) k = 1200 - k;
-            if (pos_of_bin[k] < 0) pos_of_bin[k] = 25 * t + k2;
-        }
-    for (int k = 0; k < NBIN; ++k)
-        if (pos_of_bin[k] < 0) return set_error(ADY_ERR_INVALID, "internal: bin %d has no V position", k);
     int off = 0;
     for (int j = 0; j < NMEL; ++j) {
         int first = -1, last = -1;
@@ -94,14 +78,17 @@ static int build_tables(FrontendTables& t) {
         t.melidx[j] = (int16_t)first;
         t.melidx[NMEL + j] = (int16_t)len;
         t.melidx[2 * NMEL + j] = (int16_t)off;
-        t.melidx2[j] = (int16_t)off;
-        t.melidx2[NMEL + j] = (int16_t)len;
-        for (int i = 0; i < len; ++i) {
-            t.melw[off + i] = mel[(size_t)j * NBIN + first + i];
-            t.melent_pos[off + i] = pos_of_bin[first + i];
-        }
+        for (int i = 0; i < len; ++i) t.melw[off + i] = mel[(size_t)j * NBIN + first + i];
         off += len;
     }
+    for (int n2 = 0; n2 < 25; ++n2) {
+        t.wcs[2 * n2] = (float)cos(2.0 * M_PI * n2 / 25.0);
+        t.wcs[2 * n2 + 1] = (float)sin(2.0 * M_PI * n2 / 25.0);
+    }
+    MelSchedule sch;
+    if (!build_mel_schedule(mel.data(), sch)) return set_error(ADY_ERR_INVALID, "mel schedule does not fit (%d rows)", sch.total_rows);
+    for (int i = 0; i < 4; ++i) { t.mel_hdr[i] = sch.it0[i]; t.mel_hdr[4 + i] = sch.nit[i]; }
+    for (size_t i = 0; i < sch.ent.size(); ++i) { t.mel_pos[i] = sch.ent[i].pos; t.mel_w[i] = sch.ent[i].w; }
     return ADY_OK;
 }
 

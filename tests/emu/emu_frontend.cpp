@@ -5,7 +5,7 @@
 #include <string.h>
 #include <vector>
 #include <algorithm>
-#include "../../ad-yolo_b200/csrc/frontend_core.cuh"
+#include "../../ad-yolo_b200/csrc/frontend_tables.h"
 using namespace ady;
 
 extern "C" int emu_features_foa(const int16_t* audio, int B, long long N, const float* mel_dense /*64x601*/,
@@ -16,26 +16,12 @@ extern "C" int emu_features_foa(const int16_t* audio, int B, long long N, const 
   std::vector<unsigned char> smem(SmemLayout::total, 0);
   uint32_t* s_samples = (uint32_t*)(smem.data() + SmemLayout::off_samples);
   float2* s_x1 = (float2*)(smem.data() + SmemLayout::off_x1);
-  float* s_win = (float*)(smem.data() + SmemLayout::off_win);
   MelEntry* s_melent = (MelEntry*)(smem.data() + SmemLayout::off_melent);
-  int16_t* s_melidx = (int16_t*)(smem.data() + SmemLayout::off_melidx);
-  int pos_of_bin[NBIN];
-  for (int k = 0; k < NBIN; ++k) pos_of_bin[k] = -1;
-  for (int t = 0; t < 25; ++t) for (int k2 = 0; k2 < 25; ++k2) { int k = pfa_out(t, k2); if (k > 600) k = 1200 - k; if (pos_of_bin[k] < 0) pos_of_bin[k] = 25 * t + k2; }
-  for (int n2 = 0; n2 < 25; ++n2) for (int n1 = 0; n1 < 48; ++n1) {
-    int n = pfa_in(n1, n2); double w = 0.5 - 0.5 * cos(2.0 * M_PI * n / NFFT);
-    s_win[n2 * WROW + n1] = (float)w * (1.0f / 65536.0f);
-  }
-  int off = 0;
-  for (int j = 0; j < NMEL; ++j) {
-    int first = -1, last = -1;
-    for (int k = 0; k < NBIN; ++k) if (mel_dense[j * NBIN + k] != 0.f) { if (first < 0) first = k; last = k; }
-    int len = last - first + 1;
-    if (off + len > MEL_MAXNNZ) return -1;
-    s_melidx[j] = off; s_melidx[NMEL + j] = len;
-    for (int i = 0; i < len; ++i) s_melent[off + i] = MelEntry{pos_of_bin[first + i], mel_dense[j * NBIN + first + i]};
-    off += len;
-  }
+  MelSchedule sch;
+  if (!build_mel_schedule(mel_dense, sch)) return -1;
+  for (size_t i = 0; i < sch.ent.size(); ++i) s_melent[i] = sch.ent[i];
+  float wcs[50];
+  for (int n2 = 0; n2 < 25; ++n2) { wcs[2 * n2] = (float)cos(2.0 * M_PI * n2 / 25.0); wcs[2 * n2 + 1] = (float)sin(2.0 * M_PI * n2 / 25.0); }
   const float dc0 = dc_offset * 300.0f, dc1 = -dc_offset * 150.0f;
   std::vector<float> gmax(B * 4, -INFINITY);
   for (int tile = 0; tile < B * tpc; ++tile) {
@@ -46,7 +32,7 @@ extern "C" int emu_features_foa(const int16_t* audio, int B, long long N, const 
       const int16_t* clip = audio + (long long)b * N * 4 + pair * 2;
       for (int f = 0; f < nf; ++f) {
         const int t = t0 + f;
-        uint32_t* dst = s_samples + (2 * f + pair) * SPLANE + skew(i0);
+        uint32_t* dst = s_samples + q_of_g(2 * f + pair) * SPLANE + skew(i0);
         for (int i = 0; i < 15; ++i) {
           const int idx = i0 + 80 * i;
           long long m = t > 0 ? (long long)(t - 1) * HOP + idx : (idx < HOP ? HOP - idx : idx - HOP);
@@ -55,7 +41,7 @@ extern "C" int emu_features_foa(const int16_t* audio, int B, long long N, const 
       }
     }
     // ---- stage 1
-    for (int tid = 0; tid < 150; ++tid) { int g = tid / 25, n2 = tid % 25; if ((g >> 1) < nf) stage1_task(s_samples, s_win, s_x1, g, n2); }
+    for (int tid = 0; tid < 150; ++tid) { int q = tid / 25, n2 = tid % 25; int f1 = q < 3 ? q : q - 3; if (f1 < nf) stage1_task(s_samples, s_x1, q, n2, wcs[2 * n2], wcs[2 * n2 + 1]); }
     // ---- stage 2a (all threads, then "barrier")
     std::vector<Stage2Regs> R(NTHREADS);
     for (int tid = 0; tid < NTHREADS; ++tid) { int L = std::min(tid, 149); stage2a_task(s_x1, L / 50, (L % 50) >> 1, L & 1, dc0, dc1, R[tid]); }
@@ -67,28 +53,32 @@ extern "C" int emu_features_foa(const int16_t* audio, int B, long long N, const 
         for (int s = 0; s < 2; ++s) {
           int L = std::min(tid + s, 149); int f2 = L / 50, t2 = (L % 50) >> 1, r2 = L & 1;
           float iva, ivb; slot_finish(m[s], o[s], o[1 - s], r2, iva, ivb);
-          if (tid + s < 150 && f2 < nf) slot_store(s_x1 + f2 * VFRAME + 50 * t2 + r2, k2, m[s].P0, m[s].P1, iva, ivb);
+          if (tid + s < 150 && f2 < nf) slot_store(s_x1 + v_base(f2) + 50 * t2 + r2, k2, m[s].P0, m[s].P1, iva, ivb);
         }
       }
     }
-    // ---- mel: task pairs (part 0 / part 1) summed like the shuffle in the kernel
-    for (int task = 0; task < TF * 2 * NMEL; task += 2) {
-      const int f = task >> 7, j = (task >> 1) & 63;
+    // ---- mel: static schedule, lanes of a warp-task emulated one by one, pairs summed
+    for (int code = 0; code < TF * 4; ++code) {
+      const int f = code >> 2, wt = code & 3;
       if (f >= nf) continue;
-      float a0[8], a1[8], acc[8];
-      mel_task((const float4*)(s_x1 + f * VFRAME), s_melent, s_melidx, j, 0, a0);
-      mel_task((const float4*)(s_x1 + f * VFRAME), s_melent, s_melidx, j, 1, a1);
-      for (int c = 0; c < 8; ++c) acc[c] = a0[c] + a1[c];
-      const long long tt = t0 + f;
-      for (int c = 0; c < 4; ++c) {
-        float db = power_to_db_unclamped(acc[c]);
-        gmax[b * 4 + c] = std::max(gmax[b * 4 + c], db);
-        float mu = mean ? mean[c * NMEL + j] : 0.f, is = istd ? istd[c * NMEL + j] : 1.f;
-        out[(((long long)b * 7 + c) * T + tt) * NMEL + j] = (db - mu) * is;
-      }
-      for (int c = 4; c < 7; ++c) {
-        float mu = mean ? mean[c * NMEL + j] : 0.f, is = istd ? istd[c * NMEL + j] : 1.f;
-        out[(((long long)b * 7 + c) * T + tt) * NMEL + j] = (acc[c + 1] - mu) * is;
+      float accs[32][8];
+      for (int lane = 0; lane < 32; ++lane)
+        mel_task((const float4*)(s_x1 + v_base(f)), s_melent + sch.it0[wt] * 32 + lane, sch.nit[wt], accs[lane]);
+      for (int lane = 0; lane < 32; lane += 2) {
+        float acc[8];
+        for (int c = 0; c < 8; ++c) acc[c] = accs[lane][c] + accs[lane + 1][c];
+        const int j = 16 * wt + (lane >> 1);
+        const long long tt = t0 + f;
+        for (int c = 0; c < 4; ++c) {
+          float db = power_to_db_unclamped(acc[c]);
+          gmax[b * 4 + c] = std::max(gmax[b * 4 + c], db);
+          float mu = mean ? mean[c * NMEL + j] : 0.f, is = istd ? istd[c * NMEL + j] : 1.f;
+          out[(((long long)b * 7 + c) * T + tt) * NMEL + j] = (db - mu) * is;
+        }
+        for (int c = 4; c < 7; ++c) {
+          float mu = mean ? mean[c * NMEL + j] : 0.f, is = istd ? istd[c * NMEL + j] : 1.f;
+          out[(((long long)b * 7 + c) * T + tt) * NMEL + j] = (acc[c + 1] - mu) * is;
+        }
       }
     }
   }
