@@ -63,6 +63,7 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
     float2* s_x1 = reinterpret_cast<float2*>(smem + SmemLayout::off_x1);
     MelEntry* s_melent = reinterpret_cast<MelEntry*>(smem + SmemLayout::off_melent);
     int* s_melhdr = reinterpret_cast<int*>(smem + SmemLayout::off_melhdr);
+    float2* s_scale = reinterpret_cast<float2*>(smem + SmemLayout::off_scale);
 
     const int tid = threadIdx.x;
     int tile = blockIdx.x;
@@ -74,6 +75,10 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
     // constant tables -> smem (once per persistent CTA)
     for (int i = tid; i < MEL_MAXROWS * 32; i += NTHREADS) s_melent[i] = MelEntry{tab->mel_pos[i], tab->mel_w[i]};
     if (tid < 8) s_melhdr[tid] = tab->mel_hdr[tid];
+    for (int i = tid; i < NCH_FOA * NMEL; i += NTHREADS) {   // standardisation as one FMA: x*is + (-mu*is)
+        const float mu = mean ? mean[i] : 0.f, is = istd ? istd[i] : 1.f;
+        s_scale[i] = make_float2(is, -mu * is);
+    }
 
     // fixed roles
     const int q1 = tid / 25, n2 = tid - 25 * q1;             // stage 1 (tid < 150): lane group q1 -> fft g_of_q(q1)
@@ -92,7 +97,13 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
         __syncthreads();
 
         // ---- stage 1
-        if (tid < 150 && f1 < nf) stage1_task(s_samples, s_x1, q1, n2, cB, sB);
+        {
+            // keep the 48 window values from being hoisted out of the tile loop (they would be
+            // spilled to local memory and re-loaded, which costs more than the two FMAs each)
+            float cBt = cB, sBt = sB;
+            asm volatile("" : "+f"(cBt), "+f"(sBt));
+            if (tid < 150 && f1 < nf) stage1_task(s_samples, s_x1, q1, n2, cBt, sBt);
+        }
         __syncthreads();
 
         // samples are free: prefetch the next tile while stage 2 / mel run
@@ -129,6 +140,7 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
         __syncthreads();
 
         // ---- mel projection + log + standardise + store (static schedule, balanced over warps)
+        float* const out_tile = out + (((long long)b * NCH_FOA) * T + t0) * NMEL;
 #pragma unroll 1
         for (int qq = 0; qq < 3; ++qq) {
             const int code = mel_assign(warp, qq);
@@ -140,28 +152,24 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
                      s_melhdr[4 + wt], acc);
 #pragma unroll
             for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+            // uniform epilogue: lane 0 of a pair owns the 4 log-mel channels, lane 1 the 3 IV channels
             const int j = 16 * wt + (lane >> 1), part = lane & 1;
-            float* o = out + (((long long)b * NCH_FOA) * T + (t0 + f)) * NMEL + j;
-            const long long cs = (long long)T * NMEL;
-            if (part == 0) {                           // lane 0 of the pair: the 4 log-mel channels
+            float v[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float db = power_to_db_unclamped(acc[c]);
-                    const float mu = mean ? __ldg(mean + c * NMEL + j) : 0.f;
-                    const float is = istd ? __ldg(istd + c * NMEL + j) : 1.f;
-                    o[c * cs] = (db - mu) * is;
-                }
-            } else {                                   // lane 1: the 3 intensity channels
-                bool bad = false;
+            for (int i = 0; i < 4; ++i) {
+                const float db = power_to_db_unclamped(acc[i]);
+                v[i] = part ? acc[5 + (i < 3 ? i : 0)] : db;
+            }
+            if (part && !(v[0] == v[0] && v[1] == v[1] && v[2] == v[2])) atomicOr(flags, 1);  // datasets.py:277
+            const int c0i = part * 4;
+            const int T64 = T * NMEL;
+            float* o = out_tile + (c0i * T + f) * NMEL + j;
+            const float2* sc = s_scale + c0i * NMEL + j;
 #pragma unroll
-                for (int c = 4; c < 7; ++c) {
-                    const float v = acc[c + 1];
-                    bad |= !(v == v);
-                    const float mu = mean ? __ldg(mean + c * NMEL + j) : 0.f;
-                    const float is = istd ? __ldg(istd + c * NMEL + j) : 1.f;
-                    o[c * cs] = (v - mu) * is;
-                }
-                if (bad) atomicOr(flags, 1);  // reference prints + exit() on NaN (datasets.py:277)
+            for (int i = 0; i < 4; ++i) {
+                if (i == 3 && part) break;
+                const float2 k = sc[i * NMEL];
+                o[i * T64] = fmaf(v[i], k.x, k.y);
             }
         }
         // the barrier at the top of the next iteration orders these V reads before its stage 1
@@ -207,7 +215,7 @@ clamp_topdb_kernel(float* __restrict__ out, const float* __restrict__ mean, cons
     const float thr = mx - top_db;
     float th[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) th[q] = (thr - mu[q]) * is[q];
+    for (int q = 0; q < 4; ++q) th[q] = fmaf(thr, is[q], -mu[q] * is[q]);   // same form as the front-end epilogue
     for (int i = threadIdx.x; i < n4; i += 256) {
         float4 v = base[i];
         if (v.x < th[0] || v.y < th[1] || v.z < th[2] || v.w < th[3]) {

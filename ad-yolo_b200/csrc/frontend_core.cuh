@@ -61,7 +61,8 @@ struct SmemLayout {
     static constexpr int off_x1 = ((off_samples + NFFT_TILE * SPLANE * 4 + 15) / 16) * 16;  // float2 [TF][XFRAME]
     static constexpr int off_melent = ((off_x1 + TF * XFRAME * 8 + 15) / 16) * 16;  // MelEntry [56][32]
     static constexpr int off_melhdr = off_melent + MEL_MAXROWS * 32 * 8;     // int32 [8]: it0[4], nit[4]
-    static constexpr int total = ((off_melhdr + 8 * 4 + 15) / 16) * 16;
+    static constexpr int off_scale = off_melhdr + 8 * 4;                     // float2 [7][64]: (istd, -mean*istd)
+    static constexpr int total = ((off_scale + NCH_FOA * NMEL * 8 + 15) / 16) * 16;
 };
 static_assert(SmemLayout::off_x1 % 16 == 0 && SmemLayout::off_melent % 16 == 0, "alignment");
 static_assert(v_base(0) + 2 * NPOS * 2 <= XFRAME && x1_base(1) + 1200 <= XFRAME, "V / FFT data must fit in a frame block");
@@ -228,7 +229,9 @@ ADY_HD int mel_assign(int warp, int slot) {
 // librosa.power_to_db(ref=1, amin=1e-10) before the top_db clamp (datasets.py:265)
 ADY_HD float power_to_db_unclamped(float s) {
 #if defined(__CUDA_ARCH__)
-    return 3.0102999566398120f * __log2f(fmaxf(s, 1e-10f));   // 10 log10(s); MUFU.LG2 abs err ~1e-6 dB
+    float l;   // 10 log10(s) = 3.0103 log2(s); argument >= 1e-10 is never denormal -> bare MUFU.LG2
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fmaxf(s, 1e-10f)));
+    return 3.0102999566398120f * l;
 #else
     return 10.0f * __builtin_log10f(s > 1e-10f ? s : 1e-10f);
 #endif

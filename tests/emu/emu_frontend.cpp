@@ -73,11 +73,11 @@ extern "C" int emu_features_foa(const int16_t* audio, int B, long long N, const 
           float db = power_to_db_unclamped(acc[c]);
           gmax[b * 4 + c] = std::max(gmax[b * 4 + c], db);
           float mu = mean ? mean[c * NMEL + j] : 0.f, is = istd ? istd[c * NMEL + j] : 1.f;
-          out[(((long long)b * 7 + c) * T + tt) * NMEL + j] = (db - mu) * is;
+          out[(((long long)b * 7 + c) * T + tt) * NMEL + j] = fmaf(db, is, -mu * is);
         }
         for (int c = 4; c < 7; ++c) {
           float mu = mean ? mean[c * NMEL + j] : 0.f, is = istd ? istd[c * NMEL + j] : 1.f;
-          out[(((long long)b * 7 + c) * T + tt) * NMEL + j] = (acc[c + 1] - mu) * is;
+          out[(((long long)b * 7 + c) * T + tt) * NMEL + j] = fmaf(acc[c + 1], is, -mu * is);
         }
       }
     }
@@ -88,7 +88,7 @@ extern "C" int emu_features_foa(const int16_t* audio, int B, long long N, const 
     for (int t = 0; t < T; ++t) for (int j = 0; j < NMEL; ++j) {
       float mu = mean ? mean[c * NMEL + j] : 0.f, is = istd ? istd[c * NMEL + j] : 1.f;
       float& o = out[(((long long)b * 7 + c) * T + t) * NMEL + j];
-      o = std::max(o, (thr - mu) * is);
+      o = std::max(o, fmaf(thr, is, -mu * is));
     }
   }
   return 0;

@@ -81,12 +81,14 @@ def test_digital_silence_and_full_scale(A):
     N = 24000
     z = np.zeros((N, 4), np.int16)
     fs = np.full((N, 4), -32768, np.int16); fs[::2] = 32767
-    for clip, tol in ((z, 1e-4), (fs, 5e-4)):
+    for clip, tol, tol_iv in ((z, 1e-4, 5e-6), (fs, 5e-4, 2e-3)):
         out = A.features_batched(torch.from_numpy(clip).cuda()[None], None).cpu().numpy()[0]
         ref = F.features_foa_stack(clip)
         assert np.isfinite(out).all()
         assert _mel_err(out[:4], ref[:4]) < tol
-        assert np.abs(out[4:] - ref[4:]).max() < 5e-6
+        # full-scale Nyquist: the exact spectrum is ZERO in bins 2..598, so the reference's I/E is
+        # 0/eps there while FP32 leaves ~1e-7 * full-scale leakage that eps=1e-8 does not mask
+        assert np.abs(out[4:] - ref[4:]).max() < tol_iv
 
 
 def test_per_clip_reference_surface(A, gold, scaler2021, tmp_path):
