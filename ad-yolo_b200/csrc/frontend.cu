@@ -32,11 +32,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void issue_tile_copy(uint32_t* samples, const int16_t* __restrict__ audio,
                                                 long long N, int b, int t0, int nf) {
     const int tid = threadIdx.x;
-    const int pair = tid & 1, i0 = tid >> 1;  // element (idx = i0 + 80 i, pair), i = 0..14
+    // element (idx = i0 + 80 i, pair), i = 0..14: lanes 0-15 of a warp copy the (W,Y) words of 16
+    // consecutive samples, lanes 16-31 the (Z,X) words of the same samples (one 128-byte line)
+    const int pair = (tid >> 4) & 1, i0 = (tid >> 5) * 16 + (tid & 15);
     const int16_t* clip = audio + (long long)b * N * 4 + pair * 2;
     for (int f = 0; f < nf; ++f) {
         const int t = t0 + f;
-        uint32_t* dst = samples + q_of_g(2 * f + pair) * SPLANE + skew(i0);  // skew(i0 + 80 i) = skew(i0) + 85 i
+        uint32_t* dst = samples + splane_base(q_of_g(2 * f + pair)) + skew(i0);  // skew(i0 + 80 i) = skew(i0) + 85 i
         if (t > 0) {
             const int16_t* src = clip + ((long long)(t - 1) * HOP + i0) * 4;
 #pragma unroll

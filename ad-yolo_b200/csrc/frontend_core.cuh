@@ -51,6 +51,9 @@ constexpr int MEL_MAXNNZ = 1216;
 // sequence continuing across lane groups:
 //   x1_base(g+2) - x1_base(g) == 9 (mod 16 float2)   [25 float2 of the previous group]
 //   x1_base(2f+1) - x1_base(2f) == 8 (mod 16 float2) [stage 2a: adjacent A/B lanes, disjoint banks]
+// sample plane q starts at q*1275 words, the three (Z,X) planes shifted by 31 words so that the
+// A and B planes of one frame are 16 banks apart (conflict-free 2 x 16-lane cp.async stores)
+ADY_HD constexpr int splane_base(int q) { return q * SPLANE + (q >= 3 ? 31 : 0); }
 ADY_HD constexpr int g_of_q(int q) { return q < 3 ? 2 * q : 2 * (q - 3) + 1; }
 ADY_HD constexpr int q_of_g(int g) { return (g & 1) ? 3 + (g >> 1) : (g >> 1); }
 ADY_HD constexpr int x1_base(int g) { return (g >> 1) * XFRAME + (g & 1) * FS; }
@@ -58,7 +61,7 @@ ADY_HD constexpr int v_base(int f) { return ((f * XFRAME + 1) >> 1) << 1; }   //
 
 struct SmemLayout {
     static constexpr int off_samples = 0;                                   // uint32 [6][1275]
-    static constexpr int off_x1 = ((off_samples + NFFT_TILE * SPLANE * 4 + 15) / 16) * 16;  // float2 [TF][XFRAME]
+    static constexpr int off_x1 = ((off_samples + (NFFT_TILE * SPLANE + 31) * 4 + 15) / 16) * 16;  // float2 [TF][XFRAME]
     static constexpr int off_melent = ((off_x1 + TF * XFRAME * 8 + 15) / 16) * 16;  // MelEntry [56][32]
     static constexpr int off_melhdr = off_melent + MEL_MAXROWS * 32 * 8;     // int32 [8]: it0[4], nit[4]
     static constexpr int off_scale = off_melhdr + 8 * 4;                     // float2 [7][64]: (istd, -mean*istd)
@@ -99,7 +102,7 @@ ADY_HD void stage1_task(const uint32_t* __restrict__ samples, float2* __restrict
     constexpr float WIN_W0 = 0.5f / 65536.0f;
     constexpr float WIN_CA[48] = {-7.6293945312e-06f, -7.5641240034e-06f, -7.3694292167e-06f, -7.0486414529e-06f, -6.6072494796e-06f, -6.0528056358e-06f, -5.3947966094e-06f, -4.6444811173e-06f, -3.8146972656e-06f, -2.9196428861e-06f, -1.9746326073e-06f, -9.9583581711e-07f, -4.6716567961e-22f, 9.9583581711e-07f, 1.9746326073e-06f, 2.9196428861e-06f, 3.8146972656e-06f, 4.6444811173e-06f, 5.3947966094e-06f, 6.0528056358e-06f, 6.6072494796e-06f, 7.0486414529e-06f, 7.3694292167e-06f, 7.5641240034e-06f, 7.6293945312e-06f, 7.5641240034e-06f, 7.3694292167e-06f, 7.0486414529e-06f, 6.6072494796e-06f, 6.0528056358e-06f, 5.3947966094e-06f, 4.6444811173e-06f, 3.8146972656e-06f, 2.9196428861e-06f, 1.9746326073e-06f, 9.9583581711e-07f, 1.4014970388e-21f, -9.9583581711e-07f, -1.9746326073e-06f, -2.9196428861e-06f, -3.8146972656e-06f, -4.6444811173e-06f, -5.3947966094e-06f, -6.0528056358e-06f, -6.6072494796e-06f, -7.0486414529e-06f, -7.3694292167e-06f, -7.5641240034e-06f};
     constexpr float WIN_SA[48] = {0.0000000000e+00f, 9.9583581711e-07f, 1.9746326073e-06f, 2.9196428861e-06f, 3.8146972656e-06f, 4.6444811173e-06f, 5.3947966094e-06f, 6.0528056358e-06f, 6.6072494796e-06f, 7.0486414529e-06f, 7.3694292167e-06f, 7.5641240034e-06f, 7.6293945312e-06f, 7.5641240034e-06f, 7.3694292167e-06f, 7.0486414529e-06f, 6.6072494796e-06f, 6.0528056358e-06f, 5.3947966094e-06f, 4.6444811173e-06f, 3.8146972656e-06f, 2.9196428861e-06f, 1.9746326073e-06f, 9.9583581711e-07f, 9.3433135921e-22f, -9.9583581711e-07f, -1.9746326073e-06f, -2.9196428861e-06f, -3.8146972656e-06f, -4.6444811173e-06f, -5.3947966094e-06f, -6.0528056358e-06f, -6.6072494796e-06f, -7.0486414529e-06f, -7.3694292167e-06f, -7.5641240034e-06f, -7.6293945312e-06f, -7.5641240034e-06f, -7.3694292167e-06f, -7.0486414529e-06f, -6.6072494796e-06f, -6.0528056358e-06f, -5.3947966094e-06f, -4.6444811173e-06f, -3.8146972656e-06f, -2.9196428861e-06f, -1.9746326073e-06f, -9.9583581711e-07f};
-    const uint32_t* sp = samples + q * SPLANE + 51 * n2;
+    const uint32_t* sp = samples + splane_base(q) + 51 * n2;
     const int thr = 1200 - 48 * n2;  // wrap when 25*n1 >= thr
     cx<float> x[48];
 #pragma unroll

@@ -21,6 +21,7 @@ namespace ady {
 
 struct MelSchedule {
     int it0[4], nit[4];                 // first iteration row / iteration count of each warp-task
+    long cost[4];                       // LDS.128 quarter-wavefronts per V load of each warp-task
     int total_rows;
     std::vector<MelEntry> ent;          // [total_rows][32]
 };
@@ -59,44 +60,83 @@ inline bool build_mel_schedule(const float* mel, MelSchedule& s) {
         s.it0[wt] = row;
         s.nit[wt] = nit;
         s.ent.resize((size_t)(row + nit) * 32, MelEntry{0, 0.f});
-        // greedy conflict-avoiding order: per iteration and quarter-warp, lanes with the fewest
-        // choices pick first, taking an entry whose slot (pos mod 8) is still free
-        std::vector<std::vector<char>> used(32);
-        for (int l = 0; l < 32; ++l) used[l].assign(lanes[l].size(), 0);
-        for (int it = 0; it < nit; ++it) {
-            for (int q = 0; q < 4; ++q) {
-                bool slot_taken[8] = {false, false, false, false, false, false, false, false};
-                int order[8];
-                for (int i = 0; i < 8; ++i) order[i] = 8 * q + i;
-                // lanes with fewer remaining entries first (less freedom)
-                for (int a = 0; a < 8; ++a)
-                    for (int b = a + 1; b < 8; ++b) {
-                        int ra = 0, rb = 0;
-                        for (char u : used[order[a]]) ra += !u;
-                        for (char u : used[order[b]]) rb += !u;
-                        if (rb < ra) { int t = order[a]; order[a] = order[b]; order[b] = t; }
+        // Randomised greedy with restarts (deterministic LCG).  Per iteration and quarter-warp the
+        // lanes with the least slack choose first; a lane takes an entry whose 16-byte slot
+        // (pos mod 8) is still free in this quarter, may idle (padding) while it has slack, and
+        // otherwise takes the least loaded slot.  Cost = sum over quarter-iterations of the
+        // maximum slot multiplicity == LDS.128 wavefronts.
+        unsigned long long rng = 0x9E3779B97F4A7C15ull + wt;
+        auto next = [&rng]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (unsigned)(rng >> 33); };
+        long best_cost = -1;
+        std::vector<int> best((size_t)nit * 32, -1), cur((size_t)nit * 32);
+        for (int attempt = 0; attempt < 300; ++attempt) {
+            std::vector<std::vector<int>> rem(32);
+            for (int l = 0; l < 32; ++l) {
+                rem[l].resize(lanes[l].size());
+                for (size_t e = 0; e < lanes[l].size(); ++e) rem[l][e] = (int)e;
+                for (size_t e = rem[l].size(); e > 1; --e) { size_t o = next() % e; int t = rem[l][e - 1]; rem[l][e - 1] = rem[l][o]; rem[l][o] = t; }
+            }
+            std::fill(cur.begin(), cur.end(), -1);
+            long cost = 0;
+            bool ok = true;
+            for (int it = 0; it < nit && ok; ++it) {
+                const int left = nit - it;
+                for (int q = 0; q < 4; ++q) {
+                    int load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    int order[8];
+                    for (int i = 0; i < 8; ++i) order[i] = 8 * q + i;
+                    for (int i = 7; i > 0; --i) { int o = next() % (i + 1); int t = order[i]; order[i] = order[o]; order[o] = t; }
+                    for (int a2 = 0; a2 < 8; ++a2)            // stable-ish sort: most remaining first
+                        for (int b2 = a2 + 1; b2 < 8; ++b2)
+                            if (rem[order[b2]].size() > rem[order[a2]].size()) { int t = order[a2]; order[a2] = order[b2]; order[b2] = t; }
+                    for (int a2 = 0; a2 < 8; ++a2) {
+                        const int l = order[a2];
+                        if (rem[l].empty()) continue;
+                        const int slack = left - (int)rem[l].size();
+                        int pick = -1, pick_score = -1;
+                        for (size_t e = 0; e < rem[l].size(); ++e) {
+                            const int slot = lanes[l][rem[l][e]].pos & 7;
+                            if (load[slot]) continue;
+                            int score = 0;                      // prefer the slot most common in the own list
+                            for (int e2 : rem[l]) score += ((lanes[l][e2].pos & 7) == slot);
+                            if (score > pick_score) { pick_score = score; pick = (int)e; }
+                        }
+                        if (pick < 0) {
+                            if (slack > 0) continue;            // idle this step (zero-weight padding)
+                            int bl = 1 << 30;
+                            for (size_t e = 0; e < rem[l].size(); ++e) {
+                                const int ld = load[lanes[l][rem[l][e]].pos & 7];
+                                if (ld < bl) { bl = ld; pick = (int)e; }
+                            }
+                        }
+                        const int eidx = rem[l][pick];
+                        rem[l].erase(rem[l].begin() + pick);
+                        load[lanes[l][eidx].pos & 7]++;
+                        cur[(size_t)it * 32 + l] = eidx;
                     }
-                for (int a = 0; a < 8; ++a) {
-                    const int l = order[a];
-                    int pick = -1;
-                    for (size_t e = 0; e < lanes[l].size(); ++e)
-                        if (!used[l][e] && !slot_taken[lanes[l][e].pos & 7]) { pick = (int)e; break; }
-                    if (pick < 0)
-                        for (size_t e = 0; e < lanes[l].size(); ++e)
-                            if (!used[l][e]) { pick = (int)e; break; }
-                    if (pick < 0) continue;  // lane exhausted: zero-weight padding stays
-                    // must finish within nit iterations: a lane may not idle while it still has
-                    // more entries than iterations left (never happens: sizes <= nit)
-                    used[l][pick] = 1;
-                    slot_taken[lanes[l][pick].pos & 7] = true;
-                    s.ent[(size_t)(row + it) * 32 + l] = lanes[l][pick];
+                    int mx = 1;
+                    for (int i = 0; i < 8; ++i) mx = load[i] > mx ? load[i] : mx;
+                    cost += mx;
                 }
             }
+            for (int l = 0; l < 32; ++l) ok = ok && rem[l].empty();
+            if (ok && (best_cost < 0 || cost < best_cost)) { best_cost = cost; best = cur; }
         }
-        // safety: every entry placed
-        for (int l = 0; l < 32; ++l)
-            for (char u : used[l])
-                if (!u) return false;
+        if (best_cost < 0) return false;
+        for (int it = 0; it < nit; ++it)
+            for (int l = 0; l < 32; ++l) {
+                const int e = best[(size_t)it * 32 + l];
+                if (e >= 0) s.ent[(size_t)(row + it) * 32 + l] = lanes[l][e];
+                else {
+                    // padding: weight 0 at a position already read by a neighbour lane of the same
+                    // quarter (identical address -> broadcast, no extra wavefront)
+                    int p = 0;
+                    for (int l2 = 8 * (l / 8); l2 < 8 * (l / 8) + 8; ++l2)
+                        if (best[(size_t)it * 32 + l2] >= 0) { p = lanes[l2][best[(size_t)it * 32 + l2]].pos; break; }
+                    s.ent[(size_t)(row + it) * 32 + l] = MelEntry{p, 0.f};
+                }
+            }
+        s.cost[wt] = best_cost;
         row += nit;
     }
     s.total_rows = row;

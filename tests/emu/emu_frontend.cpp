@@ -28,11 +28,11 @@ extern "C" int emu_features_foa(const int16_t* audio, int B, long long N, const 
     const int b = tile / tpc, tb = tile % tpc, t0 = tb * TF, nf = std::min(TF, T - t0);
     // ---- copy (same element mapping as issue_tile_copy)
     for (int tid = 0; tid < NTHREADS; ++tid) {
-      const int pair = tid & 1, i0 = tid >> 1;
+      const int pair = (tid >> 4) & 1, i0 = (tid >> 5) * 16 + (tid & 15);
       const int16_t* clip = audio + (long long)b * N * 4 + pair * 2;
       for (int f = 0; f < nf; ++f) {
         const int t = t0 + f;
-        uint32_t* dst = s_samples + q_of_g(2 * f + pair) * SPLANE + skew(i0);
+        uint32_t* dst = s_samples + splane_base(q_of_g(2 * f + pair)) + skew(i0);
         for (int i = 0; i < 15; ++i) {
           const int idx = i0 + 80 * i;
           long long m = t > 0 ? (long long)(t - 1) * HOP + idx : (idx < HOP ? HOP - idx : idx - HOP);
