@@ -159,38 +159,40 @@ assign_rows_kernel(const float* __restrict__ logit, const float* __restrict__ ta
 }
 
 // ------------------------------------------------------------------------------------------------
-// BCE pieces exactly as ATen (Loss.cu binary_cross_entropy_out_cuda / _backward):
+// BCE pieces as ATen defines them (Loss.cu binary_cross_entropy_out_cuda / _backward):
 //   loss = (t-1) * max(log1p(-p), -100) - t * max(log(p), -100)
 //   dL/dp = (p - t) / max((1-p) p, 1e-12);   dp/dx = (1-p) p
+// evaluated with the fast MUFU paths (ex2 / rcp / lg2): these terms only enter sums and
+// gradients gated at 1e-5 relative (the bit-exact part is the assignment above); saturation
+// behaves identically (p == 1 -> log(0) = -inf -> clamped to -100).
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float bce_fwd(float p, float t) {
-    const float lp = fmaxf(logf(p), -100.f), l1 = fmaxf(log1pf(-p), -100.f);
+    const float lp = fmaxf(__logf(p), -100.f), l1 = fmaxf(__logf(1.0f - p), -100.f);
     return (t - 1.f) * l1 - t * lp;
 }
 __device__ __forceinline__ float bce_bwd_logit(float p, float t) {
     const float q = (1.f - p) * p;
-    return (p - t) / fmaxf(q, 1e-12f) * q;
+    return q >= 1e-12f ? (p - t) : (p - t) * q * 1e12f;
 }
 
 constexpr int LA_THREADS = 256;
-constexpr int LA_TILE = 256;   // anchors per tile == threads (tile base is 16-byte aligned for any channel count)
 
-// Per tile of 256 anchors, three divergence-free passes:
-//   1. thread = anchor: objectness logit -> sigmoid, BCE sums, objectness gradient (smem);
-//      positive anchors (any threshold) are appended to a compact list
-//   2. (grad only) thread = 4 consecutive elements, float4 coalesced: objectness gradient from
-//      smem, zeros for the class channels, scaled angular partials for (u, v)
-//   3. work item = (positive anchor, class): class BCE sums / gradients (few items, uniform work)
+// Warp-autonomous pass over the anchors (no block barriers, no shared memory); a warp owns groups
+// of 32 consecutive anchors (group base is 16-byte aligned for any channel count):
+//   1. lane = anchor: objectness logit -> sigmoid, BCE sums, objectness gradient (kept in the lane)
+//   2. (grad only) lane = 4 consecutive elements of the group's 32*CH logits, float4 coalesced:
+//      objectness gradient fetched from the owning lane by shuffle, zeros for the class channels,
+//      scaled angular partials for (u, v)
+//   3. for every positive anchor of the group (ballot): lane = class -> class BCE sums / gradients
 // do_sums: accumulate the BCE sums (forward); grad != NULL: write gscale * d loss / d logit.
 __global__ void __launch_bounds__(LA_THREADS)
 loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCfg cfg,
                    const unsigned long long* __restrict__ state, const float2* __restrict__ ang_grad,
                    LossAccum* __restrict__ acc, float* __restrict__ grad, const float* __restrict__ gscale,
                    int do_sums) {
-    __shared__ float s_go[LA_TILE];
-    __shared__ int s_pos_list[LA_TILE];
-    __shared__ int s_npos;
     const unsigned CH = cfg.nb_classes + 3, C = cfg.nb_classes;
     const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
 
     // per-threshold normalisers (counts are final: assign_rows_kernel has completed)
     const double gs = gscale ? (double)gscale[0] : 1.0;   // upstream d(total)/d(loss), device scalar
@@ -207,52 +209,56 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
     const float w_ang = (float)(gs * cfg.gain_ang / (180.0 * n_ang));
     const unsigned long long OBJ_ANY = 0x0001000100010001ull;
 
-    double s_pos[ADY_MAX_THR] = {0, 0, 0, 0}, s_neg[ADY_MAX_THR] = {0, 0, 0, 0}, s_cls[ADY_MAX_THR] = {0, 0, 0, 0};
-    if (threadIdx.x == 0) s_npos = 0;
-    __syncthreads();
+    // per-thread partial sums stay in FP32 (a thread sees only tens of anchors); they are widened
+    // to FP64 for the warp reduction and the global accumulation
+    float s_pos[ADY_MAX_THR] = {0, 0, 0, 0}, s_neg[ADY_MAX_THR] = {0, 0, 0, 0}, s_cls[ADY_MAX_THR] = {0, 0, 0, 0};
 
-    const long long n_tiles = (n_anchor + LA_TILE - 1) / LA_TILE;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long a_base = tile * LA_TILE;
-        const unsigned na = (unsigned)min((long long)LA_TILE, n_anchor - a_base);
-        const unsigned nel = na * CH;
-        const float* src = logit + a_base * CH;
-        float* dst = grad ? grad + a_base * CH : nullptr;
+    const long long n_groups = (n_anchor + 31) / 32;
+    const long long warp0 = ((long long)blockIdx.x * LA_THREADS + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * LA_THREADS) >> 5;
+    for (long long grp = warp0; grp < n_groups; grp += n_warps) {
+        const long long a0 = grp * 32;
+        const unsigned na = (unsigned)min(32LL, n_anchor - a0);
+        const float* src = logit + a0 * CH;
+        float* dst = grad ? grad + a0 * CH : nullptr;
 
-        // ---- pass 1: objectness, one anchor per thread
-        if (threadIdx.x < na) {
-            const unsigned long long st = state[a_base + threadIdx.x];
-            const float p = sigmoid_torch(src[threadIdx.x * CH]);
+        // ---- pass 1: objectness, lane = anchor
+        const bool valid = (unsigned)lane < na;
+        const unsigned long long st = valid ? state[a0 + lane] : 0ull;
+        float go = 0.f;
+        if (valid) {
+            const float p = sigmoid_fast(src[(unsigned)lane * CH]);
             const float g_pos = bce_bwd_logit(p, 1.f), g_neg = bce_bwd_logit(p, 0.f);
             float l_pos = 0.f, l_neg = 0.f;
             if (do_sums) { l_pos = bce_fwd(p, 1.f); l_neg = bce_fwd(p, 0.f); }
-            float go = 0.f;
 #pragma unroll
             for (int i = 0; i < ADY_MAX_THR; ++i) {
                 if (i >= cfg.n_thr) break;
                 if ((st >> (16 * i)) & 1ull) { s_pos[i] += l_pos; go += w_pos[i] * g_pos; }
                 else                         { s_neg[i] += l_neg; go += w_neg[i] * g_neg; }
             }
-            s_go[threadIdx.x] = go;
-            if (st & OBJ_ANY) s_pos_list[atomicAdd(&s_npos, 1)] = threadIdx.x;
         }
-        __syncthreads();
+        unsigned posmask = __ballot_sync(FULL, valid && (st & OBJ_ANY));
 
-        // ---- pass 2: coalesced gradient write (objectness, zeroed classes, angular u/v)
+        // ---- pass 2: coalesced gradient write (objectness via shuffle, zeroed classes, angular u/v)
         if (dst) {
-            for (unsigned el = threadIdx.x * 4; el < nel; el += LA_THREADS * 4) {
-                unsigned a = el / CH, ch = el - a * CH;
+            const unsigned nel = na * CH;
+            const unsigned iters = (nel + 127) / 128;     // warp-uniform
+            for (unsigned k = 0; k < iters; ++k) {
+                const unsigned el = k * 128 + (unsigned)lane * 4;
+                unsigned al = el / CH, ch = el - al * CH;
                 float g[4];
 #pragma unroll
                 for (unsigned q = 0; q < 4; ++q) {
+                    const float go_al = __shfl_sync(FULL, go, (int)(al & 31u));
                     float v = 0.f;
-                    if (ch == 0) v = s_go[a < na ? a : 0];
-                    else if (ch > C && a < na) {
-                        const float2 ag = ang_grad[a_base + a];
+                    if (ch == 0) v = go_al;
+                    else if (ch > C && al < na) {
+                        const float2 ag = ang_grad[a0 + al];
                         v = (ch == C + 1 ? ag.x : ag.y) * w_ang;
                     }
                     g[q] = v;
-                    if (++ch == CH) { ch = 0; ++a; }
+                    if (++ch == CH) { ch = 0; ++al; }
                 }
                 if (el + 4 <= nel) *reinterpret_cast<float4*>(dst + el) = make_float4(g[0], g[1], g[2], g[3]);
                 else {
@@ -260,51 +266,52 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
                     for (unsigned q = 0; q < 4; ++q) if (el + q < nel) dst[el + q] = g[q];
                 }
             }
-            __syncthreads();   // class gradients of positive anchors overwrite the zeros below
+            __syncwarp();   // class gradients of positive anchors overwrite the zeros written above
         }
 
-        // ---- pass 3: (positive anchor, class) items
-        const unsigned n_items = (unsigned)s_npos * C;
-        for (unsigned it = threadIdx.x; it < n_items; it += LA_THREADS) {
-            const unsigned pi = it / C, c = it - pi * C;
-            const unsigned a = s_pos_list[pi];
-            const unsigned long long st = state[a_base + a];
-            const float pc = sigmoid_torch(src[a * CH + 1 + c]);
-            const float g1 = bce_bwd_logit(pc, 1.f), g0 = bce_bwd_logit(pc, 0.f);
-            float l1 = 0.f, l0 = 0.f;
-            if (do_sums) { l1 = bce_fwd(pc, 1.f); l0 = bce_fwd(pc, 0.f); }
-            float gc = 0.f;
+        // ---- pass 3: positive anchors, lane = class
+        while (posmask) {
+            const int al = __ffs(posmask) - 1;
+            posmask &= posmask - 1;
+            const unsigned long long sta = __shfl_sync(FULL, st, al);
+            for (unsigned c = lane; c < C; c += 32) {
+                const float pc = sigmoid_fast(src[(unsigned)al * CH + 1 + c]);
+                const float g1 = bce_bwd_logit(pc, 1.f), g0 = bce_bwd_logit(pc, 0.f);
+                float l1 = 0.f, l0 = 0.f;
+                if (do_sums) { l1 = bce_fwd(pc, 1.f); l0 = bce_fwd(pc, 0.f); }
+                float gc = 0.f;
 #pragma unroll
-            for (int i = 0; i < ADY_MAX_THR; ++i) {
-                if (i >= cfg.n_thr) break;
-                if ((st >> (16 * i)) & 1ull) {
-                    const bool t = (st >> (16 * i + 1 + c)) & 1ull;
-                    s_cls[i] += t ? l1 : l0;
-                    gc += w_cls[i] * (t ? g1 : g0);
+                for (int i = 0; i < ADY_MAX_THR; ++i) {
+                    if (i >= cfg.n_thr) break;
+                    if ((sta >> (16 * i)) & 1ull) {
+                        const bool t = (sta >> (16 * i + 1 + c)) & 1ull;
+                        s_cls[i] += t ? l1 : l0;
+                        gc += w_cls[i] * (t ? g1 : g0);
+                    }
                 }
+                if (dst) dst[(unsigned)al * CH + 1 + c] = gc;
             }
-            if (dst) dst[a * CH + 1 + c] = gc;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) s_npos = 0;
-        __syncthreads();
     }
     if (!do_sums) return;
+    double d_pos[ADY_MAX_THR], d_neg[ADY_MAX_THR], d_cls[ADY_MAX_THR];
+#pragma unroll
+    for (int i = 0; i < ADY_MAX_THR; ++i) { d_pos[i] = s_pos[i]; d_neg[i] = s_neg[i]; d_cls[i] = s_cls[i]; }
 #pragma unroll
     for (int o = 16; o; o >>= 1)
 #pragma unroll
         for (int i = 0; i < ADY_MAX_THR; ++i) {
-            s_pos[i] += __shfl_xor_sync(0xffffffffu, s_pos[i], o);
-            s_neg[i] += __shfl_xor_sync(0xffffffffu, s_neg[i], o);
-            s_cls[i] += __shfl_xor_sync(0xffffffffu, s_cls[i], o);
+            d_pos[i] += __shfl_xor_sync(FULL, d_pos[i], o);
+            d_neg[i] += __shfl_xor_sync(FULL, d_neg[i], o);
+            d_cls[i] += __shfl_xor_sync(FULL, d_cls[i], o);
         }
     if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < ADY_MAX_THR; ++i)
             if (i < cfg.n_thr) {
-                atomicAdd(&acc->s_pos[i], s_pos[i]);
-                atomicAdd(&acc->s_neg[i], s_neg[i]);
-                atomicAdd(&acc->s_cls[i], s_cls[i]);
+                atomicAdd(&acc->s_pos[i], d_pos[i]);
+                atomicAdd(&acc->s_neg[i], d_neg[i]);
+                atomicAdd(&acc->s_cls[i], d_cls[i]);
             }
     }
 }
@@ -367,7 +374,7 @@ int launch_loss(const float* logit, const float* target, long long M, int B, int
     int dev = 0, sms = 0;
     ADY_CUDA_CHECK(cudaGetDevice(&dev));
     ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    long long blocks = (n_anchor + LA_TILE - 1) / LA_TILE;
+    long long blocks = (n_anchor + LA_THREADS - 1) / LA_THREADS;
     const long long cap = (long long)sms * 8;
     if (blocks > cap) blocks = cap;
     loss_anchor_kernel<<<(int)blocks, LA_THREADS, 0, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out,
@@ -392,7 +399,7 @@ int launch_loss_backward(const float* logit, int B, int T, const AssignCfg& cfg,
     int dev = 0, sms = 0;
     ADY_CUDA_CHECK(cudaGetDevice(&dev));
     ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    long long blocks = (n_anchor + LA_TILE - 1) / LA_TILE;
+    long long blocks = (n_anchor + LA_THREADS - 1) / LA_THREADS;
     const long long cap = (long long)sms * 8;
     if (blocks > cap) blocks = cap;
     loss_anchor_kernel<<<(int)blocks, LA_THREADS, 0, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out,
