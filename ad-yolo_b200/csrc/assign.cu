@@ -177,6 +177,20 @@ __device__ __forceinline__ float bce_bwd_logit(float p, float t) {
 
 constexpr int LA_THREADS = 256;
 
+// Normalisers of the means of loss.py:236-249, computed once from the final counts (FP64 division
+// by every thread of the big kernel was 20 % of its stall samples).
+__global__ void loss_weights_kernel(long long n_anchor, AssignCfg cfg, LossAccum* __restrict__ acc) {
+    const int i = threadIdx.x;
+    if (i < ADY_MAX_THR) {
+        const double np_ = i < cfg.n_thr ? (double)acc->n_pos[i] : 0.0;
+        const double nn_ = (double)n_anchor - np_;
+        acc->w_pos[i] = i < cfg.n_thr ? (float)(cfg.gain_obj / (cfg.n_thr * np_)) : 0.f;
+        acc->w_neg[i] = i < cfg.n_thr ? (float)(cfg.gain_nonobj / (cfg.n_thr * nn_)) : 0.f;
+        acc->w_cls[i] = i < cfg.n_thr ? (float)(cfg.gain_cls / (cfg.n_thr * np_ * cfg.nb_classes)) : 0.f;
+    }
+    if (i == 0) acc->w_ang = (float)(cfg.gain_ang / (180.0 * (double)acc->ang_cnt));
+}
+
 // Warp-autonomous pass over the anchors (no block barriers, no shared memory); a warp owns groups
 // of 32 consecutive anchors (group base is 16-byte aligned for any channel count):
 //   1. lane = anchor: objectness logit -> sigmoid, BCE sums, objectness gradient (kept in the lane)
@@ -194,19 +208,16 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
 
-    // per-threshold normalisers (counts are final: assign_rows_kernel has completed)
-    const double gs = gscale ? (double)gscale[0] : 1.0;   // upstream d(total)/d(loss), device scalar
+    // per-threshold normalisers (loss_weights_kernel) times the upstream gradient (device scalar)
+    const float gs = gscale ? gscale[0] : 1.0f;
     float w_pos[ADY_MAX_THR], w_neg[ADY_MAX_THR], w_cls[ADY_MAX_THR];
 #pragma unroll
     for (int i = 0; i < ADY_MAX_THR; ++i) {
-        const double np_ = i < cfg.n_thr ? (double)acc->n_pos[i] : 0.0;
-        const double nn_ = (double)n_anchor - np_;
-        w_pos[i] = i < cfg.n_thr ? (float)(gs * cfg.gain_obj / (cfg.n_thr * np_)) : 0.f;
-        w_neg[i] = i < cfg.n_thr ? (float)(gs * cfg.gain_nonobj / (cfg.n_thr * nn_)) : 0.f;
-        w_cls[i] = i < cfg.n_thr ? (float)(gs * cfg.gain_cls / (cfg.n_thr * np_ * C)) : 0.f;
+        w_pos[i] = gs * acc->w_pos[i];
+        w_neg[i] = gs * acc->w_neg[i];
+        w_cls[i] = gs * acc->w_cls[i];
     }
-    const double n_ang = (double)acc->ang_cnt;
-    const float w_ang = (float)(gs * cfg.gain_ang / (180.0 * n_ang));
+    const float w_ang = gs * acc->w_ang;
     const unsigned long long OBJ_ANY = 0x0001000100010001ull;
 
     // per-thread partial sums stay in FP32 (a thread sees only tens of anchors); they are widened
@@ -216,6 +227,14 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
     const long long n_groups = (n_anchor + 31) / 32;
     const long long warp0 = ((long long)blockIdx.x * LA_THREADS + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * LA_THREADS) >> 5;
+    // software pipeline: the label word and objectness logit of the next group are in flight
+    // while the current group is processed
+    unsigned long long st_n = 0ull;
+    float x_n = 0.f;
+    if (warp0 < n_groups && warp0 * 32 + lane < n_anchor) {
+        st_n = state[warp0 * 32 + lane];
+        x_n = logit[(warp0 * 32 + lane) * CH];
+    }
     for (long long grp = warp0; grp < n_groups; grp += n_warps) {
         const long long a0 = grp * 32;
         const unsigned na = (unsigned)min(32LL, n_anchor - a0);
@@ -224,10 +243,16 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
 
         // ---- pass 1: objectness, lane = anchor
         const bool valid = (unsigned)lane < na;
-        const unsigned long long st = valid ? state[a0 + lane] : 0ull;
+        const unsigned long long st = st_n;
+        const float x_obj = x_n;
+        {
+            const long long an = (grp + n_warps) * 32 + lane;
+            if (grp + n_warps < n_groups && an < n_anchor) { st_n = state[an]; x_n = logit[an * CH]; }
+            else { st_n = 0ull; x_n = 0.f; }
+        }
         float go = 0.f;
         if (valid) {
-            const float p = sigmoid_fast(src[(unsigned)lane * CH]);
+            const float p = sigmoid_fast(x_obj);
             const float g_pos = bce_bwd_logit(p, 1.f), g_neg = bce_bwd_logit(p, 0.f);
             float l_pos = 0.f, l_neg = 0.f;
             if (do_sums) { l_pos = bce_fwd(p, 1.f); l_neg = bce_fwd(p, 0.f); }
@@ -269,12 +294,16 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
             __syncwarp();   // class gradients of positive anchors overwrite the zeros written above
         }
 
-        // ---- pass 3: positive anchors, lane = class
-        while (posmask) {
-            const int al = __ffs(posmask) - 1;
-            posmask &= posmask - 1;
-            const unsigned long long sta = __shfl_sync(FULL, st, al);
-            for (unsigned c = lane; c < C; c += 32) {
+        // ---- pass 3: (positive anchor, class) items spread over the lanes; the loop count is
+        // warp-uniform so the shuffles that fetch the anchor's label word are convergent
+        const unsigned n_items = (unsigned)__popc(posmask) * C;
+        for (unsigned base = 0; base < n_items; base += 32) {
+            const unsigned it = base + lane;
+            const bool on = it < n_items;
+            const unsigned pi = on ? it / C : 0u, c = on ? it - pi * C : 0u;
+            const int al = (int)__fns(posmask, 0, (int)pi + 1);       // index of the pi-th positive anchor
+            const unsigned long long sta = __shfl_sync(FULL, st, al & 31);
+            if (on) {
                 const float pc = sigmoid_fast(src[(unsigned)al * CH + 1 + c]);
                 const float g1 = bce_bwd_logit(pc, 1.f), g0 = bce_bwd_logit(pc, 0.f);
                 float l1 = 0.f, l0 = 0.f;
@@ -374,6 +403,8 @@ int launch_loss(const float* logit, const float* target, long long M, int B, int
     int dev = 0, sms = 0;
     ADY_CUDA_CHECK(cudaGetDevice(&dev));
     ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    loss_weights_kernel<<<1, 32, 0, stream>>>(n_anchor, cfg, acc);
+    ADY_LAUNCH_CHECK("loss_weights_kernel");
     long long blocks = (n_anchor + LA_THREADS - 1) / LA_THREADS;
     const long long cap = (long long)sms * 8;
     if (blocks > cap) blocks = cap;

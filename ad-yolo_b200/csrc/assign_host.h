@@ -29,6 +29,8 @@ struct LossAccum {
     unsigned long long ang_cnt;
     unsigned long long n_pos[ADY_MAX_THR];
     double s_pos[ADY_MAX_THR], s_neg[ADY_MAX_THR], s_cls[ADY_MAX_THR];
+    float w_pos[ADY_MAX_THR], w_neg[ADY_MAX_THR], w_cls[ADY_MAX_THR];   // gain / (n_thr * count), by loss_weights_kernel
+    float w_ang, pad_f[3];
     int bad_rows;
     int pad;
 };
