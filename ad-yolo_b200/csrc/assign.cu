@@ -227,28 +227,39 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
     const long long n_groups = (n_anchor + 31) / 32;
     const long long warp0 = ((long long)blockIdx.x * LA_THREADS + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * LA_THREADS) >> 5;
-    // software pipeline: the label word and objectness logit of the next group are in flight
-    // while the current group is processed
-    unsigned long long st_n = 0ull;
-    float x_n = 0.f;
-    if (warp0 < n_groups && warp0 * 32 + lane < n_anchor) {
-        st_n = state[warp0 * 32 + lane];
-        x_n = logit[(warp0 * 32 + lane) * CH];
-    }
     for (long long grp = warp0; grp < n_groups; grp += n_warps) {
         const long long a0 = grp * 32;
         const unsigned na = (unsigned)min(32LL, n_anchor - a0);
+        const unsigned nel = na * CH;
         const float* src = logit + a0 * CH;
         float* dst = grad ? grad + a0 * CH : nullptr;
 
-        // ---- pass 1: objectness, lane = anchor
+        // ---- pass 1: objectness, lane = anchor.  The group's 32*CH logits are read once with
+        // coalesced float4 loads (up to 5 per lane, all in flight together); the objectness logit of
+        // anchor `lane` (element lane*CH) is then fetched from the lane that holds it by shuffle.
         const bool valid = (unsigned)lane < na;
-        const unsigned long long st = st_n;
-        const float x_obj = x_n;
-        {
-            const long long an = (grp + n_warps) * 32 + lane;
-            if (grp + n_warps < n_groups && an < n_anchor) { st_n = state[an]; x_n = logit[an * CH]; }
-            else { st_n = 0ull; x_n = 0.f; }
+        const unsigned long long st = valid ? state[a0 + lane] : 0ull;
+        float4 xv[5];
+#pragma unroll
+        for (unsigned k = 0; k < 5; ++k) {
+            const unsigned el = k * 128 + (unsigned)lane * 4;
+            if (el + 4 <= nel) xv[k] = *reinterpret_cast<const float4*>(src + el);
+            else {
+                xv[k].x = el < nel ? src[el] : 0.f;
+                xv[k].y = el + 1 < nel ? src[el + 1] : 0.f;
+                xv[k].z = el + 2 < nel ? src[el + 2] : 0.f;
+                xv[k].w = 0.f;
+            }
+        }
+        const unsigned e_obj = (unsigned)lane * CH;
+        const unsigned k_src = e_obj >> 7, l_src = (e_obj & 127u) >> 2, c_src = e_obj & 3u;
+        float x_obj = 0.f;
+#pragma unroll
+        for (unsigned k = 0; k < 5; ++k) {
+            const float vx = __shfl_sync(FULL, xv[k].x, (int)l_src), vy = __shfl_sync(FULL, xv[k].y, (int)l_src);
+            const float vz = __shfl_sync(FULL, xv[k].z, (int)l_src), vw = __shfl_sync(FULL, xv[k].w, (int)l_src);
+            const float v = c_src == 0 ? vx : (c_src == 1 ? vy : (c_src == 2 ? vz : vw));
+            if (k == k_src) x_obj = v;
         }
         float go = 0.f;
         if (valid) {
@@ -267,7 +278,6 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
 
         // ---- pass 2: coalesced gradient write (objectness via shuffle, zeroed classes, angular u/v)
         if (dst) {
-            const unsigned nel = na * CH;
             const unsigned iters = (nel + 127) / 128;     // warp-uniform
             for (unsigned k = 0; k < iters; ++k) {
                 const unsigned el = k * 128 + (unsigned)lane * 4;
