@@ -333,25 +333,29 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
         }
     }
     if (!do_sums) return;
-    double d_pos[ADY_MAX_THR], d_neg[ADY_MAX_THR], d_cls[ADY_MAX_THR];
+    // warp reduce (FP64) -> block reduce through shared memory -> one atomic per block and sum:
+    // per-warp atomics on a handful of addresses serialise in L2 (10^5 of them cost ~10^2 us)
+    __shared__ double s_red[LA_THREADS / 32][3 * ADY_MAX_THR];
+    double d[3 * ADY_MAX_THR];
 #pragma unroll
-    for (int i = 0; i < ADY_MAX_THR; ++i) { d_pos[i] = s_pos[i]; d_neg[i] = s_neg[i]; d_cls[i] = s_cls[i]; }
+    for (int i = 0; i < ADY_MAX_THR; ++i) { d[i] = s_pos[i]; d[ADY_MAX_THR + i] = s_neg[i]; d[2 * ADY_MAX_THR + i] = s_cls[i]; }
 #pragma unroll
     for (int o = 16; o; o >>= 1)
 #pragma unroll
-        for (int i = 0; i < ADY_MAX_THR; ++i) {
-            d_pos[i] += __shfl_xor_sync(FULL, d_pos[i], o);
-            d_neg[i] += __shfl_xor_sync(FULL, d_neg[i], o);
-            d_cls[i] += __shfl_xor_sync(FULL, d_cls[i], o);
-        }
+        for (int i = 0; i < 3 * ADY_MAX_THR; ++i) d[i] += __shfl_xor_sync(FULL, d[i], o);
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < ADY_MAX_THR; ++i)
-            if (i < cfg.n_thr) {
-                atomicAdd(&acc->s_pos[i], d_pos[i]);
-                atomicAdd(&acc->s_neg[i], d_neg[i]);
-                atomicAdd(&acc->s_cls[i], d_cls[i]);
-            }
+        for (int i = 0; i < 3 * ADY_MAX_THR; ++i) s_red[threadIdx.x >> 5][i] = d[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * ADY_MAX_THR) {
+        double t = 0.0;
+        for (int w = 0; w < LA_THREADS / 32; ++w) t += s_red[w][threadIdx.x];
+        const int kind = threadIdx.x / ADY_MAX_THR, i = threadIdx.x % ADY_MAX_THR;
+        if (i < cfg.n_thr && t != 0.0) {
+            double* dstp = kind == 0 ? acc->s_pos : (kind == 1 ? acc->s_neg : acc->s_cls);
+            atomicAdd(&dstp[i], t);
+        }
     }
 }
 
@@ -367,6 +371,16 @@ __global__ void loss_finalize_kernel(long long n_anchor, AssignCfg cfg, const Lo
         total += (pos * cfg.gain_obj + neg * cfg.gain_nonobj + cls * cfg.gain_cls) / cfg.n_thr;
     }
     loss_out[0] = (float)total;
+}
+
+static int loss_anchor_blocks_per_sm() {
+    static int cached = 0;
+    if (!cached) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, loss_anchor_kernel, LA_THREADS, 0) != cudaSuccess || n < 1) n = 2;
+        cached = n;
+    }
+    return cached;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -416,7 +430,7 @@ int launch_loss(const float* logit, const float* target, long long M, int B, int
     loss_weights_kernel<<<1, 32, 0, stream>>>(n_anchor, cfg, acc);
     ADY_LAUNCH_CHECK("loss_weights_kernel");
     long long blocks = (n_anchor + LA_THREADS - 1) / LA_THREADS;
-    const long long cap = (long long)sms * 8;
+    const long long cap = (long long)sms * loss_anchor_blocks_per_sm();   // one resident wave
     if (blocks > cap) blocks = cap;
     loss_anchor_kernel<<<(int)blocks, LA_THREADS, 0, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out,
                                                                nullptr, 1);
@@ -441,7 +455,7 @@ int launch_loss_backward(const float* logit, int B, int T, const AssignCfg& cfg,
     ADY_CUDA_CHECK(cudaGetDevice(&dev));
     ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     long long blocks = (n_anchor + LA_THREADS - 1) / LA_THREADS;
-    const long long cap = (long long)sms * 8;
+    const long long cap = (long long)sms * loss_anchor_blocks_per_sm();
     if (blocks > cap) blocks = cap;
     loss_anchor_kernel<<<(int)blocks, LA_THREADS, 0, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out,
                                                                grad_output, 0);
