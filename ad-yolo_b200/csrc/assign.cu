@@ -194,10 +194,11 @@ __global__ void loss_weights_kernel(long long n_anchor, AssignCfg cfg, LossAccum
 // Warp-autonomous pass over the anchors (no block barriers, no shared memory); a warp owns groups
 // of 32 consecutive anchors (group base is 16-byte aligned for any channel count):
 //   1. lane = anchor: objectness logit -> sigmoid, BCE sums, objectness gradient (kept in the lane)
-//   2. (grad only) lane = 4 consecutive elements of the group's 32*CH logits, float4 coalesced:
-//      objectness gradient fetched from the owning lane by shuffle, zeros for the class channels,
-//      scaled angular partials for (u, v)
-//   3. for every positive anchor of the group (ballot): lane = class -> class BCE sums / gradients
+//   2. (positive anchor, class) items of the group (ballot-compacted) spread over the lanes:
+//      class BCE sums / gradients
+//   3. (grad only) the group's gradient rows are assembled in a per-warp shared-memory tile that
+//      is zero except for objectness, (u,v) and the positives' class entries, and copied out with
+//      coalesced float4 stores
 // do_sums: accumulate the BCE sums (forward); grad != NULL: write gscale * d loss / d logit.
 __global__ void __launch_bounds__(LA_THREADS)
 loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCfg cfg,
@@ -227,6 +228,25 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
     const long long n_groups = (n_anchor + 31) / 32;
     const long long warp0 = ((long long)blockIdx.x * LA_THREADS + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * LA_THREADS) >> 5;
+    // gradient staging tile of this warp: exactly the global layout of its 32 anchors (32*CH
+    // floats).  It is kept all-zero between groups; per group only the objectness / (u,v) values
+    // and the class gradients of positive anchors are written, then it is copied out with float4
+    // stores and the touched class entries are zeroed again.
+    extern __shared__ __align__(16) float s_tile_all[];
+    float* tile = s_tile_all + (threadIdx.x >> 5) * (32 * CH);
+    if (grad) {
+        for (unsigned i = lane; i < 32 * CH; i += 32) tile[i] = 0.f;
+        __syncwarp();
+    }
+
+    // software pipeline: label word and objectness logit of the next group are in flight while the
+    // current group is processed
+    unsigned long long st_n = 0ull;
+    float x_n = 0.f;
+    if (warp0 < n_groups && warp0 * 32 + lane < n_anchor) {
+        st_n = state[warp0 * 32 + lane];
+        x_n = logit[(warp0 * 32 + lane) * CH];
+    }
     for (long long grp = warp0; grp < n_groups; grp += n_warps) {
         const long long a0 = grp * 32;
         const unsigned na = (unsigned)min(32LL, n_anchor - a0);
@@ -234,32 +254,14 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
         const float* src = logit + a0 * CH;
         float* dst = grad ? grad + a0 * CH : nullptr;
 
-        // ---- pass 1: objectness, lane = anchor.  The group's 32*CH logits are read once with
-        // coalesced float4 loads (up to 5 per lane, all in flight together); the objectness logit of
-        // anchor `lane` (element lane*CH) is then fetched from the lane that holds it by shuffle.
+        // ---- pass 1: objectness, lane = anchor
         const bool valid = (unsigned)lane < na;
-        const unsigned long long st = valid ? state[a0 + lane] : 0ull;
-        float4 xv[5];
-#pragma unroll
-        for (unsigned k = 0; k < 5; ++k) {
-            const unsigned el = k * 128 + (unsigned)lane * 4;
-            if (el + 4 <= nel) xv[k] = *reinterpret_cast<const float4*>(src + el);
-            else {
-                xv[k].x = el < nel ? src[el] : 0.f;
-                xv[k].y = el + 1 < nel ? src[el + 1] : 0.f;
-                xv[k].z = el + 2 < nel ? src[el + 2] : 0.f;
-                xv[k].w = 0.f;
-            }
-        }
-        const unsigned e_obj = (unsigned)lane * CH;
-        const unsigned k_src = e_obj >> 7, l_src = (e_obj & 127u) >> 2, c_src = e_obj & 3u;
-        float x_obj = 0.f;
-#pragma unroll
-        for (unsigned k = 0; k < 5; ++k) {
-            const float vx = __shfl_sync(FULL, xv[k].x, (int)l_src), vy = __shfl_sync(FULL, xv[k].y, (int)l_src);
-            const float vz = __shfl_sync(FULL, xv[k].z, (int)l_src), vw = __shfl_sync(FULL, xv[k].w, (int)l_src);
-            const float v = c_src == 0 ? vx : (c_src == 1 ? vy : (c_src == 2 ? vz : vw));
-            if (k == k_src) x_obj = v;
+        const unsigned long long st = st_n;
+        const float x_obj = x_n;
+        {
+            const long long an = (grp + n_warps) * 32 + lane;
+            if (grp + n_warps < n_groups && an < n_anchor) { st_n = state[an]; x_n = logit[an * CH]; }
+            else { st_n = 0ull; x_n = 0.f; }
         }
         float go = 0.f;
         if (valid) {
@@ -274,37 +276,15 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
                 else                         { s_neg[i] += l_neg; go += w_neg[i] * g_neg; }
             }
         }
-        unsigned posmask = __ballot_sync(FULL, valid && (st & OBJ_ANY));
-
-        // ---- pass 2: coalesced gradient write (objectness via shuffle, zeroed classes, angular u/v)
-        if (dst) {
-            const unsigned iters = (nel + 127) / 128;     // warp-uniform
-            for (unsigned k = 0; k < iters; ++k) {
-                const unsigned el = k * 128 + (unsigned)lane * 4;
-                unsigned al = el / CH, ch = el - al * CH;
-                float g[4];
-#pragma unroll
-                for (unsigned q = 0; q < 4; ++q) {
-                    const float go_al = __shfl_sync(FULL, go, (int)(al & 31u));
-                    float v = 0.f;
-                    if (ch == 0) v = go_al;
-                    else if (ch > C && al < na) {
-                        const float2 ag = ang_grad[a0 + al];
-                        v = (ch == C + 1 ? ag.x : ag.y) * w_ang;
-                    }
-                    g[q] = v;
-                    if (++ch == CH) { ch = 0; ++al; }
-                }
-                if (el + 4 <= nel) *reinterpret_cast<float4*>(dst + el) = make_float4(g[0], g[1], g[2], g[3]);
-                else {
-#pragma unroll
-                    for (unsigned q = 0; q < 4; ++q) if (el + q < nel) dst[el + q] = g[q];
-                }
-            }
-            __syncwarp();   // class gradients of positive anchors overwrite the zeros written above
+        const unsigned posmask = __ballot_sync(FULL, valid && (st & OBJ_ANY));
+        if (dst && valid) {
+            const float2 ag = ang_grad[a0 + lane];
+            tile[(unsigned)lane * CH] = go;
+            tile[(unsigned)lane * CH + C + 1] = ag.x * w_ang;
+            tile[(unsigned)lane * CH + C + 2] = ag.y * w_ang;
         }
 
-        // ---- pass 3: (positive anchor, class) items spread over the lanes; the loop count is
+        // ---- pass 2: (positive anchor, class) items spread over the lanes; the loop count is
         // warp-uniform so the shuffles that fetch the anchor's label word are convergent
         const unsigned n_items = (unsigned)__popc(posmask) * C;
         for (unsigned base = 0; base < n_items; base += 32) {
@@ -328,8 +308,26 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
                         gc += w_cls[i] * (t ? g1 : g0);
                     }
                 }
-                if (dst) dst[(unsigned)al * CH + 1 + c] = gc;
+                if (dst) tile[(unsigned)al * CH + 1 + c] = gc;
             }
+        }
+
+        // ---- pass 3 (grad only): coalesced float4 copy-out of the tile, then restore the zeros
+        if (dst) {
+            __syncwarp();
+            for (unsigned el = (unsigned)lane * 4; el < nel; el += 128) {
+                if (el + 4 <= nel) *reinterpret_cast<float4*>(dst + el) = *reinterpret_cast<const float4*>(tile + el);
+                else for (unsigned q = 0; el + q < nel; ++q) dst[el + q] = tile[el + q];
+            }
+            __syncwarp();
+            for (unsigned base = 0; base < n_items; base += 32) {
+                const unsigned it = base + lane;
+                if (it < n_items) {
+                    const unsigned pi = it / C, c = it - pi * C;
+                    tile[(unsigned)__fns(posmask, 0, (int)pi + 1) * CH + 1 + c] = 0.f;
+                }
+            }
+            __syncwarp();
         }
     }
     if (!do_sums) return;
@@ -377,7 +375,7 @@ static int loss_anchor_blocks_per_sm() {
     static int cached = 0;
     if (!cached) {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, loss_anchor_kernel, LA_THREADS, 0) != cudaSuccess || n < 1) n = 2;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, loss_anchor_kernel, LA_THREADS, 8 * 32 * 18 * 4) != cudaSuccess || n < 1) n = 2;
         cached = n;
     }
     return cached;
@@ -432,8 +430,9 @@ int launch_loss(const float* logit, const float* target, long long M, int B, int
     long long blocks = (n_anchor + LA_THREADS - 1) / LA_THREADS;
     const long long cap = (long long)sms * loss_anchor_blocks_per_sm();   // one resident wave
     if (blocks > cap) blocks = cap;
-    loss_anchor_kernel<<<(int)blocks, LA_THREADS, 0, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out,
-                                                               nullptr, 1);
+    const size_t shmem = grad_out ? (size_t)(LA_THREADS / 32) * 32 * (cfg.nb_classes + 3) * sizeof(float) : 0;
+    loss_anchor_kernel<<<(int)blocks, LA_THREADS, shmem, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out,
+                                                                   nullptr, 1);
     ADY_LAUNCH_CHECK("loss_anchor_kernel");
     loss_finalize_kernel<<<1, 32, 0, stream>>>(n_anchor, cfg, acc, loss_out);
     ADY_LAUNCH_CHECK("loss_finalize_kernel");
@@ -457,8 +456,9 @@ int launch_loss_backward(const float* logit, int B, int T, const AssignCfg& cfg,
     long long blocks = (n_anchor + LA_THREADS - 1) / LA_THREADS;
     const long long cap = (long long)sms * loss_anchor_blocks_per_sm();
     if (blocks > cap) blocks = cap;
-    loss_anchor_kernel<<<(int)blocks, LA_THREADS, 0, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out,
-                                                               grad_output, 0);
+    const size_t shmem = (size_t)(LA_THREADS / 32) * 32 * (cfg.nb_classes + 3) * sizeof(float);
+    loss_anchor_kernel<<<(int)blocks, LA_THREADS, shmem, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out,
+                                                                   grad_output, 0);
     ADY_LAUNCH_CHECK("loss_anchor_kernel(backward)");
     return ADY_OK;
 }
