@@ -249,8 +249,14 @@ def main_ours(args):
     if fe_ms:
         alg_bytes = BATCH * CLIP_S * BYTES_PER_AUDIO_S
         ach = alg_bytes / (fe_ms / 1e3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "frontend_traffic.json")) as f:
+                traffic = json.load(f)["dram_bytes_total"]      # ncu --set full capture of the same launch shape
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": "frontend_foa_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": fe_ms,
+                "frac": ach / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": fe_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "FP32-issue-bound kernel (25 FLOP/B vs ~11 FLOP/B ridge); see DESIGN.md / profiles/"}
     if rank == 0:
