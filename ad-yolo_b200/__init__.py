@@ -16,7 +16,7 @@ Mirrors (same names / argument meaning) of the reference call surface, SURVEY.md
 from . import _lib  # noqa: F401
 from .features import (FeatureLabelProcessor, audio2stft, stft2melscale, stft2iv,  # noqa: F401
                        features_batched, mel_filterbank)
-from .labels import get_yolo_label, collate_fn, label_rows_batched  # noqa: F401
+from .labels import DeviceRows, get_yolo_label, collate_fn, label_rows_batched  # noqa: F401
 from .loss import ADYOLOloss, WrapperCriterion, adyolo_assign  # noqa: F401
 from .scaler import ScalerAccumulator, preprocess_scaler  # noqa: F401
 

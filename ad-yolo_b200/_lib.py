@@ -89,6 +89,7 @@ _SIGS = {
     "adyolo_assign": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.POINTER(GridCfg), _P, _P, _P, _P]),
     "adyolo_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.POINTER(GridCfg)]),
     "adyolo_loss": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.POINTER(GridCfg), _P, _P, _P, _P, _P, _P, _P]),
+    "adyolo_loss_devcount": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, C.c_int, C.POINTER(GridCfg), _P, _P, _P, _P]),
     "adyolo_loss_backward": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(GridCfg), _P, _P, _P, _P]),
 }
 

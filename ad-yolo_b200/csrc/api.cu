@@ -197,8 +197,18 @@ int adyolo_loss(const float* logit, const float* target, int64_t M, int B, int T
     int rc = make_cfgs(cfg, &a, nullptr);
     if (rc) return rc;
     if (!logit || !loss_out || !workspace || (M > 0 && !target)) return set_error(ADY_ERR_INVALID, "loss: NULL pointer");
-    return launch_loss(logit, target, (long long)M, B, T, a, loss_out, grad_out, D, mask, argmin, workspace,
+    return launch_loss(logit, target, (long long)M, nullptr, B, T, a, loss_out, grad_out, D, mask, argmin, workspace,
                        (cudaStream_t)stream);
+}
+
+int adyolo_loss_devcount(const float* logit, const float* target, int64_t max_rows, const int64_t* n_rows_dev, int B, int T,
+                         const adyolo_grid_cfg* cfg, float* loss_out, float* grad_out, void* workspace, void* stream) {
+    AssignCfg a;
+    int rc = make_cfgs(cfg, &a, nullptr);
+    if (rc) return rc;
+    if (!logit || !loss_out || !workspace || !target || !n_rows_dev) return set_error(ADY_ERR_INVALID, "loss_devcount: NULL pointer");
+    return launch_loss(logit, target, (long long)max_rows, (const long long*)n_rows_dev, B, T, a, loss_out, grad_out,
+                       nullptr, nullptr, nullptr, workspace, (cudaStream_t)stream);
 }
 
 int adyolo_loss_backward(const float* logit, int B, int T, const adyolo_grid_cfg* cfg, const void* workspace,

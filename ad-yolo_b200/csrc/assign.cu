@@ -50,10 +50,14 @@ __device__ __forceinline__ RowGeom read_row(const float* __restrict__ target, lo
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-assign_rows_kernel(const float* __restrict__ logit, const float* __restrict__ target, long long M, int B, int T,
+assign_rows_kernel(const float* __restrict__ logit, const float* __restrict__ target, long long M_host,
+                   const long long* __restrict__ M_dev, int B, int T,
                    AssignCfg cfg, float* __restrict__ D_out, uint8_t* __restrict__ mask_out,
                    int32_t* __restrict__ argmin_out, unsigned long long* __restrict__ state,
                    float2* __restrict__ ang_grad, LossAccum* __restrict__ acc) {
+    // M_dev (optional): the true row count lives on the device (label_rows wrote it); the launch
+    // then covers the caller's row capacity M_host and surplus threads fall through
+    const long long M = M_dev ? min(M_host, *M_dev) : M_host;
     const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int A = cfg.nb_anchors, CH = cfg.nb_classes + 3;
     double ang_sum = 0.0;
@@ -397,18 +401,19 @@ static int check_cfg(const AssignCfg& c) {
 
 int launch_assign(const float* logit, const float* target, long long M, int B, int T, const AssignCfg& cfg,
                   float* D, uint8_t* mask, int32_t* argmin, cudaStream_t stream) {
+    // (mask layout (n_thr, M, A) uses the host M: no device-count variant here)
     int rc = check_cfg(cfg);
     if (rc) return rc;
     if (M <= 0) return ADY_OK;
     const int blocks = (int)((M + 127) / 128);
-    assign_rows_kernel<<<blocks, 128, 0, stream>>>(logit, target, M, B, T, cfg, D, mask, argmin, nullptr, nullptr, nullptr);
+    assign_rows_kernel<<<blocks, 128, 0, stream>>>(logit, target, M, nullptr, B, T, cfg, D, mask, argmin, nullptr, nullptr, nullptr);
     ADY_LAUNCH_CHECK("assign_rows_kernel");
     return ADY_OK;
 }
 
-int launch_loss(const float* logit, const float* target, long long M, int B, int T, const AssignCfg& cfg,
-                float* loss_out, float* grad_out, float* D, uint8_t* mask, int32_t* argmin, void* ws,
-                cudaStream_t stream) {
+int launch_loss(const float* logit, const float* target, long long M, const long long* M_dev, int B, int T,
+                const AssignCfg& cfg, float* loss_out, float* grad_out, float* D, uint8_t* mask, int32_t* argmin,
+                void* ws, cudaStream_t stream) {
     int rc = check_cfg(cfg);
     if (rc) return rc;
     const long long n_anchor = (long long)B * T * cfg.ga * cfg.ge * cfg.nb_anchors;
@@ -419,7 +424,7 @@ int launch_loss(const float* logit, const float* target, long long M, int B, int
     ADY_CUDA_CHECK(cudaMemsetAsync(ws, 0, loss_workspace_bytes(B, T, cfg), stream));
     if (M > 0) {
         const int blocks = (int)((M + 127) / 128);
-        assign_rows_kernel<<<blocks, 128, 0, stream>>>(logit, target, M, B, T, cfg, D, mask, argmin, state, ang, acc);
+        assign_rows_kernel<<<blocks, 128, 0, stream>>>(logit, target, M, M_dev, B, T, cfg, D, mask, argmin, state, ang, acc);
         ADY_LAUNCH_CHECK("assign_rows_kernel");
     }
     int dev = 0, sms = 0;

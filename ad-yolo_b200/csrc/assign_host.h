@@ -38,9 +38,9 @@ struct LossAccum {
 size_t loss_workspace_bytes(int B, int T, const AssignCfg& cfg);
 int launch_assign(const float* logit, const float* target, long long M, int B, int T, const AssignCfg& cfg,
                   float* D, uint8_t* mask, int32_t* argmin, cudaStream_t stream);
-int launch_loss(const float* logit, const float* target, long long M, int B, int T, const AssignCfg& cfg,
-                float* loss_out, float* grad_out, float* D, uint8_t* mask, int32_t* argmin, void* ws,
-                cudaStream_t stream);
+int launch_loss(const float* logit, const float* target, long long M, const long long* M_dev, int B, int T,
+                const AssignCfg& cfg, float* loss_out, float* grad_out, float* D, uint8_t* mask, int32_t* argmin,
+                void* ws, cudaStream_t stream);
 
 int launch_loss_backward(const float* logit, int B, int T, const AssignCfg& cfg, const void* ws,
                          const float* grad_output, float* grad_out, cudaStream_t stream);

@@ -47,10 +47,26 @@ class GridSpec:
         return self.nb_classes + 3
 
 
-def label_rows_batched(events: torch.Tensor, nb_label_frames: int, grid: GridSpec, return_cellmask=False):
+class DeviceRows:
+    """Target rows whose count is only known on the device: ``rows`` has capacity rows and the first
+    ``n_rows`` (int64 tensor of shape (1,) on the device) are valid.  ``ADYOLOloss`` accepts it in
+    place of the (M, 7) tensor, so label rows and loss are enqueued with no host synchronisation."""
+
+    def __init__(self, rows: torch.Tensor, n_rows: torch.Tensor):
+        self.rows, self.n_rows = rows, n_rows
+
+    def materialize(self) -> torch.Tensor:
+        return self.rows[: int(self.n_rows.item())]
+
+
+def label_rows_batched(events: torch.Tensor, nb_label_frames: int, grid: GridSpec, return_cellmask=False,
+                       max_rows: int | None = None):
     """events (E, 5) float64 on CUDA, rows [batch, frame, class, azi, ele] in dataset order
     -> target rows (M, 7) float32 on CUDA [batch, frame, Gi, Gj, class, U, V]
-    (== get_yolo_label per clip followed by collate_fn's label half)."""
+    (== get_yolo_label per clip followed by collate_fn's label half).
+
+    With ``max_rows`` (e.g. ``E * Ga * Ge``, or ``4 * E`` for the reference's g_overlap = 0.5) the
+    result is a ``DeviceRows`` and nothing synchronises with the host."""
     require_cuda(events, "label_rows_batched")
     if events.dtype != torch.float64 or events.dim() != 2 or events.shape[1] != 5:
         raise ValueError("events must be a float64 tensor of shape (E, 5)")
@@ -63,6 +79,11 @@ def label_rows_batched(events: torch.Tensor, nb_label_frames: int, grid: GridSpe
         total = torch.zeros(1, dtype=torch.int64, device=events.device)
         check(L.adyolo_label_cells(ptr(events), E, int(nb_label_frames), C.byref(grid.c), ptr(cellmask), ptr(total),
                                    ptr(ws), stream_ptr()), "adyolo_label_cells")
+        if max_rows is not None:
+            rows = torch.empty((int(max_rows), 7), dtype=torch.float32, device=events.device)
+            check(L.adyolo_label_rows(ptr(events), E, C.byref(grid.c), ptr(cellmask), ptr(ws), ptr(rows), int(max_rows),
+                                      stream_ptr()), "adyolo_label_rows")
+            return DeviceRows(rows, total)
         M = int(total.item())   # the one host sync of the label path (sizes the output)
         rows = torch.empty((M, 7), dtype=torch.float32, device=events.device)
         check(L.adyolo_label_rows(ptr(events), E, C.byref(grid.c), ptr(cellmask), ptr(ws), ptr(rows), M, stream_ptr()),

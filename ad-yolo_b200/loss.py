@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 from ._lib import check, ptr, require_cuda, stream_ptr
-from .labels import GridSpec
+from .labels import DeviceRows, GridSpec
 
 _ws_cache = {}
 
@@ -52,7 +52,7 @@ def adyolo_assign(logit: torch.Tensor, target: torch.Tensor, grid: GridSpec):
 
 class _ADYOLOFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logit, target, grid):
+    def forward(ctx, logit, target, grid, n_rows_dev=None):
         B, T, _ = logit.shape
         M = target.shape[0]
         L = _lib.lib()
@@ -62,8 +62,12 @@ class _ADYOLOFn(torch.autograd.Function):
             nbytes = L.adyolo_loss_workspace_bytes(B, T, C.byref(grid.c))
             # the workspace carries label bits / counts to backward: private per call when needed
             ws = torch.empty(nbytes, dtype=torch.uint8, device=logit.device) if need_grad else _workspace(nbytes, logit.device)
-            check(L.adyolo_loss(ptr(logit), ptr(target), M, B, T, C.byref(grid.c), ptr(loss), None, None, None,
-                                None, ptr(ws), stream_ptr()), "adyolo_loss")
+            if n_rows_dev is None:
+                check(L.adyolo_loss(ptr(logit), ptr(target), M, B, T, C.byref(grid.c), ptr(loss), None, None, None,
+                                    None, ptr(ws), stream_ptr()), "adyolo_loss")
+            else:
+                check(L.adyolo_loss_devcount(ptr(logit), ptr(target), M, ptr(n_rows_dev), B, T, C.byref(grid.c),
+                                             ptr(loss), None, ptr(ws), stream_ptr()), "adyolo_loss_devcount")
         ctx.grid = grid
         ctx.save_for_backward(logit, ws)
         return loss
@@ -77,7 +81,7 @@ class _ADYOLOFn(torch.autograd.Function):
             grad = torch.empty_like(logit)
             check(_lib.lib().adyolo_loss_backward(ptr(logit), B, T, C.byref(ctx.grid.c), ptr(ws), ptr(gout), ptr(grad),
                                                   stream_ptr()), "adyolo_loss_backward")
-        return grad, None, None
+        return grad, None, None, None
 
 
 class ADYOLOloss(object):
@@ -112,13 +116,16 @@ class ADYOLOloss(object):
     def assign(self, logit, target):
         return adyolo_assign(logit, target, self.grid)
 
-    def __call__(self, logit: torch.Tensor, target: torch.Tensor):
+    def __call__(self, logit: torch.Tensor, target):
+        n_rows = None
+        if isinstance(target, DeviceRows):
+            target, n_rows = target.rows, target.n_rows
         _check_inputs(logit, target, self.grid)
         if logit.dtype != torch.float32:
             logit = logit.float()
         logit = logit.contiguous()
         target = target.to(logit.device, torch.float32).contiguous()   # loss.py:199
-        return _ADYOLOFn.apply(logit, target, self.grid)
+        return _ADYOLOFn.apply(logit, target, self.grid, n_rows)
 
 
 class WrapperCriterion(object):

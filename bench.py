@@ -188,7 +188,7 @@ def main_ours(args):
 
     def step(audio, events, record=False):
         A.features_batched(audio, scaler_dev, out=feat_buf, timing_events=fe_events if record else None)
-        rows = A.label_rows_batched(events, T_LABEL, grid)
+        rows = A.label_rows_batched(events, T_LABEL, grid, max_rows=4 * events.shape[0])   # no host sync
         logit.grad = None
         loss = crit(logit, rows)
         loss.backward()

@@ -144,6 +144,12 @@ int adyolo_loss(const float* logit, const float* target, int64_t M, int B, int T
                 const adyolo_grid_cfg* cfg, float* loss_out, float* grad_out, float* D, uint8_t* mask,
                 int32_t* argmin, void* workspace, void* stream);
 
+/* Same as adyolo_loss, but the number of valid target rows is read from device memory
+ * (the int64 written by adyolo_label_cells), `target` having capacity max_rows: lets label rows
+ * and loss be enqueued back to back with no host synchronisation in between.                 */
+int adyolo_loss_devcount(const float* logit, const float* target, int64_t max_rows, const int64_t* n_rows_dev,
+                         int B, int T, const adyolo_grid_cfg* cfg, float* loss_out, float* grad_out,
+                         void* workspace, void* stream);
 int adyolo_loss_backward(const float* logit, int B, int T, const adyolo_grid_cfg* cfg, const void* workspace,
                          const float* grad_output /* device float32[1] or NULL (= 1) */, float* grad_out,
                          void* stream);

@@ -163,6 +163,24 @@ def test_loss_vs_torch_oracle_on_gpu_config2_shape(A):
     assert ((logit.grad - l2.grad).norm() / l2.grad.norm()).item() < 1e-5
 
 
+def test_device_row_count_path_equals_host_path(A):
+    """label rows -> loss with the row count kept on the device (no host sync) == the (M,7) path."""
+    C, B, T = 12, 8, 50
+    rng = np.random.default_rng(21)
+    grid = _grid(A, C)
+    ev = torch.from_numpy(_events(rng, B, T, C)).cuda()
+    rows = A.label_rows_batched(ev, T, grid)
+    drows = A.label_rows_batched(ev, T, grid, max_rows=4 * len(ev))
+    assert isinstance(drows, A.DeviceRows) and torch.equal(drows.materialize(), rows)
+    crit = A.ADYOLOloss(default_params(C, "cuda:0"))
+    l1 = torch.randn((B, T, 2400), device="cuda", generator=torch.Generator(device="cuda").manual_seed(5)).requires_grad_(True)
+    l2 = l1.detach().clone().requires_grad_(True)
+    a = crit(l1, rows); a.backward()
+    b = crit(l2, drows); b.backward()
+    assert abs(a.item() - b.item()) <= 1e-6 * abs(a.item())     # atomics: summation order differs
+    assert (l1.grad - l2.grad).abs().max().item() <= 1e-6 * l1.grad.abs().max().item()
+
+
 def test_loss_nan_without_targets_and_bad_shapes(A):
     crit = A.ADYOLOloss(default_params(12, "cuda:0"))
     out = crit(torch.zeros(1, 2, 2400, device="cuda"), torch.zeros(0, 7))
