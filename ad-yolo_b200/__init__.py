@@ -19,5 +19,6 @@ from .features import (FeatureLabelProcessor, audio2stft, stft2melscale, stft2iv
 from .labels import DeviceRows, get_yolo_label, collate_fn, label_rows_batched  # noqa: F401
 from .loss import ADYOLOloss, WrapperCriterion, adyolo_assign  # noqa: F401
 from .scaler import ScalerAccumulator, preprocess_scaler  # noqa: F401
+from .pipeline import HostBatchPipeline  # noqa: F401
 
 __version__ = "0.1.0"

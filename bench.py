@@ -214,17 +214,28 @@ def main_ours(args):
     ms = e0.elapsed_time(e1)
     fe_ms = float(np.mean([a.elapsed_time(b) for a, b in fe_events])) if fe_events else None
 
-    # ---- end-to-end through the public API with host buffers
-    for _ in range(max(1, args.warmup // 2)):
-        audio_d.copy_(audio_h, non_blocking=True); events_d.copy_(events_h, non_blocking=True)
-        step(audio_d, events_d).item()
+    # ---- end-to-end through the public API with host buffers: every step's int16 batch and event
+    # table are copied from pinned host memory (double-buffered on a side stream, so the copy of
+    # step i+1 overlaps the kernels of step i) and the step's loss is read back to the host
+    pipe = A.HostBatchPipeline(dev)
+
+    def e2e_loop(n):
+        pipe.submit(audio_h, events_h)
+        last = None
+        for i in range(n):
+            a_d, e_d = pipe.get()
+            if i + 1 < n:
+                pipe.submit(audio_h, events_h)
+            loss = step(a_d, e_d)
+            pipe.release()
+            last = loss.item()                          # device -> host read of the step's result
+        return last
+
+    e2e_loop(max(2, args.warmup // 2))
     barrier()
     x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     x0.record()
-    for _ in range(args.steps):
-        audio_d.copy_(audio_h, non_blocking=True)
-        events_d.copy_(events_h, non_blocking=True)
-        lv = step(audio_d, events_d).item()            # device -> host read of the step's result
+    lv = e2e_loop(args.steps)
     x1.record()
     barrier()
     e2e_ms = x0.elapsed_time(x1)
