@@ -74,6 +74,7 @@ _SIGS = {
     "adyolo_mel_filterbank": (C.c_int, [C.c_int, C.c_int, C.c_int, _P]),
     "adyolo_frontend_workspace_bytes": (C.c_size_t, [C.POINTER(FrontendCfg), C.c_int, C.c_int64]),
     "adyolo_features_foa": (C.c_int, [_P, C.c_int, C.c_int64, C.POINTER(FrontendCfg), _P, _P, _P, _P, C.c_int, _P]),
+    "adyolo_features_foa_rot": (C.c_int, [_P, C.c_int, C.c_int64, C.POINTER(FrontendCfg), _P, _P, _P, _P, _P, C.c_int, _P]),
     "adyolo_features_foa_clamp": (C.c_int, [_P, C.c_int, C.c_int64, C.POINTER(FrontendCfg), _P, _P, _P, _P]),
     "adyolo_stft": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.POINTER(FrontendCfg), _P, _P]),
     "adyolo_logmel_from_stft": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int, C.c_int, C.POINTER(FrontendCfg), _P, _P, _P,
@@ -84,8 +85,8 @@ _SIGS = {
                                        C.POINTER(C.c_int64), _P]),
     "adyolo_scaler_partials": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, _P]),
     "adyolo_label_workspace_bytes": (C.c_size_t, [C.c_int64]),
-    "adyolo_label_cells": (C.c_int, [_P, C.c_int64, C.c_int, C.POINTER(GridCfg), _P, _P, _P, _P]),
-    "adyolo_label_rows": (C.c_int, [_P, C.c_int64, C.POINTER(GridCfg), _P, _P, _P, C.c_int64, _P]),
+    "adyolo_label_cells": (C.c_int, [_P, C.c_int64, C.c_int, C.POINTER(GridCfg), _P, _P, _P, _P, _P]),
+    "adyolo_label_rows": (C.c_int, [_P, C.c_int64, C.POINTER(GridCfg), _P, _P, _P, _P, C.c_int64, _P]),
     "adyolo_assign": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.POINTER(GridCfg), _P, _P, _P, _P]),
     "adyolo_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.POINTER(GridCfg)]),
     "adyolo_loss": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.POINTER(GridCfg), _P, _P, _P, _P, _P, _P, _P]),

@@ -91,15 +91,21 @@ size_t adyolo_frontend_workspace_bytes(const adyolo_frontend_cfg* cfg, int B, in
     return frontend_workspace_bytes(B, (long long)N);
 }
 
-int adyolo_features_foa(const int16_t* audio, int B, int64_t N, const adyolo_frontend_cfg* cfg,
-                        const float* mean, const float* inv_std, float* out, void* workspace,
-                        int apply_topdb, void* stream) {
+int adyolo_features_foa_rot(const int16_t* audio, int B, int64_t N, const adyolo_frontend_cfg* cfg,
+                            const float* mean, const float* inv_std, const int8_t* rot_comb, float* out,
+                            void* workspace, int apply_topdb, void* stream) {
     int rc = check_frontend_cfg(cfg);
     if (rc) return rc;
     if (!audio || !out || !workspace) return set_error(ADY_ERR_INVALID, "features_foa: NULL pointer");
     if ((mean == nullptr) != (inv_std == nullptr)) return set_error(ADY_ERR_INVALID, "features_foa: mean and inv_std must both be given or both NULL");
-    return launch_features_foa(audio, B, (long long)N, mean, inv_std, cfg->dc_offset, cfg->top_db, apply_topdb, out,
-                               workspace, (cudaStream_t)stream);
+    return launch_features_foa(audio, B, (long long)N, mean, inv_std, cfg->dc_offset, cfg->top_db, apply_topdb, rot_comb,
+                               out, workspace, (cudaStream_t)stream);
+}
+
+int adyolo_features_foa(const int16_t* audio, int B, int64_t N, const adyolo_frontend_cfg* cfg,
+                        const float* mean, const float* inv_std, float* out, void* workspace,
+                        int apply_topdb, void* stream) {
+    return adyolo_features_foa_rot(audio, B, N, cfg, mean, inv_std, nullptr, out, workspace, apply_topdb, stream);
 }
 
 int adyolo_features_foa_clamp(float* out, int B, int64_t N, const adyolo_frontend_cfg* cfg, const float* mean,
@@ -156,23 +162,24 @@ int adyolo_scaler_partials(const float* feats, int B, int C, int64_t T, double* 
 size_t adyolo_label_workspace_bytes(int64_t E) { return label_workspace_bytes((long long)E); }
 
 int adyolo_label_cells(const double* events, int64_t E, int nb_label_frames, const adyolo_grid_cfg* cfg,
-                       uint32_t* cellmask, int64_t* total_rows, void* workspace, void* stream) {
+                       const int8_t* rot_comb, uint32_t* cellmask, int64_t* total_rows, void* workspace, void* stream) {
     CellCfg cc;
     int rc = make_cfgs(cfg, nullptr, &cc);
     if (rc) return rc;
     if (E > 0 && (!events || !cellmask || !workspace)) return set_error(ADY_ERR_INVALID, "label_cells: NULL pointer");
     if (!total_rows) return set_error(ADY_ERR_INVALID, "label_cells: total_rows is NULL");
-    return launch_label_cells(events, (long long)E, nb_label_frames, cc, cellmask, (long long*)total_rows, workspace,
-                              (cudaStream_t)stream);
+    return launch_label_cells(events, (long long)E, nb_label_frames, cc, rot_comb, cellmask, (long long*)total_rows,
+                              workspace, (cudaStream_t)stream);
 }
 
-int adyolo_label_rows(const double* events, int64_t E, const adyolo_grid_cfg* cfg, const uint32_t* cellmask,
-                      const void* workspace, float* rows, int64_t max_rows, void* stream) {
+int adyolo_label_rows(const double* events, int64_t E, const adyolo_grid_cfg* cfg, const int8_t* rot_comb,
+                      const uint32_t* cellmask, const void* workspace, float* rows, int64_t max_rows, void* stream) {
     CellCfg cc;
     int rc = make_cfgs(cfg, nullptr, &cc);
     if (rc) return rc;
     if (E > 0 && max_rows > 0 && (!events || !cellmask || !workspace || !rows)) return set_error(ADY_ERR_INVALID, "label_rows: NULL pointer");
-    return launch_label_rows(events, (long long)E, cc, cellmask, workspace, rows, (long long)max_rows, (cudaStream_t)stream);
+    return launch_label_rows(events, (long long)E, cc, rot_comb, cellmask, workspace, rows, (long long)max_rows,
+                             (cudaStream_t)stream);
 }
 
 int adyolo_assign(const float* logit, const float* target, int64_t M, int B, int T,

@@ -121,6 +121,22 @@ ADY_HD void stage1_task(const uint32_t* __restrict__ samples, float2* __restrict
     for (int k1 = 0; k1 < 48; ++k1) xo[k1 * 25] = make_float2(x[k1].re, x[k1].im);
 }
 
+// ---------------------------------------------------------------- rotation augmentation
+// The 16 FOA channel sign / swap combinations of the reference (utils/augmentations.py:46-70),
+// packed per combination as bit0 = Y negated, bit1 = Z negated, bit2 = X negated, bit3 = X<->Y swap.
+// A sign flip of a real channel flips the sign of its spectrum: powers are unchanged, the
+// intensity component of that channel changes sign, and the "+1e-8" DC term (added after the
+// augmentation in datasets.py:146-147) keeps its sign; the swap is an output channel permutation.
+ADY_HD constexpr unsigned rot_bits(int comb) {
+    // yzx_weight / xy_swap columns of the table, in order
+    constexpr unsigned T[16] = {0x0, 0x2, 0x1, 0x3, 0x5, 0x7, 0x4, 0x6, 0x9, 0xB, 0x8, 0xA, 0xC, 0xE, 0xD, 0xF};
+    return T[comb & 15];
+}
+ADY_HD unsigned rot_bits_rt(int comb) {
+    // same table from a 64-bit immediate (no constant-memory array in device code)
+    return (unsigned)((0xFDECA8B964753120ull >> (4 * (comb & 15))) & 15ull);
+}
+
 // ---------------------------------------------------------------- stage 2a
 struct Stage2Regs {
     cx<float> P[25], Q[25];
@@ -129,8 +145,11 @@ struct Stage2Regs {
 // thread (frame f, residue pair t = 0..24 -> rows (t, (48-t)%48), role r: 0 = (W,Y) fft, 1 = (Z,X) fft)
 // dc: analytic contribution of the "+1e-8" DC offset of datasets.py:147 (pre-scaled like the
 // window): bin 0 gets +dc0 on both packed components, bins +-1 get dc1.
+// (sre, sim) = +-1: sign of the real / imaginary channel of this packed FFT under the rotation
+// augmentation; the DC term of a sign-flipped channel enters with the opposite sign so that
+// sign * (FFT(x) + sign*dc) == FFT(sign*x) + dc.
 ADY_HD void stage2a_task(const float2* __restrict__ x1, int f, int t, int r, float dc0, float dc1,
-                         Stage2Regs& s) {
+                         float sre, float sim, Stage2Regs& s) {
     const int g = 2 * f + r;
     const float2* pa = x1 + x1_base(g) + t * 25;
     const float2* pb = x1 + x1_base(g) + ((48 - t) % 48) * 25;
@@ -143,12 +162,12 @@ ADY_HD void stage2a_task(const float2* __restrict__ x1, int f, int t, int r, flo
     dft25(s.P);
     dft25(s.Q);
     if (t == 0) {  // bin 0 <-> (k1,k2) = (0,0); P and Q are the same row here
-        s.P[0].re += dc0; s.P[0].im += dc0;
-        s.Q[0].re += dc0; s.Q[0].im += dc0;
+        s.P[0].re += sre * dc0; s.P[0].im += sim * dc0;
+        s.Q[0].re += sre * dc0; s.Q[0].im += sim * dc0;
     }
     if (t == 1) {  // bin 1 <-> (1,1) in P; bin 1199 <-> (47,24) in Q
-        s.P[1].re += dc1; s.P[1].im += dc1;
-        s.Q[24].re += dc1; s.Q[24].im += dc1;
+        s.P[1].re += sre * dc1; s.P[1].im += sim * dc1;
+        s.Q[24].re += sre * dc1; s.Q[24].im += sim * dc1;
     }
 }
 

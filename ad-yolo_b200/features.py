@@ -66,7 +66,8 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 
 def features_batched(audio_i16: torch.Tensor, scaler_dev=None, out: torch.Tensor | None = None,
                      apply_topdb: bool = True, cfg: FrontendCfg | None = None,
-                     check_nan: bool = False, timing_events: list | None = None) -> torch.Tensor:
+                     check_nan: bool = False, timing_events: list | None = None,
+                     rot_comb: torch.Tensor | None = None) -> torch.Tensor:
     """int16 PCM (B, N, 4) on a CUDA device -> features (B, 7, T, 64) float32 on the same device.
 
     Equivalent to, per clip: ``audio/32768.0 + 1e-8`` -> ``FeatureLabelProcessor.get_feature`` ->
@@ -75,6 +76,8 @@ def features_batched(audio_i16: torch.Tensor, scaler_dev=None, out: torch.Tensor
     ``timing_events``: when a list is given, a (start, end) pair of CUDA events bracketing the fused
     front-end kernel alone is appended (bench.py's roofline measurement); the top_db pass is then
     issued through ``adyolo_features_foa_clamp``.
+    ``rot_comb``: optional int8 tensor (B,) on the device with the ``RotationAug`` combination number
+    (0..15, ``utils/augmentations.py:46-70``) of each clip: the augmentation is fused into the kernel.
     """
     require_cuda(audio_i16, "features_batched")
     if audio_i16.dtype != torch.int16 or audio_i16.dim() != 3 or audio_i16.shape[-1] != 4:
@@ -92,14 +95,19 @@ def features_batched(audio_i16: torch.Tensor, scaler_dev=None, out: torch.Tensor
         nbytes = L.adyolo_frontend_workspace_bytes(C.byref(cfg), B, N)
         ws = _workspace(nbytes, audio_i16.device)
         mean, istd = scaler_dev if scaler_dev is not None else (None, None)
+        if rot_comb is not None:
+            if rot_comb.dtype != torch.int8 or rot_comb.shape != (B,) or not rot_comb.is_cuda:
+                raise ValueError("rot_comb must be an int8 CUDA tensor of shape (B,)")
+            rot_comb = rot_comb.contiguous()
         if timing_events is None:
-            check(L.adyolo_features_foa(ptr(audio_i16), B, N, C.byref(cfg), ptr(mean), ptr(istd), ptr(out), ptr(ws),
-                                        1 if apply_topdb else 0, stream_ptr()), "adyolo_features_foa")
+            check(L.adyolo_features_foa_rot(ptr(audio_i16), B, N, C.byref(cfg), ptr(mean), ptr(istd), ptr(rot_comb),
+                                            ptr(out), ptr(ws), 1 if apply_topdb else 0, stream_ptr()),
+                  "adyolo_features_foa")
         else:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            check(L.adyolo_features_foa(ptr(audio_i16), B, N, C.byref(cfg), ptr(mean), ptr(istd), ptr(out), ptr(ws),
-                                        0, stream_ptr()), "adyolo_features_foa")
+            check(L.adyolo_features_foa_rot(ptr(audio_i16), B, N, C.byref(cfg), ptr(mean), ptr(istd), ptr(rot_comb),
+                                            ptr(out), ptr(ws), 0, stream_ptr()), "adyolo_features_foa")
             e1.record()
             timing_events.append((e0, e1))
             if apply_topdb:

@@ -60,13 +60,15 @@ class DeviceRows:
 
 
 def label_rows_batched(events: torch.Tensor, nb_label_frames: int, grid: GridSpec, return_cellmask=False,
-                       max_rows: int | None = None):
+                       max_rows: int | None = None, rot_comb: torch.Tensor | None = None):
     """events (E, 5) float64 on CUDA, rows [batch, frame, class, azi, ele] in dataset order
     -> target rows (M, 7) float32 on CUDA [batch, frame, Gi, Gj, class, U, V]
     (== get_yolo_label per clip followed by collate_fn's label half).
 
     With ``max_rows`` (e.g. ``E * Ga * Ge``, or ``4 * E`` for the reference's g_overlap = 0.5) the
-    result is a ``DeviceRows`` and nothing synchronises with the host."""
+    result is a ``DeviceRows`` and nothing synchronises with the host.
+    ``rot_comb`` (int8 CUDA tensor, one RotationAug combination 0..15 per clip / batch index): the
+    label half of the rotation augmentation is applied before the cell test."""
     require_cuda(events, "label_rows_batched")
     if events.dtype != torch.float64 or events.dim() != 2 or events.shape[1] != 5:
         raise ValueError("events must be a float64 tensor of shape (E, 5)")
@@ -77,17 +79,21 @@ def label_rows_batched(events: torch.Tensor, nb_label_frames: int, grid: GridSpe
         ws = torch.empty(max(L.adyolo_label_workspace_bytes(E), 64), dtype=torch.uint8, device=events.device)
         cellmask = torch.empty(max(E, 1), dtype=torch.int32, device=events.device)
         total = torch.zeros(1, dtype=torch.int64, device=events.device)
-        check(L.adyolo_label_cells(ptr(events), E, int(nb_label_frames), C.byref(grid.c), ptr(cellmask), ptr(total),
-                                   ptr(ws), stream_ptr()), "adyolo_label_cells")
+        if rot_comb is not None:
+            if rot_comb.dtype != torch.int8 or not rot_comb.is_cuda:
+                raise ValueError("rot_comb must be an int8 CUDA tensor")
+            rot_comb = rot_comb.contiguous()
+        check(L.adyolo_label_cells(ptr(events), E, int(nb_label_frames), C.byref(grid.c), ptr(rot_comb), ptr(cellmask),
+                                   ptr(total), ptr(ws), stream_ptr()), "adyolo_label_cells")
         if max_rows is not None:
             rows = torch.empty((int(max_rows), 7), dtype=torch.float32, device=events.device)
-            check(L.adyolo_label_rows(ptr(events), E, C.byref(grid.c), ptr(cellmask), ptr(ws), ptr(rows), int(max_rows),
-                                      stream_ptr()), "adyolo_label_rows")
+            check(L.adyolo_label_rows(ptr(events), E, C.byref(grid.c), ptr(rot_comb), ptr(cellmask), ptr(ws), ptr(rows),
+                                      int(max_rows), stream_ptr()), "adyolo_label_rows")
             return DeviceRows(rows, total)
         M = int(total.item())   # the one host sync of the label path (sizes the output)
         rows = torch.empty((M, 7), dtype=torch.float32, device=events.device)
-        check(L.adyolo_label_rows(ptr(events), E, C.byref(grid.c), ptr(cellmask), ptr(ws), ptr(rows), M, stream_ptr()),
-              "adyolo_label_rows")
+        check(L.adyolo_label_rows(ptr(events), E, C.byref(grid.c), ptr(rot_comb), ptr(cellmask), ptr(ws), ptr(rows), M,
+                                  stream_ptr()), "adyolo_label_rows")
     if return_cellmask:
         return rows, cellmask[:E]
     return rows

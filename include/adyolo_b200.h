@@ -66,6 +66,14 @@ int adyolo_features_foa(const int16_t* audio, int B, int64_t N, const adyolo_fro
                         const float* mean, const float* inv_std, float* out, void* workspace,
                         int apply_topdb, void* stream);
 
+/* adyolo_features_foa with the FOA rotation augmentation (RotationAug._rotate,
+ * utils/augmentations.py:84-111) fused in: rot_comb = device int8 (B) combination number 0..15
+ * per clip (NULL = none).  Equivalent to sign-flipping / swapping the int16 channels before
+ * extraction (except that -1 * -32768 does not wrap as numpy int16 does).                      */
+int adyolo_features_foa_rot(const int16_t* audio, int B, int64_t N, const adyolo_frontend_cfg* cfg,
+                            const float* mean, const float* inv_std, const int8_t* rot_comb, float* out,
+                            void* workspace, int apply_topdb, void* stream);
+
 /* Second half of adyolo_features_foa when it was called with apply_topdb = 0: applies the
  * power_to_db top_db clamp (datasets.py:265) from the per-(clip,channel) maxima left in
  * `workspace` by that call.  Exposed separately so the two kernels can be timed individually. */
@@ -119,10 +127,14 @@ typedef struct adyolo_grid_cfg {
  *   total_rows device int64[1]: M = total number of rows
  * then adyolo_label_rows writes rows device float32 (M, 7) [batch, frame, Gi, Gj, class, U, V].  */
 size_t adyolo_label_workspace_bytes(int64_t E);
+/* rot_comb: device int8 (n_clips) rotation combination per batch index, or NULL: the label half
+ * of RotationAug._rotate (augmentations.py:98-109) is applied to (azi, ele) before the cell test. */
 int adyolo_label_cells(const double* events, int64_t E, int nb_label_frames, const adyolo_grid_cfg* cfg,
-                       uint32_t* cellmask, int64_t* total_rows, void* workspace, void* stream);
-int adyolo_label_rows(const double* events, int64_t E, const adyolo_grid_cfg* cfg, const uint32_t* cellmask,
-                      const void* workspace, float* rows, int64_t max_rows, void* stream);
+                       const int8_t* rot_comb, uint32_t* cellmask, int64_t* total_rows, void* workspace,
+                       void* stream);
+int adyolo_label_rows(const double* events, int64_t E, const adyolo_grid_cfg* cfg, const int8_t* rot_comb,
+                      const uint32_t* cellmask, const void* workspace, float* rows, int64_t max_rows,
+                      void* stream);
 
 /* ADYOLOloss decode + distance_between_polar_coordinates + responsibility (loss.py:193-226):
  *   logit  device float32 (B, T, Ga*Ge*A*(C+3));  target device float32 (M, 7)

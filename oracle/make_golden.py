@@ -194,6 +194,24 @@ def main():
         lo[f"C{C}_grad"] = logit.grad.numpy()
         lo[f"C{C}_D"] = D.numpy()
     np.savez_compressed(os.path.join(GOLD, "loss_ref.npz"), **lo)
+
+    # ---- rotation augmentation (reference class, all 16 combinations)
+    import utils.augmentations as ref_aug
+    pa = ref_shims.ref_params(12)
+    pa["aug_config"]["rotation_augment"] = True
+    rot = ref_aug.RotationAug(pa, is_valid=False)
+    rng = np.random.default_rng(77)
+    snippet = rng.integers(-32768, 32768, size=(96, 4)).astype(np.int16)
+    snippet[0] = [-32768, -32768, 32767, -32768]                      # int16 wrap case of -1 * -32768
+    lab = synth_labels(5, 20, 12)
+    ro = {"snippet": snippet, "label_frames": np.asarray([fr for fr, evs in lab.items() for _ in evs], np.int64),
+          "label_events": np.asarray([ev for fr, evs in lab.items() for ev in evs], np.float64)}
+    for c in range(16):
+        a2, l2 = rot._rotate(snippet.copy(), copy.deepcopy(lab), comb_no=c)   # augmentations.py:84-111
+        ro[f"audio_{c}"] = np.asarray(a2)
+        ro[f"events_{c}"] = np.asarray([ev for fr, evs in l2.items() for ev in evs], np.float64)
+        ro[f"rows_{c}"] = np.asarray(flp.get_yolo_label(copy.deepcopy(l2), 20), np.float64)
+    np.savez_compressed(os.path.join(GOLD, "rotation.npz"), **ro)
     print("golden fixtures written to", GOLD)
     for fn in sorted(os.listdir(GOLD)):
         print(" ", fn, os.path.getsize(os.path.join(GOLD, fn)))

@@ -44,7 +44,7 @@ extern "C" int emu_features_foa(const int16_t* audio, int B, long long N, const 
     for (int tid = 0; tid < 150; ++tid) { int q = tid / 25, n2 = tid % 25; int f1 = q < 3 ? q : q - 3; if (f1 < nf) stage1_task(s_samples, s_x1, q, n2, wcs[2 * n2], wcs[2 * n2 + 1]); }
     // ---- stage 2a (all threads, then "barrier")
     std::vector<Stage2Regs> R(NTHREADS);
-    for (int tid = 0; tid < NTHREADS; ++tid) { int L = std::min(tid, 149); stage2a_task(s_x1, L / 50, (L % 50) >> 1, L & 1, dc0, dc1, R[tid]); }
+    for (int tid = 0; tid < NTHREADS; ++tid) { int L = std::min(tid, 149); stage2a_task(s_x1, L / 50, (L % 50) >> 1, L & 1, dc0, dc1, 1.f, 1.f, R[tid]); }
     // ---- stage 2b: lane pairs exchange
     for (int tid = 0; tid < NTHREADS; tid += 2) {
       for (int k2 = 0; k2 < 25; ++k2) {

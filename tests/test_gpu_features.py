@@ -190,3 +190,33 @@ def test_scaler_action_single_gpu(A):
         assert (np.abs(got[grp]["std"] - ref[grp]["std"]) <= 1e-5 * scale + 1e-9).all()
         assert (np.abs(got[grp]["max"] - ref[grp]["max"]) <= 1e-4 * np.maximum(np.abs(ref[grp]["max"]), scale)).all()
         assert (np.abs(got[grp]["min"] - ref[grp]["min"]) <= 1e-4 * np.maximum(np.abs(ref[grp]["min"]), scale)).all()
+
+
+def test_fused_rotation_augmentation_all_16_combinations(A, scaler2021):
+    """RotationAug fused into the front end (channel signs / swap) and into the
+    label kernel.  Oracle = reference rotation of the int16 audio + label dict (pinned numpy
+    restatement) followed by the plain feature / cell oracles."""
+    from oracle import augment_np, assign_np
+    rng = np.random.default_rng(12)
+    B, N = 16, 24000
+    t = np.arange(N) / 24000.0
+    s = 4000 * np.sin(2 * np.pi * 700 * t) * (t > 0.3)
+    x = rng.standard_normal((B, N, 4)) * 300 + s[None, :, None] * np.array([1.0, 0.6, -0.3, 0.7])[None, None, :]
+    x[:, :2400] = 0                                                # leading digital silence: DC term matters
+    clips = np.clip(np.round(x), -32767, 32767).astype(np.int16)   # no -32768: the reference wraps it (int16)
+    comb = np.arange(16, dtype=np.int8)
+    sd = _scaler_dev(A, scaler2021)
+    out = A.features_batched(torch.from_numpy(clips).cuda(), sd, rot_comb=torch.from_numpy(comb).cuda()).cpu().numpy()
+    for b in range(B):
+        a2, _ = augment_np.rotate(clips[b], {}, int(comb[b]))
+        ref = F.features_foa_stack(np.ascontiguousarray(a2), scaler=scaler2021)
+        assert _mel_err(out[b, :4], ref[:4]) < 1e-4, b
+        assert np.abs(out[b, 4:] - ref[4:]).max() < 1e-3, b
+    # labels
+    grid = A.labels.GridSpec(12, 5, [45, 45], 0.5)
+    E = 4000
+    ev = np.stack([rng.integers(0, B, E), rng.integers(0, 12, E), rng.integers(0, 12, E),
+                   rng.integers(-180, 181, E), rng.integers(-90, 91, E)], 1).astype(np.float64)
+    rows = A.label_rows_batched(torch.from_numpy(ev).cuda(), 10, grid, rot_comb=torch.from_numpy(comb).cuda()).cpu().numpy()
+    want = assign_np.events_to_rows(augment_np.rotate_events(ev, comb), 10).astype(np.float32)
+    assert np.array_equal(rows, want)
