@@ -55,6 +55,8 @@ __device__ __forceinline__ void issue_tile_copy(uint32_t* samples, const int16_t
 }
 
 // ------------------------------------------------------------------------------------------------
+// ROT: compile the fused rotation augmentation in (training with --augment) or out (no overhead).
+template <bool ROT>
 __global__ void __launch_bounds__(NTHREADS, 2)
 frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_per_clip, int ntiles,
                     const FrontendTables* __restrict__ tab, const float* __restrict__ mean,
@@ -95,7 +97,7 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
     for (; tile < ntiles; tile += gridDim.x) {
         const int b = tile / tiles_per_clip, tb = tile % tiles_per_clip;
         const int t0 = tb * TF, nf = min(TF, T - t0);
-        const unsigned rb = rot ? rot_bits_rt(rot[b]) : 0u;   // rotation augmentation of this clip (0 = none)
+        const unsigned rb = ROT ? rot_bits_rt(rot[b]) : 0u;   // rotation augmentation of this clip (0 = none)
         cp_async_wait_all();
         __syncthreads();
 
@@ -123,8 +125,8 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
         Stage2Regs R;
         {
             // channel signs of this lane's packed FFT: role A = (W, Y), role B = (Z, X)
-            const float sre = (r2 && (rb & 2u)) ? -1.f : 1.f;
-            const float sim = ((r2 ? (rb >> 2) : rb) & 1u) ? -1.f : 1.f;
+            const float sre = (ROT && r2 && (rb & 2u)) ? -1.f : 1.f;
+            const float sim = (ROT && (((r2 ? (rb >> 2) : rb) & 1u))) ? -1.f : 1.f;
             stage2a_task(s_x1, f2, t2, r2, dc0, dc1, sre, sim, R);
         }
         __syncthreads();  // every X1 read is done -> V may overwrite the exchange buffer
@@ -169,20 +171,32 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
                 v[i] = part ? acc[5 + (i < 3 ? i : 0)] : db;
             }
             if (part && !(v[0] == v[0] && v[1] == v[1] && v[2] == v[2])) atomicOr(flags, 1);  // datasets.py:277
-            if (part) {                                 // rotation: intensity sign follows its channel's sign
+            if (ROT && part) {                          // rotation: intensity sign follows its channel's sign
                 v[0] = (rb & 1u) ? -v[0] : v[0];        // Y
                 v[1] = (rb & 2u) ? -v[1] : v[1];        // Z
                 v[2] = (rb & 4u) ? -v[2] : v[2];        // X
             }
             const int T64 = T * NMEL;
-            const bool swap = rb & 8u;                  // X <-> Y: mel ch 1<->3, IV ch 4<->6
+            if (ROT) {
+                const bool swap = rb & 8u;              // X <-> Y: mel ch 1<->3, IV ch 4<->6
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (i == 3 && part) break;
-                int c = part * 4 + i;
-                if (swap) c = part ? (i == 0 ? 6 : (i == 2 ? 4 : c)) : (i == 1 ? 3 : (i == 3 ? 1 : c));
-                const float2 k = s_scale[c * NMEL + j];
-                out_tile[(c * T + f) * NMEL + j] = fmaf(v[i], k.x, k.y);
+                for (int i = 0; i < 4; ++i) {
+                    if (i == 3 && part) break;
+                    int c = part * 4 + i;
+                    if (swap) c = part ? (i == 0 ? 6 : (i == 2 ? 4 : c)) : (i == 1 ? 3 : (i == 3 ? 1 : c));
+                    const float2 k = s_scale[c * NMEL + j];
+                    out_tile[(c * T + f) * NMEL + j] = fmaf(v[i], k.x, k.y);
+                }
+            } else {
+                const int c0i = part * 4;
+                float* o = out_tile + (c0i * T + f) * NMEL + j;
+                const float2* sc = s_scale + c0i * NMEL + j;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (i == 3 && part) break;
+                    const float2 k = sc[i * NMEL];
+                    o[i * T64] = fmaf(v[i], k.x, k.y);
+                }
             }
         }
         // the barrier at the top of the next iteration orders these V reads before its stage 1
@@ -274,15 +288,22 @@ int launch_features_foa(const int16_t* audio, int B, long long N, const float* m
     ADY_CUDA_CHECK(cudaGetDevice(&dev));
     ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (configured_dev != dev) {
-        ADY_CUDA_CHECK(cudaFuncSetAttribute(frontend_foa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        ADY_CUDA_CHECK(cudaFuncSetAttribute(frontend_foa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            SmemLayout::total));
+        ADY_CUDA_CHECK(cudaFuncSetAttribute(frontend_foa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             SmemLayout::total));
         configured_dev = dev;
     }
     const int grid = (int)(ntiles < 2LL * sms ? ntiles : 2LL * sms);
     // window scale: 2^-15 (int16 -> [-1,1)) * 1/2 (channel split), DC terms scaled by the same 1/2
-    frontend_foa_kernel<<<grid, NTHREADS, SmemLayout::total, stream>>>(
-        audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc_offset * 300.0f, -dc_offset * 150.0f, rot, out,
-        flags);
+    if (rot)
+        frontend_foa_kernel<true><<<grid, NTHREADS, SmemLayout::total, stream>>>(
+            audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc_offset * 300.0f, -dc_offset * 150.0f, rot, out,
+            flags);
+    else
+        frontend_foa_kernel<false><<<grid, NTHREADS, SmemLayout::total, stream>>>(
+            audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc_offset * 300.0f, -dc_offset * 150.0f, rot, out,
+            flags);
     ADY_LAUNCH_CHECK("frontend_foa_kernel");
     if (apply_topdb) return launch_features_foa_clamp(out, B, N, mean, istd, top_db, ws, stream);
     return ADY_OK;
