@@ -91,15 +91,21 @@ size_t adyolo_frontend_workspace_bytes(const adyolo_frontend_cfg* cfg, int B, in
     return frontend_workspace_bytes(B, (long long)N);
 }
 
-int adyolo_features_foa_rot(const int16_t* audio, int B, int64_t N, const adyolo_frontend_cfg* cfg,
-                            const float* mean, const float* inv_std, const int8_t* rot_comb, float* out,
-                            void* workspace, int apply_topdb, void* stream) {
+int adyolo_features_foa_views(const int16_t* audio, const int64_t* clip_offsets, int B, int64_t N,
+                              const adyolo_frontend_cfg* cfg, const float* mean, const float* inv_std,
+                              const int8_t* rot_comb, float* out, void* workspace, int apply_topdb, void* stream) {
     int rc = check_frontend_cfg(cfg);
     if (rc) return rc;
     if (!audio || !out || !workspace) return set_error(ADY_ERR_INVALID, "features_foa: NULL pointer");
     if ((mean == nullptr) != (inv_std == nullptr)) return set_error(ADY_ERR_INVALID, "features_foa: mean and inv_std must both be given or both NULL");
     return launch_features_foa(audio, B, (long long)N, mean, inv_std, cfg->dc_offset, cfg->top_db, apply_topdb, rot_comb,
-                               out, workspace, (cudaStream_t)stream);
+                               (const long long*)clip_offsets, out, workspace, (cudaStream_t)stream);
+}
+
+int adyolo_features_foa_rot(const int16_t* audio, int B, int64_t N, const adyolo_frontend_cfg* cfg,
+                            const float* mean, const float* inv_std, const int8_t* rot_comb, float* out,
+                            void* workspace, int apply_topdb, void* stream) {
+    return adyolo_features_foa_views(audio, nullptr, B, N, cfg, mean, inv_std, rot_comb, out, workspace, apply_topdb, stream);
 }
 
 int adyolo_features_foa(const int16_t* audio, int B, int64_t N, const adyolo_frontend_cfg* cfg,

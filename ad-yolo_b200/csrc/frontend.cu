@@ -30,12 +30,12 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Frame t covers padded positions [600 t, 600 t + 1200) of the reflect-padded clip
 // (librosa.stft center=True, pad 600): y index = 600 t - 600 + idx, mirrored for t = 0, idx < 600.
 __device__ __forceinline__ void issue_tile_copy(uint32_t* samples, const int16_t* __restrict__ audio,
-                                                long long N, int b, int t0, int nf) {
+                                                long long clip_base, int t0, int nf) {
     const int tid = threadIdx.x;
     // element (idx = i0 + 80 i, pair), i = 0..14: lanes 0-15 of a warp copy the (W,Y) words of 16
     // consecutive samples, lanes 16-31 the (Z,X) words of the same samples (one 128-byte line)
     const int pair = (tid >> 4) & 1, i0 = (tid >> 5) * 16 + (tid & 15);
-    const int16_t* clip = audio + (long long)b * N * 4 + pair * 2;
+    const int16_t* clip = audio + clip_base * 4 + pair * 2;   // clip_base = first sample of the clip
     for (int f = 0; f < nf; ++f) {
         const int t = t0 + f;
         uint32_t* dst = samples + splane_base(q_of_g(2 * f + pair)) + skew(i0);  // skew(i0 + 80 i) = skew(i0) + 85 i
@@ -55,13 +55,16 @@ __device__ __forceinline__ void issue_tile_copy(uint32_t* samples, const int16_t
 }
 
 // ------------------------------------------------------------------------------------------------
-// ROT: compile the fused rotation augmentation in (training with --augment) or out (no overhead).
-template <bool ROT>
+// ROT : compile the fused rotation augmentation in (training with --augment) or out (no overhead).
+// VIEW: clips are views into one resident buffer, clip b starting at sample clip_off[b] (on-the-fly
+//       chunking: overlapping 20-s windows of resident 60-s files, preprocess.py:13-48) instead of
+//       a dense (B, N, 4) batch.
+template <bool ROT, bool VIEW>
 __global__ void __launch_bounds__(NTHREADS, 2)
 frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_per_clip, int ntiles,
                     const FrontendTables* __restrict__ tab, const float* __restrict__ mean,
                     const float* __restrict__ istd, float dc0, float dc1, const int8_t* __restrict__ rot,
-                    float* __restrict__ out, int* __restrict__ flags) {
+                    const long long* __restrict__ clip_off, float* __restrict__ out, int* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t* s_samples = reinterpret_cast<uint32_t*>(smem + SmemLayout::off_samples);
     float2* s_x1 = reinterpret_cast<float2*>(smem + SmemLayout::off_x1);
@@ -73,7 +76,7 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
     int tile = blockIdx.x;
     if (tile < ntiles) {
         const int b = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * TF;
-        issue_tile_copy(s_samples, audio, N, b, t0, min(TF, T - t0));
+        issue_tile_copy(s_samples, audio, VIEW ? clip_off[b] : (long long)b * N, t0, min(TF, T - t0));
     }
     cp_async_commit();
     // constant tables -> smem (once per persistent CTA)
@@ -116,7 +119,7 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
             const int nt = tile + gridDim.x;
             if (nt < ntiles) {
                 const int nb = nt / tiles_per_clip, nt0 = (nt % tiles_per_clip) * TF;
-                issue_tile_copy(s_samples, audio, N, nb, nt0, min(TF, T - nt0));
+                issue_tile_copy(s_samples, audio, VIEW ? clip_off[nb] : (long long)nb * N, nt0, min(TF, T - nt0));
             }
             cp_async_commit();
         }
@@ -218,19 +221,20 @@ clamp_topdb_kernel(float* __restrict__ out, const float* __restrict__ mean, cons
     float4* base = reinterpret_cast<float4*>(out + ((long long)b * NCH_FOA + c) * T * NMEL);
     const int n4 = T * (NMEL / 4);
     const int j4 = threadIdx.x & 15;                      // this thread always sees mel bins 4*j4..4*j4+3
-    float mu[4], is[4];
+    float mu[4], is[4], sd[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         mu[q] = mean ? mean[c * NMEL + 4 * j4 + q] : 0.f;
         is[q] = istd ? istd[c * NMEL + 4 * j4 + q] : 1.f;
+        sd[q] = 1.0f / is[q];                              // un-standardise with a multiply, not a divide per element
     }
     // pass 1: max of dB = v/istd + mean  (un-standardise; exact enough: the clamp value itself is
     // recomputed from the dB max below, and values are compared in the standardised domain)
     float mx = -INFINITY;
     for (int i = threadIdx.x; i < n4; i += 256) {          // 256 % 16 == 0 -> j4 is loop-invariant
         const float4 v = base[i];
-        mx = fmaxf(mx, fmaxf(fmaxf(v.x / is[0] + mu[0], v.y / is[1] + mu[1]),
-                             fmaxf(v.z / is[2] + mu[2], v.w / is[3] + mu[3])));
+        mx = fmaxf(mx, fmaxf(fmaxf(fmaf(v.x, sd[0], mu[0]), fmaf(v.y, sd[1], mu[1])),
+                             fmaxf(fmaf(v.z, sd[2], mu[2]), fmaf(v.w, sd[3], mu[3]))));
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -268,9 +272,27 @@ int launch_features_foa_clamp(float* out, int B, long long N, const float* mean,
     return ADY_OK;
 }
 
+template <bool ROT, bool VIEW>
+static int launch_frontend_inst(int grid, cudaStream_t stream, const int16_t* audio, long long N, int T, int tpc, int ntiles,
+                                const FrontendTables* tab, const float* mean, const float* istd, float dc0, float dc1,
+                                const int8_t* rot, const long long* clip_off, float* out, int* flags) {
+    static int configured_dev = -1;
+    int dev = 0;
+    ADY_CUDA_CHECK(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        ADY_CUDA_CHECK(cudaFuncSetAttribute(frontend_foa_kernel<ROT, VIEW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            SmemLayout::total));
+        configured_dev = dev;
+    }
+    frontend_foa_kernel<ROT, VIEW><<<grid, NTHREADS, SmemLayout::total, stream>>>(
+        audio, N, T, tpc, ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, flags);
+    ADY_LAUNCH_CHECK("frontend_foa_kernel");
+    return ADY_OK;
+}
+
 int launch_features_foa(const int16_t* audio, int B, long long N, const float* mean, const float* istd,
-                        float dc_offset, float top_db, int apply_topdb, const int8_t* rot, float* out, void* ws,
-                        cudaStream_t stream) {
+                        float dc_offset, float top_db, int apply_topdb, const int8_t* rot, const long long* clip_off,
+                        float* out, void* ws, cudaStream_t stream) {
     const long long T = N / HOP;
     if (B <= 0 || T <= 0) return set_error(ADY_ERR_INVALID, "features_foa: need B>0 and at least %d samples", HOP);
     if (N <= HOP) return set_error(ADY_ERR_INVALID, "features_foa: reflect padding needs N > %d samples", HOP);
@@ -283,28 +305,21 @@ int launch_features_foa(const int16_t* audio, int B, long long N, const float* m
     int* flags = reinterpret_cast<int*>(ws);
     ADY_CUDA_CHECK(cudaMemsetAsync(ws, 0, 16, stream));
 
-    static int configured_dev = -1;
     int dev = 0, sms = 0;
     ADY_CUDA_CHECK(cudaGetDevice(&dev));
     ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (configured_dev != dev) {
-        ADY_CUDA_CHECK(cudaFuncSetAttribute(frontend_foa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            SmemLayout::total));
-        ADY_CUDA_CHECK(cudaFuncSetAttribute(frontend_foa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            SmemLayout::total));
-        configured_dev = dev;
-    }
     const int grid = (int)(ntiles < 2LL * sms ? ntiles : 2LL * sms);
     // window scale: 2^-15 (int16 -> [-1,1)) * 1/2 (channel split), DC terms scaled by the same 1/2
-    if (rot)
-        frontend_foa_kernel<true><<<grid, NTHREADS, SmemLayout::total, stream>>>(
-            audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc_offset * 300.0f, -dc_offset * 150.0f, rot, out,
-            flags);
+    const float dc0 = dc_offset * 300.0f, dc1 = -dc_offset * 150.0f;
+    if (rot && clip_off)
+        rc = launch_frontend_inst<true, true>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, flags);
+    else if (rot)
+        rc = launch_frontend_inst<true, false>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, flags);
+    else if (clip_off)
+        rc = launch_frontend_inst<false, true>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, flags);
     else
-        frontend_foa_kernel<false><<<grid, NTHREADS, SmemLayout::total, stream>>>(
-            audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc_offset * 300.0f, -dc_offset * 150.0f, rot, out,
-            flags);
-    ADY_LAUNCH_CHECK("frontend_foa_kernel");
+        rc = launch_frontend_inst<false, false>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, flags);
+    if (rc) return rc;
     if (apply_topdb) return launch_features_foa_clamp(out, B, N, mean, istd, top_db, ws, stream);
     return ADY_OK;
 }

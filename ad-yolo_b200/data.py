@@ -1,0 +1,199 @@
+"""Raw-audio data path either side of the hot path.  Host plumbing only.
+
+* ``load_wav2npy`` / ``load_csv2dict``: the reference's on-disk formats (``utility.py:219-246``,
+  ``datasets.py:99-118``): int16 4-channel wav, 5-column polar csv ``frame,class,source,azi,ele``.
+* ``chunk_plan`` / ``ResidentClips``: the ``chunking`` action (``preprocess.py:13-85``) without the
+  41x-duplicated chunk files: whole training files stay resident in HBM as int16, a chunk is a
+  *view* (sample offset) handed to ``adyolo_features_foa_views`` and its label rows are the file's
+  events windowed and re-indexed exactly as ``chunk_instance`` does.  Chunk names follow the
+  reference's ``<file>_chunkNNN`` convention so samplers and logs stay comparable.
+* ``EpochSampler``: the without-replacement epoch sampling of ``datasets.py:67-92`` (same
+  ``random`` call sequence, so the same seed yields the same file lists; the pool of remaining
+  files is checkpointable like ``get_remaining_file`` / ``init_remaining_file_from_list``).
+"""
+from __future__ import annotations
+
+import copy
+import random
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, require_cuda, stream_ptr
+import ctypes as C
+
+
+def load_wav2npy(wav_pth):
+    """datasets.py:99-101 / utility.py:219-221 -> int16 (T, 4)."""
+    import scipy.io.wavfile as wav
+    _, audio = wav.read(wav_pth)
+    return audio
+
+
+def load_csv2dict(csv_pth):
+    """datasets.py:103-118 / utility.py:233-246."""
+    label = {}
+    with open(csv_pth, "r") as fid:
+        for line in fid:
+            words = line.strip().split(",")
+            if len(words) < 5:
+                continue
+            frame_idx = int(words[0])
+            label.setdefault(frame_idx, [])
+            if len(words) == 5:
+                label[frame_idx].append([int(words[1]), int(words[2]), float(words[3]), float(words[4])])
+            elif len(words) == 6:
+                label[frame_idx].append([int(words[1]), int(words[2]), float(words[3]), float(words[4]), float(words[5])])
+    return label
+
+
+def chunk_plan(n_samples: int, sr=24000, chunk_window_s=20, chunk_stride_s=1, label_hop_len_s=0.1):
+    """Geometry of ``chunk_instance`` (preprocess.py:27-37) for one file of ``n_samples`` samples:
+    -> dict(pad, n_chunks, wav_window, wav_stride, csv_window, csv_stride)."""
+    wav_window = sr * chunk_window_s
+    wav_stride = sr * chunk_stride_s
+    csv_window = int(chunk_window_s / label_hop_len_s)
+    csv_stride = int(chunk_stride_s / label_hop_len_s)
+    if n_samples < wav_window:
+        raise ValueError("file shorter than one chunk window")   # the reference's sliding_window_view raises too
+    rem = (n_samples - wav_window) % wav_stride
+    pad = wav_stride - rem if rem != 0 else 0
+    n_chunks = (n_samples + pad - wav_window) // wav_stride + 1
+    return {"pad": int(pad), "n_chunks": int(n_chunks), "wav_window": int(wav_window), "wav_stride": int(wav_stride),
+            "csv_window": csv_window, "csv_stride": csv_stride}
+
+
+class ResidentClips:
+    """Training files resident on the device as one int16 (S, 4) buffer + their event tables."""
+
+    def __init__(self, device="cuda", sr=24000, chunk_window_s=20, chunk_stride_s=1, label_hop_len_s=0.1):
+        self.device = torch.device(device)
+        self.geom = dict(sr=sr, chunk_window_s=chunk_window_s, chunk_stride_s=chunk_stride_s,
+                         label_hop_len_s=label_hop_len_s)
+        self._host, self._files, self._events, self._plans, self._index = [], [], [], [], {}
+        self._cursor = 0
+        self.audio = None
+
+    def add(self, name: str, audio_i16: np.ndarray, label: dict):
+        a = np.ascontiguousarray(audio_i16, dtype=np.int16)
+        if a.ndim != 2 or a.shape[1] != 4:
+            raise ValueError("audio must be int16 (T, 4)")
+        plan = chunk_plan(len(a), **self.geom)
+        if plan["pad"]:
+            a = np.pad(a, [(0, plan["pad"]), (0, 0)], "constant")      # preprocess.py:33
+        ev = np.asarray([[fr, e[0], e[2], e[3]] for fr, evs in label.items() for e in evs], dtype=np.float64).reshape(-1, 4)
+        self._index[name] = len(self._files)
+        self._files.append((name, self._cursor, len(a)))
+        self._events.append(ev)                                         # [frame, class, azi, ele] in dict order
+        self._plans.append(plan)
+        self._host.append(a)
+        self._cursor += len(a)
+        self.audio = None
+
+    def finalize(self):
+        if self.device.type == "cuda":
+            require_cuda(None, "ResidentClips")
+        host = np.concatenate(self._host, 0) if self._host else np.zeros((0, 4), np.int16)
+        self.audio = torch.from_numpy(host).to(self.device)
+        return self
+
+    def chunk_names(self):
+        """Names the reference's chunking action would have written (preprocess.py:80)."""
+        return [f"{name}_chunk{i + 1:03d}" for (name, _, _), p in zip(self._files, self._plans) for i in range(p["n_chunks"])]
+
+    def _resolve(self, chunk_name: str):
+        base, _, num = chunk_name.rpartition("_chunk")
+        fi = self._index[base]
+        return fi, int(num) - 1
+
+    def batch(self, chunk_names):
+        """-> (offsets int64 (B,) on device, events (E,5) float64 on device [batch, frame, class, azi, ele],
+        N samples per chunk, nb_label_frames).  Event order = chunk order, then the file's dict order
+        restricted to the chunk window (== load_csv2dict of the chunk csv written by write_dict2csv)."""
+        offs, evs = [], []
+        for b, cn in enumerate(chunk_names):
+            fi, ci = self._resolve(cn)
+            _, start, _ = self._files[fi]
+            p = self._plans[fi]
+            if not 0 <= ci < p["n_chunks"]:
+                raise IndexError(cn)
+            offs.append(start + ci * p["wav_stride"])
+            ev = self._events[fi]
+            f0 = ci * p["csv_stride"]
+            sel = (ev[:, 0] >= f0) & (ev[:, 0] < f0 + p["csv_window"])
+            e = ev[sel]
+            # chunk_instance walks frame_idx = 0..window-1 in order (preprocess.py:41-45)
+            order = np.argsort(e[:, 0], kind="stable")
+            e = e[order]
+            evs.append(np.column_stack([np.full(len(e), b, np.float64), e[:, 0] - f0, e[:, 1], e[:, 2], e[:, 3]]))
+        p0 = self._plans[self._resolve(chunk_names[0])[0]]
+        events = np.concatenate(evs, 0) if evs else np.zeros((0, 5))
+        return (torch.tensor(offs, dtype=torch.int64, device=self.device),
+                torch.from_numpy(events.reshape(-1, 5)).to(self.device), p0["wav_window"], p0["csv_window"])
+
+
+def features_batched_views(audio_resident: torch.Tensor, offsets: torch.Tensor, n_samples: int, scaler_dev=None,
+                           rot_comb: torch.Tensor | None = None, apply_topdb: bool = True) -> torch.Tensor:
+    """Features of B clip *views* of a resident int16 (S, 4) buffer -> (B, 7, T, 64) float32."""
+    from .features import _cfg, _workspace
+    require_cuda(audio_resident, "features_batched_views")
+    if audio_resident.dtype != torch.int16 or audio_resident.dim() != 2 or audio_resident.shape[1] != 4:
+        raise ValueError("resident audio must be an int16 tensor of shape (S, 4)")
+    offsets = offsets.to(audio_resident.device, torch.int64).contiguous()
+    B = offsets.shape[0]
+    if B and (int(offsets.min()) < 0 or int(offsets.max()) + n_samples > audio_resident.shape[0]):
+        raise IndexError("clip view out of range")
+    cfg = _cfg()
+    L = _lib.lib()
+    T = n_samples // 600
+    with torch.cuda.device(audio_resident.device):
+        out = torch.empty((B, 7, T, 64), dtype=torch.float32, device=audio_resident.device)
+        ws = _workspace(L.adyolo_frontend_workspace_bytes(C.byref(cfg), B, n_samples), audio_resident.device)
+        mean, istd = scaler_dev if scaler_dev is not None else (None, None)
+        check(L.adyolo_features_foa_views(ptr(audio_resident.contiguous()), ptr(offsets), B, n_samples, C.byref(cfg),
+                                          ptr(mean), ptr(istd), ptr(rot_comb), ptr(out), ptr(ws),
+                                          1 if apply_topdb else 0, stream_ptr()), "adyolo_features_foa_views")
+    return out
+
+
+class EpochSampler:
+    """datasets.py:67-98: ``nb_samples`` names per epoch drawn without replacement from a pool
+    that is carried across epochs (and checkpoints) and refilled when it runs dry."""
+
+    def __init__(self, total_filelist, nb_samples: int):
+        self.total_filelist = list(total_filelist)
+        self.remaining_file = copy.deepcopy(self.total_filelist)
+        self.nb_samples = nb_samples
+        self.filelist = []
+
+    def sample_filelist_for_train_iter(self):
+        self.filelist = []
+        if len(self.remaining_file) >= self.nb_samples:
+            self.filelist = random.sample(self.remaining_file, self.nb_samples)
+            for fnm in self.filelist:
+                self.remaining_file.remove(fnm)
+        else:
+            if len(self.remaining_file) <= 0:
+                self.remaining_file = copy.deepcopy(self.total_filelist)
+                self.filelist = random.sample(self.remaining_file, self.nb_samples)
+                for fnm in self.filelist:
+                    self.remaining_file.remove(fnm)
+            else:
+                random.shuffle(self.remaining_file)
+                pre_sampled = copy.deepcopy(self.remaining_file)
+                self.remaining_file = copy.deepcopy(self.total_filelist)
+                self.filelist = random.sample(self.remaining_file, (self.nb_samples - len(pre_sampled)))
+                for fnm in self.filelist:
+                    self.remaining_file.remove(fnm)
+                self.filelist.extend(pre_sampled)
+        return self.filelist
+
+    def init_remaining_file_from_list(self, remaining_file):
+        self.remaining_file = remaining_file
+
+    def get_remaining_file(self):
+        return self.remaining_file
+
+    def get_filelist(self):
+        return self.filelist

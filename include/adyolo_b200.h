@@ -74,6 +74,15 @@ int adyolo_features_foa_rot(const int16_t* audio, int B, int64_t N, const adyolo
                             const float* mean, const float* inv_std, const int8_t* rot_comb, float* out,
                             void* workspace, int apply_topdb, void* stream);
 
+/* adyolo_features_foa over VIEWS of one resident buffer: clip b = N samples starting at sample
+ * clip_offsets[b] (device int64 (B); even offsets) of `audio` (device int16 (S, 4)).  Serves the
+ * reference's `chunking` action (preprocess.py:13-48: 20-s windows every 1 s) without writing the
+ * 41x-duplicated chunk files: each chunk is still extracted as an independent clip (own reflect
+ * padding and top_db maximum).  rot_comb as above (may be NULL).                     */
+int adyolo_features_foa_views(const int16_t* audio, const int64_t* clip_offsets, int B, int64_t N,
+                              const adyolo_frontend_cfg* cfg, const float* mean, const float* inv_std,
+                              const int8_t* rot_comb, float* out, void* workspace, int apply_topdb, void* stream);
+
 /* Second half of adyolo_features_foa when it was called with apply_topdb = 0: applies the
  * power_to_db top_db clamp (datasets.py:265) from the per-(clip,channel) maxima left in
  * `workspace` by that call.  Exposed separately so the two kernels can be timed individually. */

@@ -212,6 +212,41 @@ def main():
         ro[f"events_{c}"] = np.asarray([ev for fr, evs in l2.items() for ev in evs], np.float64)
         ro[f"rows_{c}"] = np.asarray(flp.get_yolo_label(copy.deepcopy(l2), 20), np.float64)
     np.savez_compressed(os.path.join(GOLD, "rotation.npz"), **ro)
+    # ---- chunking action + epoch sampler (reference functions executed as-is)
+    import random
+    import preprocess as ref_pre
+    cp = {"sr": 24000, "chunk_window_s": 20, "chunk_stride_s": 1, "label_hop_len_s": 0.1}
+    rng = np.random.default_rng(31)
+    n = int(24000 * 26.3)
+    ca = rng.integers(-3000, 3000, size=(n, 4)).astype(np.int16)
+    clab = synth_labels(9, 263, 12)
+    chunks = ref_pre.chunk_instance(ca.copy(), copy.deepcopy(clab), cp)          # preprocess.py:13-48
+    ck = {"audio_seed": np.int64(31), "n_samples": np.int64(n), "n_chunks": np.int64(len(chunks)),
+          "label_frames": np.asarray([fr for fr, evs in clab.items() for _ in evs], np.int64),
+          "label_events": np.asarray([ev for fr, evs in clab.items() for ev in evs], np.float64),
+          "chunk_sum": np.asarray([np.asarray(a, np.int64).sum() for a, _ in chunks], np.int64),
+          "chunk_first": np.asarray([np.asarray(a)[0] for a, _ in chunks], np.int64),
+          "chunk_last": np.asarray([np.asarray(a)[-1] for a, _ in chunks], np.int64),
+          "chunk_len": np.asarray([len(a) for a, _ in chunks], np.int64)}
+    rows = []
+    for ci, (_, lab) in enumerate(chunks):
+        for fr, evs in lab.items():
+            for ev in evs:
+                rows.append([ci, fr, ev[0], ev[1], ev[2], ev[3]])
+    ck["chunk_label_rows"] = np.asarray(rows, np.float64)
+
+    class _Stub:  # carries the attributes Dataset.sample_filelist_for_train_iter reads (datasets.py:67-92)
+        pass
+    names = [f"f{i:02d}" for i in range(23)]
+    stub = _Stub()
+    stub.total_filelist = list(names); stub.remaining_file = list(names); stub.nb_samples = 7; stub.filelist = []
+    random.seed(5)
+    epochs = []
+    for _ in range(9):
+        ref_datasets.Dataset.sample_filelist_for_train_iter(stub)
+        epochs.append([names.index(x) for x in stub.filelist])
+    ck["sampler_epochs"] = np.asarray(epochs, np.int64)
+    np.savez_compressed(os.path.join(GOLD, "chunking.npz"), **ck)
     print("golden fixtures written to", GOLD)
     for fn in sorted(os.listdir(GOLD)):
         print(" ", fn, os.path.getsize(os.path.join(GOLD, fn)))
