@@ -114,6 +114,17 @@ int adyolo_features_foa(const int16_t* audio, int B, int64_t N, const adyolo_fro
     return adyolo_features_foa_rot(audio, B, N, cfg, mean, inv_std, nullptr, out, workspace, apply_topdb, stream);
 }
 
+int adyolo_features_mic_logmel(const int16_t* audio, int B, int64_t N, const adyolo_frontend_cfg* cfg, const float* mean,
+                               const float* inv_std, float* out, void* spec_c64, void* workspace, int apply_topdb,
+                               void* stream) {
+    int rc = check_frontend_cfg(cfg);
+    if (rc) return rc;
+    if (!audio || !out || !spec_c64 || !workspace) return set_error(ADY_ERR_INVALID, "features_mic_logmel: NULL pointer");
+    if ((mean == nullptr) != (inv_std == nullptr)) return set_error(ADY_ERR_INVALID, "features_mic_logmel: mean and inv_std must both be given or both NULL");
+    return launch_features_mic_logmel(audio, B, (long long)N, mean, inv_std, cfg->dc_offset, cfg->top_db, apply_topdb, out,
+                                      (float2*)spec_c64, workspace, (cudaStream_t)stream);
+}
+
 int adyolo_features_foa_clamp(float* out, int B, int64_t N, const adyolo_frontend_cfg* cfg, const float* mean,
                               const float* inv_std, void* workspace, void* stream) {
     int rc = check_frontend_cfg(cfg);

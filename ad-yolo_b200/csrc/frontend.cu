@@ -59,12 +59,17 @@ __device__ __forceinline__ void issue_tile_copy(uint32_t* samples, const int16_t
 // VIEW: clips are views into one resident buffer, clip b starting at sample clip_off[b] (on-the-fly
 //       chunking: overlapping 20-s windows of resident 60-s files, preprocess.py:13-48) instead of
 //       a dense (B, N, 4) batch.
-template <bool ROT, bool VIEW>
+// MIC : microphone-array format: 4 log-mel channels into a (B, 10, T, 64) tensor and the four
+//       channel spectra written to `spec` (B, T, 601, 4) complex64 for the GCC-PHAT kernel; no
+//       intensity vectors (ROT must be false).
+template <bool ROT, bool VIEW, bool MIC>
 __global__ void __launch_bounds__(NTHREADS, 2)
 frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_per_clip, int ntiles,
                     const FrontendTables* __restrict__ tab, const float* __restrict__ mean,
                     const float* __restrict__ istd, float dc0, float dc1, const int8_t* __restrict__ rot,
-                    const long long* __restrict__ clip_off, float* __restrict__ out, int* __restrict__ flags) {
+                    const long long* __restrict__ clip_off, float* __restrict__ out, float2* __restrict__ spec,
+                    int* __restrict__ flags) {
+    constexpr int NCH_OUT = MIC ? 10 : NCH_FOA;
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t* s_samples = reinterpret_cast<uint32_t*>(smem + SmemLayout::off_samples);
     float2* s_x1 = reinterpret_cast<float2*>(smem + SmemLayout::off_x1);
@@ -94,6 +99,7 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
     const int L = min(tid, 6 * 25 - 1);                      // stage 2: lane pairs (A,B) adjacent
     const int f2 = L / 50, t2 = (L % 50) >> 1, r2 = L & 1;
     const float c0 = r2 == 0 ? 1.0f : (1.0f / 3.0f);
+    const int kt = (625 * t2) % 1200;
     float2* const vbase = s_x1 + v_base(f2) + 50 * t2 + r2;
     const int warp = tid >> 5, lane = tid & 31;
 
@@ -137,23 +143,38 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
         // ---- stage 2b
         {
             const bool valid = tid < 150 && f2 < nf;
+            float2* const sp = MIC ? spec + ((long long)b * T + (t0 + f2)) * (NBIN * 4) + 2 * r2 : nullptr;
+            int ktt = kt;
+            if (MIC) asm volatile("" : "+r"(ktt));   // keep the 25 bin indices from being hoisted (and spilled)
 #pragma unroll
             for (int k2 = 0; k2 < 25; ++k2) {
                 SlotMine m;
                 SlotOut mine, other;
                 slot_split(R.P[k2], R.Q[(25 - k2) % 25], c0, m, mine);
-                other.s0re = __shfl_xor_sync(0xffffffffu, mine.s0re, 1);
-                other.s0im = __shfl_xor_sync(0xffffffffu, mine.s0im, 1);
-                other.e = __shfl_xor_sync(0xffffffffu, mine.e, 1);
-                float iva, ivb;
-                slot_finish(m, mine, other, r2, iva, ivb);
-                if (valid) slot_store(vbase, k2, m.P0, m.P1, iva, ivb);
+                if (!MIC) {
+                    other.s0re = __shfl_xor_sync(0xffffffffu, mine.s0re, 1);
+                    other.s0im = __shfl_xor_sync(0xffffffffu, mine.s0im, 1);
+                    other.e = __shfl_xor_sync(0xffffffffu, mine.e, 1);
+                    float iva, ivb;
+                    slot_finish(m, mine, other, r2, iva, ivb);
+                    if (valid) slot_store(vbase, k2, m.P0, m.P1, iva, ivb);
+                } else if (valid) {
+                    vbase[2 * k2] = make_float2(m.P0, m.P1);
+                    // spectra of this lane's two channels at bin k (k > 600 holds the conjugate of
+                    // bin 1200 - k); the four channels of a bin fill exactly one 32-byte sector
+                    int k = ktt + (576 * k2) % 1200;
+                    k = k >= 1200 ? k - 1200 : k;
+                    const float sg = k > 600 ? -1.f : 1.f;
+                    const int kb = k > 600 ? 1200 - k : k;
+                    sp[kb * 4] = make_float2(m.S0.re, sg * m.S0.im);
+                    sp[kb * 4 + 1] = make_float2(m.S1.re, sg * m.S1.im);
+                }
             }
         }
         __syncthreads();
 
         // ---- mel projection + log + standardise + store (static schedule, balanced over warps)
-        float* const out_tile = out + (((long long)b * NCH_FOA) * T + t0) * NMEL;
+        float* const out_tile = out + (((long long)b * NCH_OUT) * T + t0) * NMEL;
 #pragma unroll 1
         for (int qq = 0; qq < 3; ++qq) {
             const int code = mel_assign(warp, qq);
@@ -161,8 +182,8 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
             const int f = code >> 2, wt = code & 3;
             if (f >= nf) continue;
             float acc[8];
-            mel_task(reinterpret_cast<const float4*>(s_x1 + v_base(f)), s_melent + s_melhdr[wt] * 32 + lane,
-                     s_melhdr[4 + wt], acc);
+            mel_task<!MIC>(reinterpret_cast<const float4*>(s_x1 + v_base(f)), s_melent + s_melhdr[wt] * 32 + lane,
+                           s_melhdr[4 + wt], acc);
 #pragma unroll
             for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
             // uniform epilogue: lane 0 of a pair owns the 4 log-mel channels, lane 1 the 3 IV channels
@@ -190,7 +211,7 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
                     const float2 k = s_scale[c * NMEL + j];
                     out_tile[(c * T + f) * NMEL + j] = fmaf(v[i], k.x, k.y);
                 }
-            } else {
+            } else if (!MIC || part == 0) {
                 const int c0i = part * 4;
                 float* o = out_tile + (c0i * T + f) * NMEL + j;
                 const float2* sc = s_scale + c0i * NMEL + j;
@@ -214,11 +235,11 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
 // from the front-end kernel), pass 2 rewrites only the values below the threshold.
 __global__ void __launch_bounds__(256)
 clamp_topdb_kernel(float* __restrict__ out, const float* __restrict__ mean, const float* __restrict__ istd,
-                   int T, float top_db) {
+                   int T, float top_db, int nch) {
     __shared__ float s_max[8];
     const int b = blockIdx.x >> 2, c = blockIdx.x & 3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4* base = reinterpret_cast<float4*>(out + ((long long)b * NCH_FOA + c) * T * NMEL);
+    float4* base = reinterpret_cast<float4*>(out + ((long long)b * nch + c) * T * NMEL);
     const int n4 = T * (NMEL / 4);
     const int j4 = threadIdx.x & 15;                      // this thread always sees mel bins 4*j4..4*j4+3
     float mu[4], is[4], sd[4];
@@ -267,25 +288,25 @@ int launch_features_foa_clamp(float* out, int B, long long N, const float* mean,
     (void)ws;
     const long long T = N / HOP;
     if (B <= 0 || T <= 0) return set_error(ADY_ERR_INVALID, "features_foa_clamp: empty input");
-    clamp_topdb_kernel<<<B * 4, 256, 0, stream>>>(out, mean, istd, (int)T, top_db);
+    clamp_topdb_kernel<<<B * 4, 256, 0, stream>>>(out, mean, istd, (int)T, top_db, NCH_FOA);
     ADY_LAUNCH_CHECK("clamp_topdb_kernel");
     return ADY_OK;
 }
 
-template <bool ROT, bool VIEW>
+template <bool ROT, bool VIEW, bool MIC>
 static int launch_frontend_inst(int grid, cudaStream_t stream, const int16_t* audio, long long N, int T, int tpc, int ntiles,
                                 const FrontendTables* tab, const float* mean, const float* istd, float dc0, float dc1,
-                                const int8_t* rot, const long long* clip_off, float* out, int* flags) {
+                                const int8_t* rot, const long long* clip_off, float* out, float2* spec, int* flags) {
     static int configured_dev = -1;
     int dev = 0;
     ADY_CUDA_CHECK(cudaGetDevice(&dev));
     if (configured_dev != dev) {
-        ADY_CUDA_CHECK(cudaFuncSetAttribute(frontend_foa_kernel<ROT, VIEW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        ADY_CUDA_CHECK(cudaFuncSetAttribute(frontend_foa_kernel<ROT, VIEW, MIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             SmemLayout::total));
         configured_dev = dev;
     }
-    frontend_foa_kernel<ROT, VIEW><<<grid, NTHREADS, SmemLayout::total, stream>>>(
-        audio, N, T, tpc, ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, flags);
+    frontend_foa_kernel<ROT, VIEW, MIC><<<grid, NTHREADS, SmemLayout::total, stream>>>(
+        audio, N, T, tpc, ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, spec, flags);
     ADY_LAUNCH_CHECK("frontend_foa_kernel");
     return ADY_OK;
 }
@@ -312,16 +333,46 @@ int launch_features_foa(const int16_t* audio, int B, long long N, const float* m
     // window scale: 2^-15 (int16 -> [-1,1)) * 1/2 (channel split), DC terms scaled by the same 1/2
     const float dc0 = dc_offset * 300.0f, dc1 = -dc_offset * 150.0f;
     if (rot && clip_off)
-        rc = launch_frontend_inst<true, true>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, flags);
+        rc = launch_frontend_inst<true, true, false>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, nullptr, flags);
     else if (rot)
-        rc = launch_frontend_inst<true, false>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, flags);
+        rc = launch_frontend_inst<true, false, false>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, nullptr, flags);
     else if (clip_off)
-        rc = launch_frontend_inst<false, true>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, flags);
+        rc = launch_frontend_inst<false, true, false>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, nullptr, flags);
     else
-        rc = launch_frontend_inst<false, false>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, flags);
+        rc = launch_frontend_inst<false, false, false>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, nullptr, flags);
     if (rc) return rc;
     if (apply_topdb) return launch_features_foa_clamp(out, B, N, mean, istd, top_db, ws, stream);
     return ADY_OK;
 }
+
+// MIC format, first half: 4 log-mel channels of a (B, 10, T, 64) tensor + the channel spectra
+// (B, T, 601, 4) complex64 for launch_gcc_from_stft.
+int launch_features_mic_logmel(const int16_t* audio, int B, long long N, const float* mean, const float* istd,
+                               float dc_offset, float top_db, int apply_topdb, float* out, float2* spec, void* ws,
+                               cudaStream_t stream) {
+    const long long T = N / HOP;
+    if (B <= 0 || T <= 0 || N <= HOP) return set_error(ADY_ERR_INVALID, "features_mic: need N > %d samples", HOP);
+    const FrontendTables* tab = nullptr;
+    int rc = get_frontend_tables(&tab);
+    if (rc) return rc;
+    const long long tpc = (T + TF - 1) / TF;
+    const long long ntiles = (long long)B * tpc;
+    if (ntiles > 0x7fffffffLL) return set_error(ADY_ERR_INVALID, "features_mic: too many tiles");
+    int* flags = reinterpret_cast<int*>(ws);
+    ADY_CUDA_CHECK(cudaMemsetAsync(ws, 0, 16, stream));
+    int dev = 0, sms = 0;
+    ADY_CUDA_CHECK(cudaGetDevice(&dev));
+    ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = (int)(ntiles < 2LL * sms ? ntiles : 2LL * sms);
+    rc = launch_frontend_inst<false, false, true>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd,
+                                                  dc_offset * 300.0f, -dc_offset * 150.0f, nullptr, nullptr, out, spec, flags);
+    if (rc) return rc;
+    if (apply_topdb) {
+        clamp_topdb_kernel<<<B * 4, 256, 0, stream>>>(out, mean, istd, (int)T, top_db, 10);
+        ADY_LAUNCH_CHECK("clamp_topdb_kernel");
+    }
+    return ADY_OK;
+}
+
 
 }  // namespace ady

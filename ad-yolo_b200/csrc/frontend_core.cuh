@@ -225,6 +225,7 @@ ADY_HD void slot_store(float2* __restrict__ vbase, int k2, float P0, float P1, f
 // ---------------------------------------------------------------- mel phase
 // warp-task wt (16 filters x 2 parts = 32 lanes): lane walks its column of the static schedule
 // ent[it0 + it][lane]; every lane of the warp runs nit iterations (zero-weight padding).
+template <bool WITH_B = true>
 ADY_HD void mel_task(const float4* __restrict__ vframe4, const MelEntry* __restrict__ ent_col, int nit,
                      float (&acc)[8]) {
 #pragma unroll
@@ -232,9 +233,12 @@ ADY_HD void mel_task(const float4* __restrict__ vframe4, const MelEntry* __restr
 #pragma unroll 2
     for (int it = 0; it < nit; ++it) {
         const MelEntry e = ent_col[it * 32];
-        const float4 a = vframe4[e.pos], b = vframe4[NPOS + e.pos];
+        const float4 a = vframe4[e.pos];
         acc[0] += e.w * a.x; acc[1] += e.w * a.y; acc[2] += e.w * a.z; acc[3] += e.w * a.w;
-        acc[4] += e.w * b.x; acc[5] += e.w * b.y; acc[6] += e.w * b.z; acc[7] += e.w * b.w;
+        if (WITH_B) {
+            const float4 b = vframe4[NPOS + e.pos];
+            acc[4] += e.w * b.x; acc[5] += e.w * b.y; acc[6] += e.w * b.z; acc[7] += e.w * b.w;
+        }
     }
 }
 

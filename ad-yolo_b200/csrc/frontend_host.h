@@ -28,6 +28,9 @@ int launch_features_foa(const int16_t* audio, int B, long long N, const float* m
                         float dc_offset, float top_db, int apply_topdb, const int8_t* rot, const long long* clip_off,
                         float* out, void* ws, cudaStream_t stream);
 
+int launch_features_mic_logmel(const int16_t* audio, int B, long long N, const float* mean, const float* istd,
+                               float dc_offset, float top_db, int apply_topdb, float* out, float2* spec, void* ws,
+                               cudaStream_t stream);
 int launch_features_foa_clamp(float* out, int B, long long N, const float* mean, const float* istd, float top_db,
                               void* ws, cudaStream_t stream);
 

@@ -89,6 +89,14 @@ int adyolo_features_foa_views(const int16_t* audio, const int64_t* clip_offsets,
 int adyolo_features_foa_clamp(float* out, int B, int64_t N, const adyolo_frontend_cfg* cfg, const float* mean,
                               const float* inv_std, void* workspace, void* stream);
 
+/* MIC (microphone array) format, first half: the fused front end writes the 4 log-mel channels
+ * into channels 0..3 of out (B, 10, T, 64) (mean / inv_std: device (>=4, 64) or NULL) and the four
+ * channel spectra into spec_c64 (B, T, 601, 4) complex64; adyolo_gcc_from_stft then fills
+ * channels 4..9.  The reference has no MIC path: parity unpinned.                  */
+int adyolo_features_mic_logmel(const int16_t* audio, int B, int64_t N, const adyolo_frontend_cfg* cfg, const float* mean,
+                               const float* inv_std, float* out, void* spec_c64, void* workspace, int apply_topdb,
+                               void* stream);
+
 /* Un-fused stages behind the reference's per-function surface (they materialise the STFT):
  *
  * adyolo_stft  — utility.audio2stft (utility.py:142-165) == get_stft_spectrogram (datasets.py:252-258)
