@@ -11,7 +11,7 @@ ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libadyolo_b200.so")
-SOURCES = ["frontend.cu", "frontend_aux.cu", "assign.cu", "labels.cu", "tables.cu", "scaler.cu", "api.cu"]
+SOURCES = ["frontend.cu", "frontend_aux.cu", "assign.cu", "labels.cu", "nms.cu", "tables.cu", "scaler.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC"]
 
@@ -93,6 +93,7 @@ _SIGS = {
     "adyolo_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.POINTER(GridCfg)]),
     "adyolo_loss": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.POINTER(GridCfg), _P, _P, _P, _P, _P, _P, _P]),
     "adyolo_loss_devcount": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, C.c_int, C.POINTER(GridCfg), _P, _P, _P, _P]),
+    "adyolo_yolo_post": (C.c_int, [_P, C.c_int64, C.POINTER(GridCfg), C.c_float, C.c_float, C.c_float, C.c_int, _P, _P, _P, _P]),
     "adyolo_loss_backward": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(GridCfg), _P, _P, _P, _P]),
 }
 

@@ -244,4 +244,15 @@ int adyolo_loss_backward(const float* logit, int B, int T, const adyolo_grid_cfg
     return launch_loss_backward(logit, B, T, a, workspace, grad_output, grad_out, (cudaStream_t)stream);
 }
 
+int adyolo_yolo_post(const float* logit, int64_t n_frames, const adyolo_grid_cfg* cfg, float conf_thresh,
+                     float clss_thresh, float unify_thresh, int max_det, float* det, int32_t* count, int32_t* overflow,
+                     void* stream) {
+    AssignCfg a;
+    int rc = make_cfgs(cfg, &a, nullptr);
+    if (rc) return rc;
+    if (!logit || !det || !count || !overflow) return set_error(ADY_ERR_INVALID, "yolo_post: NULL pointer");
+    return launch_yolo_post(logit, (long long)n_frames, a, conf_thresh, clss_thresh, unify_thresh, max_det, det, count,
+                            overflow, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -45,6 +45,10 @@ int launch_loss(const float* logit, const float* target, long long M, const long
 int launch_loss_backward(const float* logit, int B, int T, const AssignCfg& cfg, const void* ws,
                          const float* grad_output, float* grad_out, cudaStream_t stream);
 
+// decode + conn-merge NMS (datasets.py:741-857)
+int launch_yolo_post(const float* logit, long long n_frames, const AssignCfg& cfg, float conf_thresh, float clss_thresh,
+                     float unify_thresh, int max_det, float* det, int32_t* count, int* overflow, cudaStream_t stream);
+
 // grid-cell responsibility (datasets.py:457-482): events -> 32-bit cell mask + count, rows
 struct CellCfg {
     int ga, ge;

@@ -183,6 +183,15 @@ int adyolo_loss_backward(const float* logit, int B, int T, const adyolo_grid_cfg
                          const float* grad_output /* device float32[1] or NULL (= 1) */, float* grad_out,
                          void* stream);
 
+/* LabelPostProcessor.get_yolo_output (datasets.py:741-857, nms == 'conn-merge') for n_frames
+ * frames of logits (n_frames, Ga*Ge*A*(C+3)): decode, class-confidence thresholding, per-class
+ * connectivity merge under the great-circle distance, softmax-weighted Cartesian vote.
+ *   det   device float32 (n_frames, max_det, 4) rows [class, x, y, z] in the reference's order
+ *   count device int32 (n_frames); overflow device int32[1] set when a frame had > max_det rows */
+int adyolo_yolo_post(const float* logit, int64_t n_frames, const adyolo_grid_cfg* cfg, float conf_thresh,
+                     float clss_thresh, float unify_thresh, int max_det, float* det, int32_t* count, int32_t* overflow,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -247,6 +247,20 @@ def main():
         epochs.append([names.index(x) for x in stub.filelist])
     ck["sampler_epochs"] = np.asarray(epochs, np.int64)
     np.savez_compressed(os.path.join(GOLD, "chunking.npz"), **ck)
+    # ---- decode + conn-merge NMS (reference LabelPostProcessor on CPU)
+    pn = ref_shims.ref_params(12)
+    pn["train_config"].update({"conf_thresh": 0.5, "clss_thresh": 0.5, "unify_thresh": 15., "nms": "conn-merge"})
+    post = ref_datasets.LabelPostProcessor(pn)
+    gn = torch.Generator().manual_seed(3)
+    Tn = 24
+    lg = torch.randn(1, Tn, 2400, generator=gn) * 1.5 - 1.0
+    yv = lg.reshape(1, Tn, 8, 4, 5, 15)
+    yv[0, :, 2, 1, :, 0] += 5; yv[0, :, 2, 1, :, 3] += 5                       # a cluster of class 2 in cell (2,1)
+    yv[0, ::2, 3, 1, :2, 0] += 5; yv[0, ::2, 3, 1, :2, 3] += 5                # neighbours in the next cell
+    yv[0, :, 6, 2, 0, 0] += 5; yv[0, :, 6, 2, 0, 8] += 5                       # an isolated class-7 detection
+    dn = post.postprocess(lg.clone())                                          # datasets.py:741-857
+    rows = [[fr] + d for fr, dets in dn.items() for d in dets]
+    np.savez_compressed(os.path.join(GOLD, "nms_ref.npz"), logit=lg.numpy(), rows=np.asarray(rows, np.float64))
     print("golden fixtures written to", GOLD)
     for fn in sorted(os.listdir(GOLD)):
         print(" ", fn, os.path.getsize(os.path.join(GOLD, fn)))

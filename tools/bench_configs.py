@@ -49,7 +49,7 @@ out.append({"config": "config[0] one 60-s FOA clip, raw log-mel+IV (preprocess.p
 Bm = 512 // world
 am = audio(Bm, 120_000)
 ms = timed(lambda: features_mic_batched(am), 3, 1)
-out.append({"config": "config[2] MIC log-mel + GCC-PHAT (10ch), 512 x 5-s chunks (un-fused STFT->logmel/GCC route)", "ms": ms,
+out.append({"config": "config[2] MIC log-mel + GCC-PHAT (10ch), 512 x 5-s chunks (fused log-mel+spectra kernel -> GCC-PHAT kernel)", "ms": ms,
             "audio_hours_per_s": world * Bm * 5 / 3600 / (ms / 1e3), "n_gpus": world})
 # config[3]: scaler action, resident pool of 60-s clips streamed in batches + all-reduce at the end
 pool = audio(8, 1_440_000)
