@@ -14,14 +14,17 @@ from .labels import GridSpec
 
 
 def yolo_post_batched(logit: torch.Tensor, grid: GridSpec, conf_thresh: float, clss_thresh: float, unify_thresh: float,
-                      max_det: int = 256):
+                      max_det: int | None = None):
     """logit (B, T, Ga*Ge*A*(C+3)) float32 CUDA -> det (B, T, max_det, 4) float32 [class, x, y, z],
-    count (B, T) int32.  Raises if any frame produced more than ``max_det`` detections."""
+    count (B, T) int32.  ``max_det`` defaults to the exact upper bound (anchors x classes per frame);
+    with a smaller cap the call raises if any frame produced more detections."""
     require_cuda(logit, "yolo_post_batched")
     if logit.dim() != 3 or logit.shape[-1] != grid.nb_predicts * grid.nb_channels:
         raise ValueError(f"logit must be (B, T, {grid.nb_predicts * grid.nb_channels})")
     logit = logit.detach().contiguous().float()
     B, T, _ = logit.shape
+    if max_det is None:
+        max_det = grid.nb_predicts * grid.nb_classes
     with torch.cuda.device(logit.device):
         det = torch.zeros((B, T, max_det, 4), dtype=torch.float32, device=logit.device)
         count = torch.zeros((B, T), dtype=torch.int32, device=logit.device)
@@ -62,7 +65,7 @@ class LabelPostProcessor:
         self.conf_thresh = thresh
         self.clss_thresh = thresh
 
-    def get_yolo_output(self, batch_yolo_output: torch.Tensor, max_det: int = 256):
+    def get_yolo_output(self, batch_yolo_output: torch.Tensor, max_det: int | None = None):
         """datasets.py:741-857: (1, T, 160*(C+3)) logits -> {frame_idx: [[class_idx, X, Y, Z], ...]}."""
         if batch_yolo_output.dim() != 3 or batch_yolo_output.shape[0] != 1:
             raise ValueError("get_yolo_output expects (1, T, n) logits (the reference evaluates with batch 1)")

@@ -47,13 +47,13 @@ def test_postprocess_vs_reference_golden(A, gold):
 @pytest.mark.parametrize("C,scale", [(12, 1.5), (13, 2.5), (14, 0.7)])
 def test_postprocess_vs_torch_oracle_on_gpu(A, C, scale):
     gen = torch.Generator(device="cuda").manual_seed(C)
-    T = 60
+    T = 12
     logit = torch.randn((2, T, 160 * (C + 3)), device="cuda", generator=gen) * scale
     y = logit.view(2, T, 8, 4, 5, C + 3)
     y[:, :, 1, 2, :, 0] += 4; y[:, :, 1, 2, :, 4] += 4; y[:, ::3, 2, 2, :3, 0] += 4; y[:, ::3, 2, 2, :3, 4] += 4
     post = A.LabelPostProcessor(_params(C))
     orc = YoloPostOracle(nb_classes=C, device="cuda")
-    for thr in (0.5, 0.3):
+    for thr in ((0.5, 0.3) if C == 12 else (0.5,)):
         post.set_conf_thresh(thr)
         orc.conf_thresh = orc.clss_thresh = thr
         for b in range(2):

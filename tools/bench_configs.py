@@ -61,6 +61,19 @@ def scaler_pass():
 ms = timed(scaler_pass, 5, 2)
 out.append({"config": "config[3] scaler action: per-(mel,ch) mean/std/max/min, 32 audio-min per rank per pass + all-reduce", "ms": ms,
             "audio_hours_per_s": world * 32 / 60 / (ms / 1e3), "n_gpus": world})
+# N1: decode + conn-merge NMS of one 60-s validation clip (600 label frames), sparse detections
+if rank == 0:
+    import time as _t
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle.nms_torch import YoloPostOracle
+    grid = A.labels.GridSpec(12, 5, [45, 45], 0.5)
+    lg = torch.randn((1, 600, 2400), device=dev, generator=g) - 3.0
+    yv = lg.view(1, 600, 8, 4, 5, 15)
+    yv[0, :, 2, 1, :3, 0] += 7; yv[0, :, 2, 1, :3, 3] += 7; yv[0, ::2, 5, 2, :2, 0] += 7; yv[0, ::2, 5, 2, :2, 9] += 7
+    ms = timed(lambda: A.yolo_post_batched(lg, grid, 0.5, 0.5, 15.0), 10, 3) if world == 1 else None
+    t0 = _t.perf_counter(); ref = YoloPostOracle(device="cpu").clip_output(lg[0].cpu()); cpu_ms = (_t.perf_counter() - t0) * 1e3
+    out.append({"config": "N1 decode + conn-merge NMS, one 60-s clip (600 frames)", "ms": ms, "reference_cpu_ms": cpu_ms,
+                "detections": sum(len(v) for v in ref.values()), "n_gpus": 1})
 if rank == 0:
     for o in out:
         print(json.dumps(o))
