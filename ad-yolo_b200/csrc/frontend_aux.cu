@@ -1,12 +1,10 @@
-// Un-fused front-end stages behind the reference's per-function call surface, plus the MIC
-// (GCC-PHAT) path.  These materialise the STFT in HBM, so they are the compatibility / offline
+// Un-fused front-end stages behind the reference's per-function call surface (the MIC GCC-PHAT
+// lag transform lives in gcc_tc.cu).  These materialise the STFT in HBM, so they are the compatibility / offline
 // route; the training hot path is the fused kernel in frontend.cu.
 //
 //   stft_kernel            utility.py:142-165 audio2stft  == datasets.py:252-258 get_stft_spectrogram
 //   logmel_from_stft       utility.py:168-191 stft2melscale == datasets.py:260-267
 //   iv_from_stft           utility.py:194-215 stft2iv       == datasets.py:269-279
-//   gcc_from_stft          NOT in the reference; upstream seld-dcase2022 _get_gcc semantics:
-//                          cc = irfft(exp(1j*angle(conj(X_m) X_n))), lags [-L/2, L/2)
 //   clamp_strided          librosa.power_to_db top_db clamp with the global max per (clip, channel)
 #include "common.cuh"
 #include "frontend_core.cuh"
@@ -150,97 +148,6 @@ iv_from_stft_kernel(const float2* __restrict__ spec, int T, const FrontendTables
     out[b * os.sb + c * os.sc + t * os.st + j * os.sj] = (acc - mu) * is;
 }
 
-// GCC-PHAT, 64 lags x 6 microphone pairs per frame.  One block (4 warps) per (clip, frame):
-//   1. PHAT-normalised cross spectra of the 6 pairs -> smem, laid out [bin][pair] so that one
-//      bin's six values are three 16-byte loads that every lane of a warp shares (broadcast)
-//   2. lane = lag magnitude l (0..31), warp = quarter of the bins.  cc[+l] and cc[-l] share
-//        C = sum_k Re(P_k) cos(2 pi k l / N),  S = sum_k Im(P_k) sin(2 pi k l / N):
-//        cc[+l] = (e + 2 (C - S)) / N,  cc[-l] = (e + 2 (C + S)) / N
-//      (cos, sin) advance by a per-lane rotation each bin (restarted exactly every quarter);
-//      lag magnitude 32 (only cc[-32] is needed) is summed with lane = bin residue
-//   3. partial sums of the 4 warps are combined through smem; standardise; store
-__global__ void __launch_bounds__(128)
-gcc_from_stft_kernel(const float2* __restrict__ spec, int T, const float* __restrict__ mean,
-                     const float* __restrict__ istd, float* __restrict__ out, OutStrides os) {
-    __shared__ __align__(16) float2 P[NBIN][6];           // 28.8 KB
-    __shared__ float red[4][13][32];                       // per warp: C[6], S[6] per lane (+ row 12: lag-32 partials)
-    const long long bt = blockIdx.x;
-    const long long b = bt / T;
-    const int t = (int)(bt - b * T);
-    const float2* s = spec + bt * NBIN * 4;
-    for (int k = threadIdx.x; k < NBIN; k += 128) {
-        const float4 v01 = *reinterpret_cast<const float4*>(s + k * 4), v23 = *reinterpret_cast<const float4*>(s + k * 4 + 2);
-        const float2 x[4] = {make_float2(v01.x, v01.y), make_float2(v01.z, v01.w), make_float2(v23.x, v23.y), make_float2(v23.z, v23.w)};
-        int p = 0;
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-#pragma unroll
-            for (int n = m + 1; n < 4; ++n) {
-                float re = x[m].x * x[n].x + x[m].y * x[n].y, im = x[m].x * x[n].y - x[m].y * x[n].x;   // conj(x_m) x_n
-                const float mx = fmaxf(fabsf(re), fabsf(im));
-                if (mx == 0.f) { re = 1.f; im = 0.f; }                                                // np.angle(0) = 0
-                else {
-                    re /= mx; im /= mx;
-                    const float r = rsqrtf(re * re + im * im);
-                    re *= r; im *= r;
-                }
-                P[k][p++] = make_float2(re, im);
-            }
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int k0 = 1 + warp * 150, k1 = min(600, k0 + 150);       // bins 1..599 in four quarters
-    float C[6] = {0, 0, 0, 0, 0, 0}, S[6] = {0, 0, 0, 0, 0, 0};
-    float cs, sn, rc, rs;
-    sincospif((float)((k0 * lane) % NFFT) * (1.0f / 600.0f), &sn, &cs);   // angle of bin k0 for lag `lane`
-    sincospif((float)lane * (1.0f / 600.0f), &rs, &rc);                   // per-bin rotation
-#pragma unroll 2
-    for (int k = k0; k < k1; ++k) {
-        const float4 a = *reinterpret_cast<const float4*>(&P[k][0]), c = *reinterpret_cast<const float4*>(&P[k][2]),
-                     e = *reinterpret_cast<const float4*>(&P[k][4]);
-        C[0] += a.x * cs; S[0] += a.y * sn; C[1] += a.z * cs; S[1] += a.w * sn;
-        C[2] += c.x * cs; S[2] += c.y * sn; C[3] += c.z * cs; S[3] += c.w * sn;
-        C[4] += e.x * cs; S[4] += e.y * sn; C[5] += e.z * cs; S[5] += e.w * sn;
-        const float nc = cs * rc - sn * rs;
-        sn = sn * rc + cs * rs;
-        cs = nc;
-    }
-    // lag magnitude 32: lane takes the bins k0 + lane, k0 + lane + 32, ... of this quarter
-    float L32[6] = {0, 0, 0, 0, 0, 0};
-    for (int k = k0 + lane; k < k1; k += 32) {
-        float s32, c32;
-        sincospif((float)((k * 32) % NFFT) * (1.0f / 600.0f), &s32, &c32);
-#pragma unroll
-        for (int p = 0; p < 6; ++p) L32[p] += P[k][p].x * c32 + P[k][p].y * s32;     // cc[-32]: cos + sin
-    }
-#pragma unroll
-    for (int p = 0; p < 6; ++p) {
-#pragma unroll
-        for (int o = 16; o; o >>= 1) L32[p] += __shfl_xor_sync(0xffffffffu, L32[p], o);
-        red[warp][p][lane] = C[p];
-        red[warp][6 + p][lane] = S[p];
-    }
-    if (lane < 6) red[warp][12][lane] = L32[lane];
-    __syncthreads();
-    // 6 pairs x 64 outputs = 384 values over 128 threads
-    for (int o = threadIdx.x; o < 6 * NMEL; o += 128) {
-        const int p = o >> 6, j = o & 63;
-        const int lag = j - 32;                                   // output order: cc[-32:], cc[:32]
-        const int l = lag < 0 ? -lag : lag;
-        const float edge = P[0][p].x + ((l & 1) ? -P[600][p].x : P[600][p].x);
-        float v;
-        if (l == 32) v = red[0][12][p] + red[1][12][p] + red[2][12][p] + red[3][12][p];
-        else {
-            const float c = red[0][p][l] + red[1][p][l] + red[2][p][l] + red[3][p][l];
-            const float sgm = red[0][6 + p][l] + red[1][6 + p][l] + red[2][6 + p][l] + red[3][6 + p][l];
-            v = lag < 0 ? c + sgm : c - sgm;
-        }
-        const float cc = (2.f * v + edge) * (1.0f / NFFT);
-        const float mu = mean ? mean[p * NMEL + j] : 0.f, is = istd ? istd[p * NMEL + j] : 1.f;
-        out[b * os.sb + p * os.sc + t * os.st + j * os.sj] = (cc - mu) * is;
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 int launch_stft(const void* audio, int dtype, int B, long long N, float dc, float2* out, cudaStream_t stream) {
     const long long T = N / HOP;
@@ -284,13 +191,6 @@ int launch_iv_from_stft(const float2* spec, int B, long long T, const float* mea
     if (rc) return rc;
     iv_from_stft_kernel<<<(unsigned)(B * T), 256, 0, stream>>>(spec, (int)T, tab, mean, istd, out, os, flags);
     ADY_LAUNCH_CHECK("iv_from_stft_kernel");
-    return ADY_OK;
-}
-
-int launch_gcc_from_stft(const float2* spec, int B, long long T, const float* mean, const float* istd, float* out,
-                         OutStrides os, cudaStream_t stream) {
-    gcc_from_stft_kernel<<<(unsigned)(B * T), 128, 0, stream>>>(spec, (int)T, mean, istd, out, os);
-    ADY_LAUNCH_CHECK("gcc_from_stft_kernel");
     return ADY_OK;
 }
 
