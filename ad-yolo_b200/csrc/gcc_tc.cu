@@ -8,21 +8,24 @@
 // B[2k][l] = c_k cos(2 pi k l/N), B[2k+1][l] = -c_k sin(2 pi k l/N)  (c_0 = c_600 = 1/2, else 1;
 // the common factor 2/N is applied in FP32 in the epilogue so that lag 0 is exact in TF32).
 //
-// One CTA = 64 frames = 384 items = 3 UMMA M-tiles of 128 rows, N = 64 lags, K = 1216 (608 bins).
-// Per chunk of 16 bins (K = 32):
-//   - all threads load the 4 channel spectra of (64 frames x 16 bins), form the 6 PHAT-normalised
-//     cross spectra and store them as the A operand in shared memory in the canonical K-major,
-//     no-swizzle UMMA layout (core matrix = 8 rows x 16 bytes); the B chunk (8 KB, precomputed in
-//     that layout) is copied from global memory
+// One CTA = 64 frames = 384 items (row = pair * 64 + frame) = 3 UMMA M-tiles of 128 rows, N = 64
+// lags, K = 1216 (608 bins).  Per chunk of 16 bins (K = 32):
+//   - all threads take the 4 channel spectra of (64 frames x 16 bins) from registers (loaded one
+//     chunk ahead), normalise each channel to unit modulus, form the 6 cross spectra and store them
+//     as the A operand in shared memory in the canonical K-major, no-swizzle UMMA layout (core
+//     matrix = 8 rows x 16 bytes); the B chunk (8 KB, precomputed in that layout) arrives by cp.async
 //   - fence.proxy.async + barrier; one thread issues 4 (k-steps) x 3 (M-tiles) tcgen05.mma and a
 //     tcgen05.commit on the stage's mbarrier.  Two stages: chunk c+1 is generated while the tensor
 //     core consumes chunk c; a stage is only waited for when it is about to be overwritten
-// Epilogue: tcgen05.ld (32x32b) brings each item's 64 lags from TMEM into one thread's registers,
-// which standardises and stores them (256 contiguous bytes per item).
+// Epilogue: all 8 warps tcgen05.ld (32x32b.x32) a 32-item x 32-lag block each, stage it through
+// shared memory and store standardised 128-byte row segments.
 // The MMA truncates FP32 operands to TF32, which biases a coherent peak low by ~6e-4; both operands
-// are therefore rounded to nearest (cvt.rna / host) first: the error of the 1202-term sum scaled by
-// 1/1200 is then ~1e-5 absolute, two orders inside the 1e-3 gate.
+// are therefore rounded to nearest first: measured max error 2.9e-5 absolute against the float64
+// oracle (gate 1e-3); all-(1,0) cross spectra (digital silence) give cc[0] = 1 exactly.
+// B200, 128 x 5-s clips: 0.57 ms (CUDA-core kernel this replaces) -> 0.22-0.24 ms; at 512 clips the
+// kernel streams the 1.97 GB of spectra at 2.7 TB/s (profiles/r01_ncu_gcc_tc.txt).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -65,12 +68,6 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 64, M = 128
 constexpr uint32_t GT_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
-__device__ __forceinline__ float to_tf32_rn(float x) {       // the MMA truncates; round to nearest first
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-
 __device__ __forceinline__ void mbar_wait(uint32_t mb, uint32_t parity) {
     uint32_t done = 0;
     while (!done) {
@@ -78,6 +75,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t mb, uint32_t parity) {
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(mb), "r"(parity) : "memory");
     }
+}
+
+// The MMA reads only the upper 19 bits of an FP32 operand (truncation).  Adding half a TF32 ulp to
+// the bit pattern first turns that into round-to-nearest (ties away), like cvt.rna.tf32.f32 but in
+// one integer add; operands here are bounded by 1, so the carry cannot reach infinity.
+__device__ __forceinline__ float tf32_rn_bits(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 // x / |x| per channel.  The value is brought to [0.5, 1) by an exact power of two before the rsqrt,
@@ -89,7 +97,7 @@ __device__ __forceinline__ float2 unit(float2 a, bool& zero) {
     const int e = (int)(__float_as_uint(mx) >> 23);
     const float sc = __uint_as_float((uint32_t)max(253 - e, 1) << 23);
     const float re = a.x * sc, im = a.y * sc;
-    const float r = rsqrtf(re * re + im * im);
+    const float r = rsqrt_ftz(re * re + im * im);
     return make_float2(re * r, im * r);
 }
 
@@ -160,10 +168,23 @@ gcc_tc_kernel(const float2* __restrict__ spec, long long n_frames, int T, const 
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
             const int combo = it * 8 + warp, f = (combo & 3) * 16 + f_lo, kb = (combo >> 2) * 2 + kb_lo;
-            const bool live = (f0 + f) < n_frames && (ch * GT_BINS + kb) < NBIN;
-            bool z[4];
-            const float2 u[4] = {unit(make_float2(cur.v01[it].x, cur.v01[it].y), z[0]), unit(make_float2(cur.v01[it].z, cur.v01[it].w), z[1]),
-                                 unit(make_float2(cur.v23[it].x, cur.v23[it].y), z[2]), unit(make_float2(cur.v23[it].z, cur.v23[it].w), z[3])};
+            const float2 x[4] = {make_float2(cur.v01[it].x, cur.v01[it].y), make_float2(cur.v01[it].z, cur.v01[it].w),
+                                 make_float2(cur.v23[it].x, cur.v23[it].y), make_float2(cur.v23[it].z, cur.v23[it].w)};
+            // fast path: |x|^2 comfortably inside the FP32 range for all four channels
+            float2 u[4];
+            bool ok = true;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float sq = fmaf(x[c].x, x[c].x, x[c].y * x[c].y);
+                ok = ok && sq > 1e-30f && sq < 1e30f;
+                const float r = rsqrt_ftz(sq);
+                u[c] = make_float2(x[c].x * r, x[c].y * r);
+            }
+            bool z[4] = {false, false, false, false};
+            if (!ok) {   // rare: silence, padding (rows / bins past the end load zeros), extreme magnitudes, NaN
+#pragma unroll
+                for (int c = 0; c < 4; ++c) u[c] = unit(x[c], z[c]);
+            }
             // canonical layout: [k-chunk = kb/2][m-group = row/8] core matrices of 8 rows x 16 B
             unsigned char* dst = sA + ((kb >> 1) * (GT_ITEMS / 8) + (f >> 3)) * 128 + (f & 7) * 16 + (kb & 1) * 8;
             int p = 0;
@@ -172,9 +193,8 @@ gcc_tc_kernel(const float2* __restrict__ spec, long long n_frames, int T, const 
 #pragma unroll
                 for (int n = m + 1; n < 4; ++n) {
                     float re = u[m].x * u[n].x + u[m].y * u[n].y, im = u[m].x * u[n].y - u[m].y * u[n].x;   // conj(u_m) u_n
-                    if (z[m] || z[n]) { re = 1.f; im = 0.f; }
-                    if (!live) { re = 0.f; im = 0.f; }
-                    *reinterpret_cast<float2*>(dst + p * (GT_FRAMES / 8) * 128) = make_float2(to_tf32_rn(re), to_tf32_rn(im));   // row = p * 64 + f
+                    if (!ok && (z[m] || z[n])) { re = 1.f; im = 0.f; }
+                    *reinterpret_cast<float2*>(dst + p * (GT_FRAMES / 8) * 128) = make_float2(tf32_rn_bits(re), tf32_rn_bits(im));   // row = p * 64 + f
                     ++p;
                 }
         }
@@ -205,54 +225,57 @@ gcc_tc_kernel(const float2* __restrict__ spec, long long n_frames, int T, const 
     mbar_wait(smem_u32(&mbar[(GT_CHUNKS - 1) & (GT_STAGES - 1)]), (uint32_t)(((GT_CHUNKS - 1) / GT_STAGES) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;");
 
-    // ---- epilogue: warps 0..3 own TMEM lanes 32w..32w+31; row = pair * 64 + frame
-    if (warp < 4) {
+    // ---- epilogue.  A warp may read TMEM lanes 32 (w % 4) .. +31: warps w and w + 4 share a lane
+    // quarter and split the 64 lag columns.  TMEM lane = row of the M-tile = pair (mt*2 + q/2), frame
+    // (q & 1) * 32 + lane.  Natural output layout: the 32 x 32 block goes through shared memory so
+    // that global stores are 128-byte row segments; any other stride set is stored directly.
+    {
         constexpr float kScale = 2.0f / NFFT;               // B holds cos / -sin (x 1/2 at bins 0 and 600): exact at lag 0
+        const int q = warp & 3, h = warp >> 2;
         const bool vec = os.sj == 1 && ((os.sb | os.sc | os.st) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+        float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);      // 32 rows, 144-byte pitch: conflict-free
+        long long off[8];                                                     // vec: this lane's 8 (row, 16-byte column) targets
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int f = (q & 1) * 32 + (vec ? 4 * it + (lane >> 3) : lane);
+            const long long fr = f0 + f;
+            const long long b = fr / T;
+            off[it] = fr < n_frames ? b * os.sb + (fr - b * T) * os.st + (vec ? h * 32 + (lane & 7) * 4 : 0) : -1;
+        }
 #pragma unroll 1
         for (int mt = 0; mt < 3; ++mt) {
-            uint32_t r[64];
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + mt * 64;
+            uint32_t r[32];
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + mt * 64 + h * 32;
             asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-                "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-                "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
-                  "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
-                  "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
-                  "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
-                  "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int item = mt * 128 + warp * 32 + lane;
-            const int p = item >> 6, f = item & 63;
-            const long long fr = f0 + f;
-            if (fr < n_frames) {
-                const long long b = fr / T;
-                const int t = (int)(fr - b * T);
-                float* o = out + b * os.sb + p * os.sc + t * os.st;
-                const float* mu = mean ? mean + p * NMEL : nullptr;
-                const float* is = istd ? istd + p * NMEL : nullptr;
-                if (vec) {
+            const int p = mt * 2 + (q >> 1);
+            const float* mu = mean ? mean + p * NMEL + h * 32 : nullptr;
+            const float* is = istd ? istd + p * NMEL + h * 32 : nullptr;
+            if (vec) {
 #pragma unroll
-                    for (int j = 0; j < 64; j += 4) {
-                        float4 v;
-                        v.x = (__uint_as_float(r[j]) * kScale - (mu ? mu[j] : 0.f)) * (is ? is[j] : 1.f);
-                        v.y = (__uint_as_float(r[j + 1]) * kScale - (mu ? mu[j + 1] : 0.f)) * (is ? is[j + 1] : 1.f);
-                        v.z = (__uint_as_float(r[j + 2]) * kScale - (mu ? mu[j + 2] : 0.f)) * (is ? is[j + 2] : 1.f);
-                        v.w = (__uint_as_float(r[j + 3]) * kScale - (mu ? mu[j + 3] : 0.f)) * (is ? is[j + 3] : 1.f);
-                        *reinterpret_cast<float4*>(o + j) = v;
-                    }
-                } else {
+                for (int j4 = 0; j4 < 8; ++j4)
+                    *reinterpret_cast<float4*>(stage + lane * 36 + j4 * 4) =
+                        make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]), __uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3]));
+                __syncwarp();
+                const int c4 = (lane & 7) * 4;
+                const float4 m4 = mu ? *reinterpret_cast<const float4*>(mu + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 i4 = is ? *reinterpret_cast<const float4*>(is + c4) : make_float4(1.f, 1.f, 1.f, 1.f);
 #pragma unroll
-                    for (int j = 0; j < 64; ++j)
-                        o[j * os.sj] = (__uint_as_float(r[j]) * kScale - (mu ? mu[j] : 0.f)) * (is ? is[j] : 1.f);
+                for (int it = 0; it < 8; ++it) {
+                    float4 v = *reinterpret_cast<const float4*>(stage + (4 * it + (lane >> 3)) * 36 + c4);
+                    v.x = (v.x * kScale - m4.x) * i4.x; v.y = (v.y * kScale - m4.y) * i4.y;
+                    v.z = (v.z * kScale - m4.z) * i4.z; v.w = (v.w * kScale - m4.w) * i4.w;
+                    if (off[it] >= 0) *reinterpret_cast<float4*>(out + off[it] + p * os.sc) = v;
                 }
+                __syncwarp();
+            } else if (off[0] >= 0) {
+                float* o = out + off[0] + p * os.sc + (long long)(h * 32) * os.sj;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    o[j * os.sj] = (__uint_as_float(r[j]) * kScale - (mu ? mu[j] : 0.f)) * (is ? is[j] : 1.f);
             }
         }
     }

@@ -162,7 +162,10 @@ def gcc_phat(linear_spectra, n_fft, nb_lags):
     for m in range(C):
         for n in range(m + 1, C):
             R = np.conj(linear_spectra[:, :, m]) * linear_spectra[:, :, n]
-            cc = np.fft.irfft(np.exp(1.0j * np.angle(R)), n=n_fft, axis=1)
+            # upstream's np.angle(R) of an exactly vanishing R is 0 or pi depending on the SIGN of the
+            # zero (conj(0) * x can be -0.0): an accident, pinned here to phase 0 (what the kernel does)
+            ph = np.where(R == 0, 1.0 + 0.0j, np.exp(1.0j * np.angle(R)))
+            cc = np.fft.irfft(ph, n=n_fft, axis=1)
             out.append(np.concatenate((cc[:, -nb_lags // 2:], cc[:, :nb_lags // 2]), axis=-1))
     return np.stack(out, axis=-1)
 

@@ -177,6 +177,47 @@ def test_mic_gcc_path_selfconsistent(A):
         assert (out[b, 4, 5:35].argmax(-1) == 32 + 7).all()
 
 
+def test_gcc_tensor_core_kernel_against_oracle(A):
+    """adyolo_gcc_from_stft (tcgen05 TF32 lag transform) straight through the C ABI on synthetic
+    spectra: random phases, a dead microphone, digital silence, magnitudes far outside the range
+    where |x|^2 fits FP32, a frame count that leaves the last 64-frame tile ragged, and a
+    channels-last output (generic-stride epilogue).  Gate 1e-3 absolute (north_star); observed 3e-5."""
+    import ctypes as C
+    from adyolo_b200 import _lib
+    from adyolo_b200.features import _cfg, ptr, stream_ptr
+    rng = np.random.default_rng(21)
+    B, T = 2, 83                                             # 166 frames = 2 full tiles + 38
+    spec = (rng.standard_normal((B, T, 601, 4)) + 1j * rng.standard_normal((B, T, 601, 4))).astype(np.complex64)
+    spec[0, 3:6, :, 2] = 0                                   # dead microphone: its pairs -> delta at lag 0
+    spec[0, 10:12] = 0                                       # silence
+    spec[1, 5] *= 1e-25                                      # |x|^2 underflows FP32
+    spec[1, 6] *= 1e+24                                      # |x|^2 overflows FP32
+    spec[1, 7, 100:200] = 0
+    ref = np.stack([F.gcc_phat(spec[b].astype(np.complex128), 1200, 64) for b in range(B)])   # (B, T, 64, 6)
+    L, cfg = _lib.lib(), _cfg()
+    d_spec = torch.from_numpy(spec).cuda()
+    out = torch.empty(B, 6, T, 64, device="cuda")
+    st = (C.c_int64 * 4)(6 * T * 64, T * 64, 64, 1)
+    assert L.adyolo_gcc_from_stft(ptr(d_spec), B, T, C.byref(cfg), None, None, ptr(out), st, stream_ptr()) == 0
+    got = out.permute(0, 2, 3, 1).cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got - ref).max() < 1e-3
+    assert np.abs(got - ref).max() < 1e-4                    # tighter than the gate: TF32 operands are rounded, not truncated
+    assert (got[0, 10:12, 32, :] == 1.0).all()               # silence: cc[0] exactly 1
+    assert np.abs(got[0, 10:12, 33:, :]).max() < 5e-5        # TF32-rounded twiddles: sum_k cos(2 pi k l / N) cancels to ~1e-5
+    # channels-last output with standardisation: generic-stride path == natural path
+    mean = torch.from_numpy(rng.standard_normal((6, 64)).astype(np.float32) * 0.01).cuda()
+    istd = torch.from_numpy((5 + rng.random((6, 64))).astype(np.float32)).cuda()
+    nat = torch.empty(B, 6, T, 64, device="cuda")
+    cl = torch.empty(B, T, 64, 6, device="cuda")
+    st2 = (C.c_int64 * 4)(T * 64 * 6, 1, 64 * 6, 6)
+    assert L.adyolo_gcc_from_stft(ptr(d_spec), B, T, C.byref(cfg), ptr(mean), ptr(istd), ptr(nat), st, stream_ptr()) == 0
+    assert L.adyolo_gcc_from_stft(ptr(d_spec), B, T, C.byref(cfg), ptr(mean), ptr(istd), ptr(cl), st2, stream_ptr()) == 0
+    assert torch.equal(cl.permute(0, 3, 1, 2), nat)
+    want = (ref.transpose(0, 3, 1, 2) - mean.cpu().numpy()[None, :, None, :]) * istd.cpu().numpy()[None, :, None, :]
+    assert np.abs(nat.cpu().numpy() - want).max() < 1e-3
+
+
 def test_scaler_action_single_gpu(A):
     rng = np.random.default_rng(4)
     clips = [np.clip(rng.standard_normal((24000 * 2, 4)) * (500 + 800 * i), -32768, 32767).astype(np.int16) for i in range(5)]

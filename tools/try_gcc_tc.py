@@ -17,14 +17,14 @@ def run(mode):
     out = features_mic_batched(torch.from_numpy(clips).cuda())
     torch.cuda.synchronize()
     np.save(f"gpurun_out/gcc_{mode}.npy", out.cpu().numpy())
-    if mode == "tc":
+    if mode.startswith("tc"):
         from oracle import features_np as F
         o = out.cpu().numpy()
         for b in range(B):
             ref = F.features_mic_stack(clips[b])
             print("clip", b, "gcc max abs err vs oracle", np.abs(o[b, 4:] - ref[4:]).max(), "mel", np.abs(o[b, :4] - ref[:4]).max(), flush=True)
     # timing at config-3 size
-    Bc, Nc = 128, 24000 * 5
+    Bc, Nc = int(os.environ.get("GT_B", 128)), 24000 * 5
     audio = torch.randint(-3000, 3000, (Bc, Nc, 4), dtype=torch.int16, device="cuda")
     for _ in range(3): o2 = features_mic_batched(audio)
     torch.cuda.synchronize()
@@ -49,6 +49,12 @@ def run(mode):
     for _ in range(10): go()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
+    # generic-stride path: channels-last output (B, T, 64, 6) must hold the same numbers
+    g2 = torch.empty(Bc, T, 64, 6, device="cuda")
+    st2 = (C.c_int64 * 4)(T * 64 * 6, 1, 64 * 6, 6)
+    rc = L.adyolo_gcc_from_stft(ptr(spec), Bc, T, C.byref(cfg), None, None, ptr(g2), st2, stream_ptr()); assert rc == 0
+    torch.cuda.synchronize()
+    print("strided == natural:", bool(torch.equal(g2.permute(0, 3, 1, 2), g)), flush=True)
     print(mode, "GCC kernel alone: %.3f ms  (%.0f GB/s algorithmic)" % (ms, (spec.numel() * 8 + g.numel() * 4) / ms / 1e6), flush=True)
 
 if __name__ == "__main__":
