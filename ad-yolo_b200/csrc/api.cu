@@ -244,6 +244,11 @@ int adyolo_loss_backward(const float* logit, int B, int T, const adyolo_grid_cfg
     return launch_loss_backward(logit, B, T, a, workspace, grad_output, grad_out, (cudaStream_t)stream);
 }
 
+int adyolo_loss_grad_scale(float* grad, int64_t n, const float* grad_output, void* stream) {
+    if (!grad || !grad_output || n < 0) return set_error(ADY_ERR_INVALID, "loss_grad_scale: bad args");
+    return launch_grad_scale(grad, (long long)n, grad_output, (cudaStream_t)stream);
+}
+
 int adyolo_yolo_post(const float* logit, int64_t n_frames, const adyolo_grid_cfg* cfg, float conf_thresh,
                      float clss_thresh, float unify_thresh, int max_det, float* det, int32_t* count, int32_t* overflow,
                      void* stream) {

@@ -468,4 +468,32 @@ int launch_loss_backward(const float* logit, int B, int T, const AssignCfg& cfg,
     return ADY_OK;
 }
 
+// grad *= gscale[0] in place; nothing to do (and nothing touched) for the usual upstream gradient 1
+__global__ void __launch_bounds__(256) grad_scale_kernel(float* __restrict__ g, long long n, const float* __restrict__ gscale) {
+    const float s = gscale[0];
+    if (s == 1.0f) return;
+    const long long n4 = n >> 2, stride = (long long)gridDim.x * blockDim.x;
+    float4* g4 = reinterpret_cast<float4*>(g);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 v = g4[i];
+        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        g4[i] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) g[(n4 << 2) + threadIdx.x] *= s;
+}
+
+int launch_grad_scale(float* grad, long long n, const float* gscale, cudaStream_t stream) {
+    if (n <= 0) return ADY_OK;
+    if (reinterpret_cast<uintptr_t>(grad) & 15) return set_error(ADY_ERR_INVALID, "adyolo_loss_grad_scale: grad must be 16-byte aligned");
+    int dev = 0, sms = 0;
+    ADY_CUDA_CHECK(cudaGetDevice(&dev));
+    ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long long blocks = ((n >> 2) + 255) / 256;
+    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+    if (blocks < 1) blocks = 1;
+    grad_scale_kernel<<<(int)blocks, 256, 0, stream>>>(grad, n, gscale);
+    ADY_LAUNCH_CHECK("grad_scale_kernel");
+    return ADY_OK;
+}
+
 }  // namespace ady

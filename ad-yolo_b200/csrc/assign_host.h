@@ -44,6 +44,7 @@ int launch_loss(const float* logit, const float* target, long long M, const long
 
 int launch_loss_backward(const float* logit, int B, int T, const AssignCfg& cfg, const void* ws,
                          const float* grad_output, float* grad_out, cudaStream_t stream);
+int launch_grad_scale(float* grad, long long n, const float* gscale, cudaStream_t stream);
 
 // decode + conn-merge NMS (datasets.py:741-857)
 int launch_yolo_post(const float* logit, long long n_frames, const AssignCfg& cfg, float conf_thresh, float clss_thresh,

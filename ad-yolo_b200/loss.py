@@ -51,6 +51,11 @@ def adyolo_assign(logit: torch.Tensor, target: torch.Tensor, grid: GridSpec):
 
 
 class _ADYOLOFn(torch.autograd.Function):
+    """Forward launches assignment + loss; when ``logit`` needs a gradient the same pass over the
+    logits also writes d loss / d logit (the normalisers are known before that pass), so backward
+    is a single launch that scales the stored gradient by ``grad_output`` on the device -- and
+    returns without touching memory when that is exactly 1 (``loss.backward()``, train.py:54)."""
+
     @staticmethod
     def forward(ctx, logit, target, grid, n_rows_dev=None):
         B, T, _ = logit.shape
@@ -60,15 +65,17 @@ class _ADYOLOFn(torch.autograd.Function):
         with torch.cuda.device(logit.device):
             loss = torch.empty(1, dtype=torch.float32, device=logit.device)
             nbytes = L.adyolo_loss_workspace_bytes(B, T, C.byref(grid.c))
-            # the workspace carries label bits / counts to backward: private per call when needed
+            # the workspace carries label bits / counts to a repeated backward: private per call when needed
             ws = torch.empty(nbytes, dtype=torch.uint8, device=logit.device) if need_grad else _workspace(nbytes, logit.device)
+            grad = torch.empty_like(logit) if need_grad else None
             if n_rows_dev is None:
-                check(L.adyolo_loss(ptr(logit), ptr(target), M, B, T, C.byref(grid.c), ptr(loss), None, None, None,
+                check(L.adyolo_loss(ptr(logit), ptr(target), M, B, T, C.byref(grid.c), ptr(loss), ptr(grad), None, None,
                                     None, ptr(ws), stream_ptr()), "adyolo_loss")
             else:
                 check(L.adyolo_loss_devcount(ptr(logit), ptr(target), M, ptr(n_rows_dev), B, T, C.byref(grid.c),
-                                             ptr(loss), None, ptr(ws), stream_ptr()), "adyolo_loss_devcount")
+                                             ptr(loss), ptr(grad), ptr(ws), stream_ptr()), "adyolo_loss_devcount")
         ctx.grid = grid
+        ctx.grad = grad                     # consumed (scaled in place and handed out) by the first backward
         ctx.save_for_backward(logit, ws)
         return loss
 
@@ -77,10 +84,15 @@ class _ADYOLOFn(torch.autograd.Function):
         logit, ws = ctx.saved_tensors
         B, T, _ = logit.shape
         gout = gout.to(torch.float32).contiguous()
+        L = _lib.lib()
         with torch.cuda.device(logit.device):
-            grad = torch.empty_like(logit)
-            check(_lib.lib().adyolo_loss_backward(ptr(logit), B, T, C.byref(ctx.grid.c), ptr(ws), ptr(gout), ptr(grad),
-                                                  stream_ptr()), "adyolo_loss_backward")
+            grad, ctx.grad = ctx.grad, None
+            if grad is not None:
+                check(L.adyolo_loss_grad_scale(ptr(grad), grad.numel(), ptr(gout), stream_ptr()), "adyolo_loss_grad_scale")
+            else:                           # backward again (retain_graph=True): rebuild from the workspace
+                grad = torch.empty_like(logit)
+                check(L.adyolo_loss_backward(ptr(logit), B, T, C.byref(ctx.grid.c), ptr(ws), ptr(gout), ptr(grad),
+                                             stream_ptr()), "adyolo_loss_backward")
         return grad, None, None, None
 
 

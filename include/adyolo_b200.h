@@ -183,6 +183,12 @@ int adyolo_loss_backward(const float* logit, int B, int T, const adyolo_grid_cfg
                          const float* grad_output /* device float32[1] or NULL (= 1) */, float* grad_out,
                          void* stream);
 
+/* Autograd glue for the fused forward (adyolo_loss with grad_out != NULL already holds
+ * d loss / d logit): grad[0..n) *= grad_output[0], in place, with the scalar read on the device
+ * -- when it is exactly 1 (the plain `loss.backward()` of train.py:54) the kernel returns without
+ * touching the buffer, so backward costs one launch and no memory traffic.                     */
+int adyolo_loss_grad_scale(float* grad, int64_t n, const float* grad_output /* device float32[1] */, void* stream);
+
 /* LabelPostProcessor.get_yolo_output (datasets.py:741-857, nms == 'conn-merge') for n_frames
  * frames of logits (n_frames, Ga*Ge*A*(C+3)): decode, class-confidence thresholding, per-class
  * connectivity merge under the great-circle distance, softmax-weighted Cartesian vote.

@@ -181,6 +181,29 @@ def test_device_row_count_path_equals_host_path(A):
     assert (l1.grad - l2.grad).abs().max().item() <= 1e-6 * l1.grad.abs().max().item()
 
 
+def test_fused_forward_gradient_reuse_and_repeat_backward(A):
+    """The gradient is produced by the forward pass and handed out by the first backward (scaled on
+    the device); a second backward through a retained graph rebuilds it from the workspace; no_grad
+    forward allocates no gradient and returns the same loss."""
+    C, B, T = 13, 4, 50
+    rng = np.random.default_rng(5)
+    grid = _grid(A, C)
+    rows = A.label_rows_batched(torch.from_numpy(_events(rng, B, T, C)).cuda(), T, grid)
+    crit = A.ADYOLOloss(default_params(C, "cuda:0"))
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    logit = torch.randn((B, T, grid.nb_predicts * grid.nb_channels), device="cuda", generator=gen).requires_grad_(True)
+    loss = crit(logit, rows)
+    loss.backward(retain_graph=True)
+    g1 = logit.grad.clone()
+    loss.backward()                                            # accumulates the rebuilt gradient
+    assert torch.allclose(logit.grad, 2 * g1, rtol=1e-6, atol=0)
+    logit.grad = None
+    (crit(logit, rows) * 0.25).sum().backward()                # expanded, non-unit upstream gradient
+    assert torch.allclose(logit.grad, 0.25 * g1, rtol=1e-6, atol=0)
+    with torch.no_grad():
+        assert crit(logit, rows).item() == loss.item()
+
+
 def test_loss_nan_without_targets_and_bad_shapes(A):
     crit = A.ADYOLOloss(default_params(12, "cuda:0"))
     out = crit(torch.zeros(1, 2, 2400, device="cuda"), torch.zeros(0, 7))
