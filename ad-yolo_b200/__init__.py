@@ -12,6 +12,7 @@ Mirrors (same names / argument meaning) of the reference call surface, SURVEY.md
 * ``labels.get_yolo_label`` / ``labels.collate_fn`` (src/datasets.py:457-482, 164-184)
 * ``loss.ADYOLOloss`` / ``loss.WrapperCriterion`` (src/models/loss.py:156-251, src/wrapper.py:63-88)
 * ``scaler.preprocess_scaler`` (src/preprocess.py:87-130) with a multi-GPU all-reduce
+* ``augment.SpecAug`` (src/utils/augmentations.py:6-33); rotation is fused into features / labels
 """
 from . import _lib  # noqa: F401
 from .features import (FeatureLabelProcessor, audio2stft, stft2melscale, stft2iv,  # noqa: F401
@@ -21,6 +22,7 @@ from .loss import ADYOLOloss, WrapperCriterion, adyolo_assign  # noqa: F401
 from .scaler import ScalerAccumulator, preprocess_scaler  # noqa: F401
 from .pipeline import HostBatchPipeline  # noqa: F401
 from .postprocess import LabelPostProcessor, yolo_post_batched  # noqa: F401
+from .augment import SpecAug  # noqa: F401
 from .data import (ResidentClips, EpochSampler, chunk_plan, features_batched_views,  # noqa: F401
                    load_wav2npy, load_csv2dict)
 

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libadyolo_b200.so")
-SOURCES = ["frontend.cu", "frontend_aux.cu", "assign.cu", "labels.cu", "nms.cu", "gcc_tc.cu", "tables.cu", "scaler.cu", "api.cu"]
+SOURCES = ["frontend.cu", "frontend_aux.cu", "assign.cu", "labels.cu", "nms.cu", "gcc_tc.cu", "augment.cu", "tables.cu", "scaler.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC"]
 
@@ -96,6 +96,7 @@ _SIGS = {
     "adyolo_yolo_post": (C.c_int, [_P, C.c_int64, C.POINTER(GridCfg), C.c_float, C.c_float, C.c_float, C.c_int, _P, _P, _P, _P]),
     "adyolo_loss_backward": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(GridCfg), _P, _P, _P, _P]),
     "adyolo_loss_grad_scale": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "adyolo_spec_mask": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.c_int, _P, C.c_int, _P, _P]),
 }
 
 _lib = None

@@ -17,6 +17,8 @@ int launch_logmel_from_stft(const float2* spec, int B, long long T, int C, int C
                             float* out, OutStrides os, uint32_t* gmax_ws, float top_db, int apply_topdb, cudaStream_t stream);
 int launch_iv_from_stft(const float2* spec, int B, long long T, const float* mean, const float* istd, float* out,
                         OutStrides os, int* flags, cudaStream_t stream);
+int launch_spec_mask(float* feat, int B, int C, long long T, int F, const int* rects, int G, const int* bounds,
+                     cudaStream_t stream);
 int launch_gcc_from_stft(const float2* spec, int B, long long T, const float* mean, const float* istd, float* out,
                          OutStrides os, cudaStream_t stream);
 
@@ -242,6 +244,13 @@ int adyolo_loss_backward(const float* logit, int B, int T, const adyolo_grid_cfg
     if (rc) return rc;
     if (!logit || !workspace || !grad_out) return set_error(ADY_ERR_INVALID, "loss_backward: NULL pointer");
     return launch_loss_backward(logit, B, T, a, workspace, grad_output, grad_out, (cudaStream_t)stream);
+}
+
+int adyolo_spec_mask(float* feat, int B, int C, int64_t T, int F, const int32_t* rects, int n_groups,
+                     const int32_t* group_bounds, void* stream) {
+    if (!feat || !rects || !group_bounds || B < 0 || C <= 0 || T <= 0 || F <= 0 || n_groups < 0)
+        return set_error(ADY_ERR_INVALID, "spec_mask: bad args");
+    return launch_spec_mask(feat, B, C, (long long)T, F, rects, n_groups, group_bounds, (cudaStream_t)stream);
 }
 
 int adyolo_loss_grad_scale(float* grad, int64_t n, const float* grad_output, void* stream) {

@@ -189,6 +189,16 @@ int adyolo_loss_backward(const float* logit, int B, int T, const adyolo_grid_cfg
  * touching the buffer, so backward costs one launch and no memory traffic.                     */
 int adyolo_loss_grad_scale(float* grad, int64_t n, const float* grad_output /* device float32[1] */, void* stream);
 
+/* SpecAug masks (augmentations.py:6-33 as applied by datasets.py:158-160 to each feature group
+ * permuted to (C, T, F): torchaudio "TimeMasking" therefore zeroes a band of MEL bins and
+ * "FrequencyMasking" a run of FRAMES, shared by the channels of a group; mask value 0).
+ *   feat        device float32 (B, C, T, F) contiguous, masked in place (write-only)
+ *   rects       device int32 (B, n_groups, 4) = [mel0, mel1, frame0, frame1), empty = no mask
+ *   group_bounds device int32 (n_groups, 2) = [c0, c1) channel range of each group
+ * The intervals are drawn on the host with the reference's RNG sequence (adyolo_b200.SpecAug).  */
+int adyolo_spec_mask(float* feat, int B, int C, int64_t T, int F, const int32_t* rects, int n_groups,
+                     const int32_t* group_bounds, void* stream);
+
 /* LabelPostProcessor.get_yolo_output (datasets.py:741-857, nms == 'conn-merge') for n_frames
  * frames of logits (n_frames, Ga*Ge*A*(C+3)): decode, class-confidence thresholding, per-class
  * connectivity merge under the great-circle distance, softmax-weighted Cartesian vote.

@@ -212,8 +212,23 @@ def main():
         ro[f"events_{c}"] = np.asarray([ev for fr, evs in l2.items() for ev in evs], np.float64)
         ro[f"rows_{c}"] = np.asarray(flp.get_yolo_label(copy.deepcopy(l2), 20), np.float64)
     np.savez_compressed(os.path.join(GOLD, "rotation.npz"), **ro)
-    # ---- chunking action + epoch sampler (reference functions executed as-is)
+    # ---- SpecAug (reference class executed as-is on (C,T,F) tensors of ones; seeded python + torch RNG)
     import random
+    ps = ref_shims.ref_params(12)
+    ps["aug_config"].update({"spec_augment": True, "spec_augment_thresh": 0.5,
+                             "spec_augment_time_mask_param": 40, "spec_augment_freq_mask_param": 40})
+    sa = ref_aug.SpecAug(ps, is_valid=False)
+    random.seed(11)
+    torch.manual_seed(11)
+    sm = np.zeros((24, 2, 200, 64), np.uint8)
+    for clip in range(24):
+        for gi, ch in enumerate((4, 3)):                       # datasets.py:158-160: MEL group, then IV group
+            y = sa.augment(torch.ones(ch, 200, 64))             # augmentations.py:28-33
+            assert bool((y == y[0:1]).all())
+            sm[clip, gi] = (y[0] == 0).numpy()
+    np.savez_compressed(os.path.join(GOLD, "specaug.npz"), masked=sm, seed=np.int64(11), thresh=np.float64(0.5),
+                        time_mask_param=np.int64(40), freq_mask_param=np.int64(40))
+    # ---- chunking action + epoch sampler (reference functions executed as-is)
     import preprocess as ref_pre
     cp = {"sr": 24000, "chunk_window_s": 20, "chunk_stride_s": 1, "label_hop_len_s": 0.1}
     rng = np.random.default_rng(31)

@@ -261,3 +261,42 @@ def test_fused_rotation_augmentation_all_16_combinations(A, scaler2021):
     rows = A.label_rows_batched(torch.from_numpy(ev).cuda(), 10, grid, rot_comb=torch.from_numpy(comb).cuda()).cpu().numpy()
     want = assign_np.events_to_rows(augment_np.rotate_events(ev, comb), 10).astype(np.float32)
     assert np.array_equal(rows, want)
+
+
+def test_specaug_masks_on_device(A, scaler2021):
+    """SURVEY §8(f) N2 (SpecAug half): the mask kernel applied to front-end output equals the oracle
+    restatement of the reference's masking (pinned by tests/golden/specaug.npz on the CPU side);
+    per-clip reference surface; MIC grouping; intervals clipped to the tensor."""
+    import random
+    from oracle import augment_np
+    params = {"aug_config": {"spec_augment": True, "spec_augment_thresh": 0.7,
+                             "spec_augment_time_mask_param": 40, "spec_augment_freq_mask_param": 40}}
+    sa = A.SpecAug(params, is_valid=False)
+    rng = np.random.default_rng(8)
+    audio = torch.from_numpy(rng.integers(-3000, 3000, size=(6, 24000 * 2, 4)).astype(np.int16)).cuda()
+    sd = _scaler_dev(A, scaler2021)
+    feat = A.features_batched(audio, sd)
+    ref_in = feat.cpu().numpy()
+    random.seed(3); torch.manual_seed(3)
+    rects = sa.draw(6, feat.shape[2], 64)
+    assert rects.any()
+    out = sa.apply_rects(feat.clone(), rects)
+    np.testing.assert_array_equal(out.cpu().numpy(), augment_np.specaug_apply(ref_in, rects.numpy()))
+    # batched draw+apply consumes the RNG exactly like draw()
+    random.seed(3); torch.manual_seed(3)
+    assert torch.equal(sa.augment_batched(feat.clone()), out)
+    # per-clip reference surface: (C, T, F) group -> masked copy, input untouched
+    random.seed(5); torch.manual_seed(5)
+    r1 = sa.draw(1, feat.shape[2], 64, 1)
+    random.seed(5); torch.manual_seed(5)
+    grp = feat[2, :4].clone()
+    y = sa.augment(grp)
+    want = augment_np.specaug_apply(grp.cpu().numpy()[None], r1.numpy(), groups=((0, 4),))[0]
+    np.testing.assert_array_equal(y.cpu().numpy(), want)
+    assert torch.equal(grp, feat[2, :4])
+    # MIC grouping (4 + 6 channels), odd F (no float4 path), out-of-range intervals are clipped
+    x = torch.randn(2, 10, 37, 63, device="cuda")
+    rr = torch.tensor([[[5, 20, 30, 99], [0, 0, -3, 2]], [[60, 70, 0, 0], [1, 2, 36, 37]]], dtype=torch.int32)
+    got = sa.apply_rects(x.clone(), rr, groups=((0, 4), (4, 10))).cpu().numpy()
+    np.testing.assert_array_equal(got, augment_np.specaug_apply(x.cpu().numpy(), np.clip(rr.numpy(), 0, None), groups=((0, 4), (4, 10))))
+    assert A.SpecAug(params, is_valid=True).augment_batched(feat) is feat
