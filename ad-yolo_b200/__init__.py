@@ -20,7 +20,7 @@ from .features import (FeatureLabelProcessor, audio2stft, stft2melscale, stft2iv
 from .labels import DeviceRows, get_yolo_label, collate_fn, label_rows_batched  # noqa: F401
 from .loss import ADYOLOloss, WrapperCriterion, adyolo_assign  # noqa: F401
 from .scaler import ScalerAccumulator, preprocess_scaler  # noqa: F401
-from .pipeline import HostBatchPipeline  # noqa: F401
+from .pipeline import HostBatchPipeline, bind_host_to_device  # noqa: F401
 from .postprocess import LabelPostProcessor, yolo_post_batched  # noqa: F401
 from .augment import SpecAug  # noqa: F401
 from .data import (ResidentClips, EpochSampler, chunk_plan, features_batched_views,  # noqa: F401

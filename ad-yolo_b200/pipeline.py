@@ -7,7 +7,61 @@ i.  Pure plumbing (torch streams / events); no arithmetic.
 """
 from __future__ import annotations
 
+import os
+
 import torch
+
+
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_device(device) -> dict:
+    """Restrict the calling process to the CPU cores of the NUMA node the GPU hangs off, so that the
+    pinned staging buffers allocated afterwards are node-local (first touch) and host -> device copies
+    do not cross the socket interconnect.  With one process per GPU (``torchrun``) an unbound rank can
+    land on the other socket: 8 ranks then share the inter-socket link instead of 8 PCIe root ports.
+    Call once per rank after ``torch.cuda.set_device`` and before ``pin_memory``.  Best effort:
+    returns ``{"bound": False, "why": ...}`` when the topology is not visible (sysfs, then NVML)."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    props = torch.cuda.get_device_properties(idx)
+    try:
+        bus = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+    except AttributeError:
+        return {"bound": False, "why": "torch does not expose the PCI address"}
+    allowed = os.sched_getaffinity(0)
+    cpus, node, how = set(), None, None
+    try:
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read())
+        if node >= 0:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                cpus, how = _parse_cpulist(f.read()), "sysfs"
+    except (OSError, ValueError):
+        pass
+    if not cpus:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(("0000" + bus).encode() if len(bus) < 13 else bus.encode())
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {i for i in range(os.cpu_count()) if (int(words[i // 64]) >> (i % 64)) & 1}
+            how = "nvml"
+        except Exception as e:  # noqa: BLE001 - topology is optional
+            return {"bound": False, "why": f"no NUMA information for {bus} ({type(e).__name__})"}
+    cpus &= allowed
+    if not cpus:
+        return {"bound": False, "why": f"NUMA node {node} has no CPU this process may use"}
+    if cpus != allowed:
+        os.sched_setaffinity(0, cpus)
+    return {"bound": True, "pci": bus, "numa_node": node, "cpus": len(cpus), "via": how}
 
 
 class HostBatchPipeline:

@@ -169,6 +169,8 @@ def main_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # node-local pinned staging buffers: without this the e2e number stops scaling at 4 ranks
+    numa = A.bind_host_to_device(dev)
 
     rng = np.random.default_rng(1234 + rank)
     audio_h = torch.from_numpy(synth_audio(rng, BATCH)).pin_memory()
@@ -279,7 +281,7 @@ def main_ours(args):
                            "parallelism": f"clip-sharded x{world}, no collective"},
                 "e2e": {"value": e2e_value, "unit": "audio-hours/s", "ms_per_step": e2e_ms / args.steps,
                         "h2d_bytes_per_step": int(audio_h.numel() * 2 + events_h.numel() * 8), "d2h_bytes_per_step": 4 + 8},
-                "gpu_launches": args.steps * 10, "roofline": roof, "cpu_baseline": cpu_base, "clocks": clocks,
+                "gpu_launches": args.steps * 10, "roofline": roof, "cpu_baseline": cpu_base, "clocks": clocks, "host_numa": numa,
                 "loss": lv}
         print(json.dumps(line))
     if world > 1:
