@@ -20,6 +20,11 @@ for tgt in (rows, drows):
     logit = torch.randn(5, 10, 2400, device="cuda", requires_grad=True)
     loss = crit(logit, tgt); loss.backward()
 D, mk, am = A.adyolo_assign(logit, rows, grid)
+(crit(logit, rows) * 0.5).backward()                       # grad_scale path with a non-unit upstream gradient
+sa = A.SpecAug({"aug_config": {"spec_augment": True, "spec_augment_thresh": 1.0, "spec_augment_time_mask_param": 40,
+                               "spec_augment_freq_mask_param": 40}}, is_valid=False)
+f = sa.augment_batched(f)
+dets = A.yolo_post_batched(logit.detach()[:1], grid, 0.5, 0.5, 15.0)
 acc = A.ScalerAccumulator(7); acc.update(A.features_batched(clips, None)); r = acc.result()
 torch.cuda.synchronize()
 print("sanitize pass ok", float(loss), f.shape, m.shape)
