@@ -93,7 +93,7 @@ _SIGS = {
     "adyolo_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.POINTER(GridCfg)]),
     "adyolo_loss": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.POINTER(GridCfg), _P, _P, _P, _P, _P, _P, _P]),
     "adyolo_loss_devcount": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, C.c_int, C.POINTER(GridCfg), _P, _P, _P, _P]),
-    "adyolo_yolo_post": (C.c_int, [_P, C.c_int64, C.POINTER(GridCfg), C.c_float, C.c_float, C.c_float, C.c_int, _P, _P, _P, _P]),
+    "adyolo_yolo_post": (C.c_int, [_P, C.c_int64, C.POINTER(GridCfg), C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _P, _P, _P, _P]),
     "adyolo_loss_backward": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(GridCfg), _P, _P, _P, _P]),
     "adyolo_loss_grad_scale": (C.c_int, [_P, C.c_int64, _P, _P]),
     "adyolo_spec_mask": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.c_int, _P, C.c_int, _P, _P]),

@@ -259,14 +259,14 @@ int adyolo_loss_grad_scale(float* grad, int64_t n, const float* grad_output, voi
 }
 
 int adyolo_yolo_post(const float* logit, int64_t n_frames, const adyolo_grid_cfg* cfg, float conf_thresh,
-                     float clss_thresh, float unify_thresh, int max_det, float* det, int32_t* count, int32_t* overflow,
-                     void* stream) {
+                     float clss_thresh, float unify_thresh, int nms_mode, int max_det, float* det, int32_t* count,
+                     int32_t* overflow, void* stream) {
     AssignCfg a;
     int rc = make_cfgs(cfg, &a, nullptr);
     if (rc) return rc;
     if (!logit || !det || !count || !overflow) return set_error(ADY_ERR_INVALID, "yolo_post: NULL pointer");
-    return launch_yolo_post(logit, (long long)n_frames, a, conf_thresh, clss_thresh, unify_thresh, max_det, det, count,
-                            overflow, (cudaStream_t)stream);
+    return launch_yolo_post(logit, (long long)n_frames, a, conf_thresh, clss_thresh, unify_thresh, nms_mode, max_det, det,
+                            count, overflow, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -48,7 +48,8 @@ int launch_grad_scale(float* grad, long long n, const float* gscale, cudaStream_
 
 // decode + conn-merge NMS (datasets.py:741-857)
 int launch_yolo_post(const float* logit, long long n_frames, const AssignCfg& cfg, float conf_thresh, float clss_thresh,
-                     float unify_thresh, int max_det, float* det, int32_t* count, int* overflow, cudaStream_t stream);
+                     float unify_thresh, int nms_mode, int max_det, float* det, int32_t* count, int* overflow,
+                     cudaStream_t stream);
 
 // grid-cell responsibility (datasets.py:457-482): events -> 32-bit cell mask + count, rows
 struct CellCfg {

@@ -1,7 +1,8 @@
-// AD-YOLO decode + connectivity-merge NMS post-processing on the GPU.
+// AD-YOLO decode + NMS post-processing on the GPU: the reference's default
+// connectivity-merge and its two alternatives, soft-merge and plain NMS.
 //
 // Reference behaviour replaced: /root/reference/src/datasets.py:741-857 (LabelPostProcessor.
-// get_yolo_output with nms == 'conn-merge') and its helpers :863-919.  The reference walks the
+// get_yolo_output, all three `nms` branches) and its helpers :863-919.  The reference walks the
 // frames of one clip in Python on the CPU (it dominates validation time); here one block handles
 // one (clip, frame):
 //   1. thread = anchor: decode (sigmoid / tanh, scale, offset, clamp V, wrap U) with the same
@@ -29,6 +30,7 @@ struct NmsCfg {
     float conf_thresh, clss_thresh, unify_thresh, v_hi;   // v_hi = float(90 - 1e-7)
     float inv_clss;                                       // ATen divides by a scalar as a * (1/b)
     int max_det;
+    int mode;                                             // 0 conn-merge, 1 soft-merge, 2 plain NMS (datasets.py:786-848)
 };
 
 __global__ void __launch_bounds__(NMS_MAXA)
@@ -121,7 +123,8 @@ yolo_post_kernel(const float* __restrict__ logit, AssignCfg cfg, NmsCfg nc, floa
                 const float du = fabsf(__fadd_rn(w_ur[j], -ui));
                 const float dist = __fadd_rn(__fmul_rn(w_sv[j], svi), __fmul_rn(__fmul_rn(w_cv[j], cvi), cosf(du)));
                 const float D = __fmul_rn(acosf(nms_clamp(dist, -1.f, 1.f)), cfg.rad2deg);
-                if (D < nc.unify_thresh) row[j >> 5] |= 1u << (j & 31);
+                // conn-merge links with D < thr (:801); soft-merge / plain NMS unify and suppress with D <= thr (:826-831, :845-846)
+                if (nc.mode == 0 ? D < nc.unify_thresh : D <= nc.unify_thresh) row[j >> 5] |= 1u << (j & 31);
             }
 #pragma unroll
             for (int w = 0; w < 8; ++w) adj[tid * 8 + w] = row[w];
@@ -138,6 +141,45 @@ yolo_post_kernel(const float* __restrict__ logit, AssignCfg cfg, NmsCfg nc, floa
 #pragma unroll
                 for (int w = 7; w >= 0; --w) if (rem[w]) seed = 32 * w + __ffs(rem[w]) - 1;
                 unsigned cur[8], pre[8];
+                if (nc.mode != 0) {
+                    // soft-merge (:818-831): the best remaining candidate is voted together with ALL candidates
+                    // of the class within the threshold (also already suppressed ones); plain NMS (:834-846)
+                    // emits it as it is.  Both then drop it and every remaining candidate within the threshold.
+                    const int d = s_ndet;
+                    if (nc.mode == 2) {
+                        if (d < nc.max_det) { out[d * 4] = (float)c; out[d * 4 + 1] = w_cx[seed]; out[d * 4 + 2] = w_cy[seed]; out[d * 4 + 3] = w_cz[seed]; }
+                        else *overflow = 1;
+                    } else {
+                        float emax = -INFINITY;
+                        for (int w = 0; w < 8; ++w) for (unsigned b = adj[seed * 8 + w]; b; b &= b - 1) {
+                            const int m = 32 * w + __ffs(b) - 1;
+                            emax = fmaxf(emax, expf(__fmul_rn(__fmul_rn(w_score[m], w_score[m]), nc.inv_clss)));
+                        }
+                        float den = 0.f;
+                        for (int w = 0; w < 8; ++w) for (unsigned b = adj[seed * 8 + w]; b; b &= b - 1) {
+                            const int m = 32 * w + __ffs(b) - 1;
+                            den += expf(expf(__fmul_rn(__fmul_rn(w_score[m], w_score[m]), nc.inv_clss)) - emax);
+                        }
+                        float vx = 0.f, vy = 0.f, vz = 0.f;
+                        for (int w = 0; w < 8; ++w) for (unsigned b = adj[seed * 8 + w]; b; b &= b - 1) {
+                            const int m = 32 * w + __ffs(b) - 1;
+                            const float wt = expf(expf(__fmul_rn(__fmul_rn(w_score[m], w_score[m]), nc.inv_clss)) - emax) / den;
+                            vx += w_cx[m] * wt; vy += w_cy[m] * wt; vz += w_cz[m] * wt;
+                        }
+                        const float nrm = sqrtf(vx * vx + vy * vy + vz * vz);
+                        if (d < nc.max_det) { out[d * 4] = (float)c; out[d * 4 + 1] = vx / nrm; out[d * 4 + 2] = vy / nrm; out[d * 4 + 3] = vz / nrm; }
+                        else *overflow = 1;
+                    }
+                    s_ndet = d + 1;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        unsigned drop = adj[seed * 8 + w] & rem[w];
+                        if (w == (seed >> 5)) drop |= 1u << (seed & 31);
+                        left -= __popc(drop & rem[w]);
+                        rem[w] &= ~drop;
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int w = 0; w < 8; ++w) { cur[w] = adj[seed * 8 + w] & rem[w]; pre[w] = 0; }
                 cur[seed >> 5] |= 1u << (seed & 31);
@@ -197,12 +239,14 @@ size_t nms_shared_bytes(const AssignCfg& c) {
 }
 
 int launch_yolo_post(const float* logit, long long n_frames, const AssignCfg& cfg, float conf_thresh, float clss_thresh,
-                     float unify_thresh, int max_det, float* det, int32_t* count, int* overflow, cudaStream_t stream) {
+                     float unify_thresh, int nms_mode, int max_det, float* det, int32_t* count, int* overflow,
+                     cudaStream_t stream) {
     const int NA = cfg.ga * cfg.ge * cfg.nb_anchors;
     if (NA > NMS_MAXA) return set_error(ADY_ERR_UNSUPPORTED, "yolo_post: %d anchors per frame exceed %d", NA, NMS_MAXA);
     if (n_frames <= 0 || max_det <= 0) return set_error(ADY_ERR_INVALID, "yolo_post: empty input");
     if (n_frames > 0x7fffffffLL) return set_error(ADY_ERR_INVALID, "yolo_post: too many frames");
-    NmsCfg nc{conf_thresh, clss_thresh, unify_thresh, (float)(90 - 1e-7), 1.0f / clss_thresh, max_det};
+    if (nms_mode < 0 || nms_mode > 2) return set_error(ADY_ERR_INVALID, "yolo_post: nms_mode must be 0 (conn-merge), 1 (soft-merge) or 2 (nms)");
+    NmsCfg nc{conf_thresh, clss_thresh, unify_thresh, (float)(90 - 1e-7), 1.0f / clss_thresh, max_det, nms_mode};
     const size_t shmem = nms_shared_bytes(cfg);
     static int configured_dev = -1;
     int dev = 0;

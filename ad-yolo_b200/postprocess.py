@@ -13,8 +13,15 @@ from ._lib import check, ptr, require_cuda, stream_ptr
 from .labels import GridSpec
 
 
+NMS_MODES = {"conn-merge": 0, "soft-merge": 1}       # any other string -> plain NMS (datasets.py:834)
+
+
+def nms_mode(name: str) -> int:
+    return NMS_MODES.get(name, 2)
+
+
 def yolo_post_batched(logit: torch.Tensor, grid: GridSpec, conf_thresh: float, clss_thresh: float, unify_thresh: float,
-                      max_det: int | None = None):
+                      max_det: int | None = None, nms: str = "conn-merge"):
     """logit (B, T, Ga*Ge*A*(C+3)) float32 CUDA -> det (B, T, max_det, 4) float32 [class, x, y, z],
     count (B, T) int32.  ``max_det`` defaults to the exact upper bound (anchors x classes per frame);
     with a smaller cap the call raises if any frame produced more detections."""
@@ -30,7 +37,7 @@ def yolo_post_batched(logit: torch.Tensor, grid: GridSpec, conf_thresh: float, c
         count = torch.zeros((B, T), dtype=torch.int32, device=logit.device)
         over = torch.zeros(1, dtype=torch.int32, device=logit.device)
         check(_lib.lib().adyolo_yolo_post(ptr(logit), B * T, C.byref(grid.c), float(conf_thresh), float(clss_thresh),
-                                          float(unify_thresh), int(max_det), ptr(det), ptr(count), ptr(over), stream_ptr()),
+                                          float(unify_thresh), nms_mode(nms), int(max_det), ptr(det), ptr(count), ptr(over), stream_ptr()),
               "adyolo_yolo_post")
     if int(over.item()):
         raise RuntimeError(f"yolo_post_batched: a frame produced more than max_det={max_det} detections")
@@ -50,9 +57,7 @@ class LabelPostProcessor:
         self.clss_thresh = tc["clss_thresh"]
         self.unify_thresh = tc["unify_thresh"]
         self.g_overlap = tc["g_overlap"]
-        self.nms = tc["nms"]
-        if self.nms != "conn-merge":
-            raise NotImplementedError(f"nms: {self.nms} (the reference default 'conn-merge' is implemented)")
+        self.nms = tc["nms"]                          # 'conn-merge' | 'soft-merge' | anything else = plain NMS
         self.nb_anchors = tc["nb_anchors"]
         self.grid = GridSpec(self.nb_classes, tc["nb_anchors"], tc["grid_size"], tc["g_overlap"],
                              tc.get("train_unify", [45., 25., 10.]), tc.get("loss_gains"))
@@ -71,6 +76,6 @@ class LabelPostProcessor:
             raise ValueError("get_yolo_output expects (1, T, n) logits (the reference evaluates with batch 1)")
         dev = batch_yolo_output.device if batch_yolo_output.is_cuda else torch.device("cuda")
         det, count = yolo_post_batched(batch_yolo_output.to(dev), self.grid, self.conf_thresh, self.clss_thresh,
-                                       self.unify_thresh, max_det)
+                                       self.unify_thresh, max_det, self.nms)
         det, count = det[0].cpu(), count[0].cpu().tolist()
         return {t: det[t, :n].tolist() for t, n in enumerate(count) if n > 0}

@@ -199,14 +199,18 @@ int adyolo_loss_grad_scale(float* grad, int64_t n, const float* grad_output /* d
 int adyolo_spec_mask(float* feat, int B, int C, int64_t T, int F, const int32_t* rects, int n_groups,
                      const int32_t* group_bounds, void* stream);
 
-/* LabelPostProcessor.get_yolo_output (datasets.py:741-857, nms == 'conn-merge') for n_frames
- * frames of logits (n_frames, Ga*Ge*A*(C+3)): decode, class-confidence thresholding, per-class
- * connectivity merge under the great-circle distance, softmax-weighted Cartesian vote.
+/* LabelPostProcessor.get_yolo_output (datasets.py:741-857) for n_frames frames of logits
+ * (n_frames, Ga*Ge*A*(C+3)): decode, class-confidence thresholding, then per class
+ *   nms_mode 0  'conn-merge' (reference default, :786-814): connected components of D < unify_thresh,
+ *               softmax-weighted Cartesian vote per component
+ *   nms_mode 1  'soft-merge' (:817-831): best remaining candidate voted with every candidate of the
+ *               class within D <= unify_thresh, then it and its neighbours are suppressed
+ *   nms_mode 2  any other string (:834-846): plain NMS, best kept as is, D <= unify_thresh suppressed
  *   det   device float32 (n_frames, max_det, 4) rows [class, x, y, z] in the reference's order
  *   count device int32 (n_frames); overflow device int32[1] set when a frame had > max_det rows */
 int adyolo_yolo_post(const float* logit, int64_t n_frames, const adyolo_grid_cfg* cfg, float conf_thresh,
-                     float clss_thresh, float unify_thresh, int max_det, float* det, int32_t* count, int32_t* overflow,
-                     void* stream);
+                     float clss_thresh, float unify_thresh, int nms_mode, int max_det, float* det, int32_t* count,
+                     int32_t* overflow, void* stream);
 
 #ifdef __cplusplus
 }

@@ -275,7 +275,12 @@ def main():
     yv[0, :, 6, 2, 0, 0] += 5; yv[0, :, 6, 2, 0, 8] += 5                       # an isolated class-7 detection
     dn = post.postprocess(lg.clone())                                          # datasets.py:741-857
     rows = [[fr] + d for fr, dets in dn.items() for d in dets]
-    np.savez_compressed(os.path.join(GOLD, "nms_ref.npz"), logit=lg.numpy(), rows=np.asarray(rows, np.float64))
+    extra = {}
+    for mode in ("soft-merge", "nms"):                                         # datasets.py:817-846
+        pn["train_config"]["nms"] = mode
+        dm = ref_datasets.LabelPostProcessor(pn).postprocess(lg.clone())
+        extra["rows_" + mode.replace("-", "_")] = np.asarray([[fr] + d for fr, dets in dm.items() for d in dets], np.float64)
+    np.savez_compressed(os.path.join(GOLD, "nms_ref.npz"), logit=lg.numpy(), rows=np.asarray(rows, np.float64), **extra)
     print("golden fixtures written to", GOLD)
     for fn in sorted(os.listdir(GOLD)):
         print(" ", fn, os.path.getsize(os.path.join(GOLD, fn)))

@@ -1,7 +1,7 @@
-"""Torch oracle for the AD-YOLO decode + conn-merge NMS post-processing (TEST INFRASTRUCTURE).
+"""Torch oracle for the AD-YOLO decode + NMS post-processing (TEST INFRASTRUCTURE).
 
 Restates ``/root/reference/src/datasets.py:741-919`` (``LabelPostProcessor.get_yolo_output`` with
-``nms == 'conn-merge'`` and its helper functions) op for op, generalised to a batch of clips and
+its three ``nms`` branches -- 'conn-merge', 'soft-merge', plain -- and its helper functions) op for op, generalised to a batch of clips and
 returning, per (clip, frame), the list ``[[class_idx, x, y, z], ...]`` the reference builds.
 Pinned against the unmodified reference class by ``oracle/make_golden.py`` ->
 ``tests/golden/nms_ref.npz``.
@@ -45,7 +45,8 @@ def _voted(unifying_output, conf_thresh):
 
 class YoloPostOracle:
     def __init__(self, nb_classes=12, grid_size=(45, 45), nb_anchors=5, g_overlap=0.5, conf_thresh=0.5,
-                 clss_thresh=0.5, unify_thresh=15.0, device="cpu"):
+                 clss_thresh=0.5, unify_thresh=15.0, device="cpu", nms="conn-merge"):
+        self.nms = nms
         self.nb_classes, self.nb_anchors, self.g_overlap = nb_classes, nb_anchors, g_overlap
         self.conf_thresh, self.clss_thresh, self.unify_thresh = conf_thresh, clss_thresh, unify_thresh
         self.device = torch.device(device)
@@ -88,6 +89,24 @@ class YoloPostOracle:
                 co = fo[fo[..., 0] == class_idx]
                 if len(co) == 1:
                     det.append(_polar_to_cartesian(co))
+                    continue
+                if self.nms == "soft-merge":               # datasets.py:817-831
+                    ref_out = copy.deepcopy(co)
+                    while co.shape[0]:
+                        D = distance_between_polar_coordinates(co[:1, -2:], ref_out[:, -2:])
+                        det.append(_voted(ref_out[D <= self.unify_thresh], self.clss_thresh))
+                        if len(co) == 1:
+                            break
+                        D = distance_between_polar_coordinates(co[:1, -2:], co[1:, -2:])
+                        co = co[1:][D > self.unify_thresh]
+                    continue
+                if self.nms != "conn-merge":               # datasets.py:834-846 plain NMS
+                    while co.shape[0]:
+                        det.append(_polar_to_cartesian(co[:1]))
+                        if len(co) == 1:
+                            break
+                        D = distance_between_polar_coordinates(co[:1, -2:], co[1:, -2:])
+                        co = co[1:][D > self.unify_thresh]
                     continue
                 D = distance_between_polar_coordinates(co[None, :, -2:].repeat(len(co), 1, 1), co[:, None, -2:].repeat(1, len(co), 1))
                 ref = (D < self.unify_thresh)

@@ -33,15 +33,20 @@ def _compare(got: dict, want: dict, tol=2e-6):
         assert np.abs(g[:, 1:] - w[:, 1:]).max() < tol, fr
 
 
-def test_postprocess_vs_reference_golden(A, gold):
+@pytest.mark.parametrize("nms,key", [("conn-merge", "rows"), ("soft-merge", "rows_soft_merge"), ("nms", "rows_nms")])
+def test_postprocess_vs_reference_golden(A, gold, nms, key):
+    """All three `nms` branches of the unmodified reference LabelPostProcessor (CPU) on the same logits."""
     g = gold("nms_ref.npz")
-    post = A.LabelPostProcessor(_params())
+    p = _params(); p["train_config"]["nms"] = nms
+    post = A.LabelPostProcessor(p)
     got = post.postprocess(torch.from_numpy(g["logit"]).cuda())
     want = {}
-    for r in g["rows"]:
+    for r in g[key]:
         want.setdefault(int(r[0]), []).append(list(r[1:]))
     assert len(want) > 0 and max(len(v) for v in want.values()) >= 2
     _compare(got, want)
+    if nms != "conn-merge":                                   # the modes really differ on this fixture
+        assert len(g[key]) != len(g["rows"]) or not np.allclose(g[key], g["rows"])
 
 
 @pytest.mark.parametrize("C,scale", [(12, 1.5), (13, 2.5), (14, 0.7)])
@@ -51,13 +56,15 @@ def test_postprocess_vs_torch_oracle_on_gpu(A, C, scale):
     logit = torch.randn((2, T, 160 * (C + 3)), device="cuda", generator=gen) * scale
     y = logit.view(2, T, 8, 4, 5, C + 3)
     y[:, :, 1, 2, :, 0] += 4; y[:, :, 1, 2, :, 4] += 4; y[:, ::3, 2, 2, :3, 0] += 4; y[:, ::3, 2, 2, :3, 4] += 4
-    post = A.LabelPostProcessor(_params(C))
-    orc = YoloPostOracle(nb_classes=C, device="cuda")
-    for thr in ((0.5, 0.3) if C == 12 else (0.5,)):
-        post.set_conf_thresh(thr)
-        orc.conf_thresh = orc.clss_thresh = thr
-        for b in range(2):
-            _compare(post.postprocess(logit[b:b + 1]), orc.clip_output(logit[b]))
+    for nms in ("conn-merge", "soft-merge", "nms"):
+        p = _params(C); p["train_config"]["nms"] = nms
+        post = A.LabelPostProcessor(p)
+        orc = YoloPostOracle(nb_classes=C, device="cuda", nms=nms)
+        for thr in ((0.5, 0.3) if C == 12 and nms == "conn-merge" else (0.5,)):
+            post.set_conf_thresh(thr)
+            orc.conf_thresh = orc.clss_thresh = thr
+            for b in range(2):
+                _compare(post.postprocess(logit[b:b + 1]), orc.clip_output(logit[b]))
 
 
 def test_overflow_and_modes(A):
@@ -65,6 +72,10 @@ def test_overflow_and_modes(A):
     big = torch.full((1, 2, 2400), 6.0, device="cuda")
     with pytest.raises(RuntimeError):
         post.get_yolo_output(big, max_det=4)
-    p = _params(); p["train_config"]["nms"] = "soft-merge"
-    with pytest.raises(NotImplementedError):
-        A.LabelPostProcessor(p)
+    import ctypes as C
+    from adyolo_b200 import _lib
+    from adyolo_b200._lib import ptr, stream_ptr
+    det = torch.zeros(2, 4, 4, device="cuda"); cnt = torch.zeros(2, dtype=torch.int32, device="cuda")
+    ov = torch.zeros(1, dtype=torch.int32, device="cuda")
+    rc = _lib.lib().adyolo_yolo_post(ptr(big), 2, C.byref(post.grid.c), 0.5, 0.5, 15.0, 7, 4, ptr(det), ptr(cnt), ptr(ov), stream_ptr())
+    assert rc != 0 and b"nms_mode" in _lib.lib().adyolo_last_error()
