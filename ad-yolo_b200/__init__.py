@@ -22,7 +22,7 @@ from .loss import ADYOLOloss, WrapperCriterion, adyolo_assign  # noqa: F401
 from .scaler import ScalerAccumulator, preprocess_scaler  # noqa: F401
 from .pipeline import HostBatchPipeline, bind_host_to_device  # noqa: F401
 from .postprocess import LabelPostProcessor, yolo_post_batched  # noqa: F401
-from .augment import SpecAug  # noqa: F401
+from .augment import RotationAug, SpecAug  # noqa: F401
 from .data import (ResidentClips, EpochSampler, chunk_plan, features_batched_views,  # noqa: F401
                    load_wav2npy, load_csv2dict)
 

@@ -31,6 +31,25 @@ FOA_GROUPS = ((0, 4), (4, 7))       # [mel W,Y,Z,X | iv Y,Z,X]   datasets.py:158
 MIC_GROUPS = ((0, 4), (4, 10))      # [mel x4 | gcc x6]
 
 
+class RotationAug(object):
+    """Host half of ``augmentations.py:36-111``: same constructor and on/off rule; ``draw`` picks one of
+    the 16 channel-sign / swap combinations per clip with the reference's own call,
+    ``int(random.uniform(0, 16))`` (``:93``), and returns them as the int8 device tensor that
+    ``features_batched(..., rot_comb=)`` and ``label_rows_batched(..., rot_comb=)`` take -- the
+    rotation itself happens inside those kernels (audio channel signs / X<->Y swap folded into the
+    front end, azimuth / elevation transform into the label kernel)."""
+
+    def __init__(self, params: dict, is_valid: bool):
+        self.apply_augment = bool(params["aug_config"]["rotation_augment"]) and not is_valid
+
+    def draw(self, n_clips: int, device) -> torch.Tensor | None:
+        """int8 (n_clips,) combination numbers on ``device``; ``None`` when augmentation is off."""
+        if not self.apply_augment:
+            return None
+        comb = [int(random.uniform(0, 16)) for _ in range(n_clips)]
+        return torch.tensor(comb, dtype=torch.int8).to(device, non_blocking=True)
+
+
 class SpecAug(object):
     """Same constructor and ``augment(spectrogram)`` as the reference class, plus the batched form."""
 

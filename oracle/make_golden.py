@@ -211,6 +211,18 @@ def main():
         ro[f"audio_{c}"] = np.asarray(a2)
         ro[f"events_{c}"] = np.asarray([ev for fr, evs in l2.items() for ev in evs], np.float64)
         ro[f"rows_{c}"] = np.asarray(flp.get_yolo_label(copy.deepcopy(l2), 20), np.float64)
+    # draw sequence of the reference class (comb_no=None -> int(random.uniform(0, 16)), augmentations.py:90-93),
+    # identified by matching the augmented audio against the 16 known outputs
+    import random as _random
+    _random.seed(21)
+    draws = []
+    for _ in range(48):
+        a2, _l2 = rot.augment(snippet.copy(), copy.deepcopy(lab))
+        hit = [c for c in range(16) if np.array_equal(np.asarray(a2), ro[f"audio_{c}"])]
+        assert len(hit) == 1
+        draws.append(hit[0])
+    ro["draw_seed"] = np.int64(21)
+    ro["draws"] = np.asarray(draws, np.int64)
     np.savez_compressed(os.path.join(GOLD, "rotation.npz"), **ro)
     # ---- SpecAug (reference class executed as-is on (C,T,F) tensors of ones; seeded python + torch RNG)
     import random

@@ -66,3 +66,16 @@ def test_specaug_oracle_and_host_draws_match_reference(gold, A):
     random.seed(seed); torch.manual_seed(seed)
     assert not A.SpecAug(params, is_valid=True).draw(n, 200, 64).any()
     assert random.random() == random.Random(seed).random()
+
+
+def test_rotation_draw_sequence_matches_reference(gold, A):
+    """RotationAug.draw consumes python's RNG exactly like the reference class (golden: the
+    combinations the unmodified class picked under random.seed(21))."""
+    import random
+    g = gold("rotation.npz")
+    params = {"aug_config": {"rotation_augment": True}}
+    random.seed(int(g["draw_seed"]))
+    got = A.RotationAug(params, is_valid=False).draw(len(g["draws"]), "cpu")
+    np.testing.assert_array_equal(got.numpy().astype(np.int64), g["draws"])
+    assert len(set(g["draws"].tolist())) > 8
+    assert A.RotationAug(params, is_valid=True).draw(4, "cpu") is None
