@@ -77,6 +77,8 @@ _SIGS = {
     "adyolo_features_foa_rot": (C.c_int, [_P, C.c_int, C.c_int64, C.POINTER(FrontendCfg), _P, _P, _P, _P, _P, C.c_int, _P]),
     "adyolo_features_foa_views": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.POINTER(FrontendCfg), _P, _P, _P, _P, _P, C.c_int, _P]),
     "adyolo_features_mic_logmel": (C.c_int, [_P, C.c_int, C.c_int64, C.POINTER(FrontendCfg), _P, _P, _P, _P, _P, C.c_int, _P]),
+    "adyolo_features_mic_gcc": (C.c_int, [_P, C.c_int, C.c_int64, C.POINTER(FrontendCfg), _P, _P, _P, _P, _P, C.c_int, _P]),
+    "adyolo_mic_spec_bytes": (C.c_size_t, [C.c_int, C.c_int64]),
     "adyolo_features_foa_clamp": (C.c_int, [_P, C.c_int, C.c_int64, C.POINTER(FrontendCfg), _P, _P, _P, _P]),
     "adyolo_stft": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.POINTER(FrontendCfg), _P, _P]),
     "adyolo_logmel_from_stft": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int, C.c_int, C.POINTER(FrontendCfg), _P, _P, _P,

@@ -127,6 +127,22 @@ int adyolo_features_mic_logmel(const int16_t* audio, int B, int64_t N, const ady
                                       (float2*)spec_c64, workspace, (cudaStream_t)stream);
 }
 
+size_t adyolo_mic_spec_bytes(int B, int64_t N) {
+    if (B <= 0 || N < HOP) return 0;
+    return (size_t)B * (size_t)(N / HOP) * NBIN * 4 * sizeof(float2);
+}
+
+int adyolo_features_mic_gcc(const int16_t* audio, int B, int64_t N, const adyolo_frontend_cfg* cfg, const float* mean,
+                            const float* inv_std, float* out, void* spec_c64, void* workspace, int apply_topdb,
+                            void* stream) {
+    int rc = adyolo_features_mic_logmel(audio, B, N, cfg, mean, inv_std, out, spec_c64, workspace, apply_topdb, stream);
+    if (rc) return rc;
+    const long long T = (long long)N / HOP;
+    return launch_gcc_from_stft((const float2*)spec_c64, B, T, mean ? mean + 4 * NMEL : nullptr,
+                                inv_std ? inv_std + 4 * NMEL : nullptr, out + 4 * T * NMEL,
+                                OutStrides{10 * T * NMEL, T * NMEL, NMEL, 1}, (cudaStream_t)stream);
+}
+
 int adyolo_features_foa_clamp(float* out, int B, int64_t N, const adyolo_frontend_cfg* cfg, const float* mean,
                               const float* inv_std, void* workspace, void* stream) {
     int rc = check_frontend_cfg(cfg);

@@ -213,19 +213,13 @@ def features_mic_batched(audio_i16: torch.Tensor, scaler_dev=None, apply_topdb: 
     cfg = _cfg()
     L = _lib.lib()
     with torch.cuda.device(audio_i16.device):
-        spec = torch.empty((B, T, 601, 4), dtype=torch.complex64, device=audio_i16.device)
+        spec = torch.empty(L.adyolo_mic_spec_bytes(B, N), dtype=torch.uint8, device=audio_i16.device)
         out = torch.empty((B, 10, T, 64), dtype=torch.float32, device=audio_i16.device)
         mean, istd = scaler_dev if scaler_dev is not None else (None, None)
         ws = _workspace(L.adyolo_frontend_workspace_bytes(C.byref(cfg), B, N), audio_i16.device)
-        # fused front end: log-mel of the 4 channels + the channel spectra for the GCC kernel
-        check(L.adyolo_features_mic_logmel(ptr(audio_i16), B, N, C.byref(cfg), ptr(mean), ptr(istd), ptr(out), ptr(spec),
-                                           ptr(ws), 1 if apply_topdb else 0, stream_ptr()), "adyolo_features_mic_logmel")
-        st = (C.c_int64 * 4)(10 * T * 64, T * 64, 64, 1)
-        gout = out[:, 4:]
-        gmean = None if mean is None else mean[4:]
-        gistd = None if istd is None else istd[4:]
-        check(L.adyolo_gcc_from_stft(ptr(spec), B, T, C.byref(cfg), ptr(gmean), ptr(gistd),
-                                     C.c_void_p(gout.data_ptr()), st, stream_ptr()), "adyolo_gcc_from_stft")
+        # fused front end (log-mel of the 4 channels + channel spectra) -> tcgen05 GCC-PHAT lag transform
+        check(L.adyolo_features_mic_gcc(ptr(audio_i16), B, N, C.byref(cfg), ptr(mean), ptr(istd), ptr(out), ptr(spec),
+                                        ptr(ws), 1 if apply_topdb else 0, stream_ptr()), "adyolo_features_mic_gcc")
     return out
 
 

@@ -97,6 +97,15 @@ int adyolo_features_mic_logmel(const int16_t* audio, int B, int64_t N, const ady
                                const float* inv_std, float* out, void* spec_c64, void* workspace, int apply_topdb,
                                void* stream);
 
+/* MIC format in one call: adyolo_features_mic_logmel followed by adyolo_gcc_from_stft on the same
+ * stream.  out (B, 10, T, 64) = 4 log-mel + 6 GCC-PHAT (64 lags, pairs (0,1) (0,2) (0,3) (1,2) (1,3)
+ * (2,3)); mean / inv_std: device (10, 64) or NULL; spec_c64: caller-owned scratch of
+ * adyolo_mic_spec_bytes(B, N) bytes (the channel spectra travel through it).                     */
+size_t adyolo_mic_spec_bytes(int B, int64_t N);
+int adyolo_features_mic_gcc(const int16_t* audio, int B, int64_t N, const adyolo_frontend_cfg* cfg, const float* mean,
+                            const float* inv_std, float* out, void* spec_c64, void* workspace, int apply_topdb,
+                            void* stream);
+
 /* Un-fused stages behind the reference's per-function surface (they materialise the STFT):
  *
  * adyolo_stft  — utility.audio2stft (utility.py:142-165) == get_stft_spectrogram (datasets.py:252-258)
