@@ -300,3 +300,31 @@ def test_specaug_masks_on_device(A, scaler2021):
     got = sa.apply_rects(x.clone(), rr, groups=((0, 4), (4, 10))).cpu().numpy()
     np.testing.assert_array_equal(got, augment_np.specaug_apply(x.cpu().numpy(), np.clip(rr.numpy(), 0, None), groups=((0, 4), (4, 10))))
     assert A.SpecAug(params, is_valid=True).augment_batched(feat) is feat
+
+
+def test_long_clips_batch_equals_per_clip_and_oracle(A, scaler2021):
+    """60-s clips (BASELINE config[0] length) in a batch: every clip equals its single-clip result
+    bit for bit (no cross-clip leakage; 2400 frames per clip = 800 front-end tiles, 37.5 GCC tiles so
+    GCC tiles straddle clip boundaries), and one clip is checked against the float64 oracle."""
+    from adyolo_b200.features import features_mic_batched
+    rng = np.random.default_rng(33)
+    B, N = 3, 24000 * 60
+    x = rng.standard_normal((B, N, 4)) * 1500
+    x[:, :, 1:] += x[:, :, :1] * 0.5
+    x[1, 300000:340000] = 0
+    audio = torch.from_numpy(np.clip(x, -32768, 32767).astype(np.int16)).cuda()
+    sd = _scaler_dev(A, scaler2021)
+    out = A.features_batched(audio, sd)
+    assert out.shape == (B, 7, 2400, 64)
+    for b in range(B):
+        assert torch.equal(A.features_batched(audio[b:b + 1], sd)[0], out[b])
+    ref = F.features_foa_stack(audio[1].cpu().numpy(), scaler=scaler2021)
+    o = out[1].cpu().numpy()
+    assert _mel_err(o[:4], ref[:4]) < 1e-4 and np.abs(o[4:] - ref[4:]).max() < 1e-3
+    mic = features_mic_batched(audio)
+    assert mic.shape == (B, 10, 2400, 64) and bool(torch.isfinite(mic).all())
+    for b in range(B):
+        assert torch.equal(features_mic_batched(audio[b:b + 1])[0], mic[b])
+    refm = F.features_mic_stack(audio[2].cpu().numpy())
+    m = mic[2].cpu().numpy()
+    assert _mel_err(m[:4], refm[:4]) < 1e-4 and np.abs(m[4:] - refm[4:]).max() < 1e-3
