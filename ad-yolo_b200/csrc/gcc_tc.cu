@@ -8,22 +8,28 @@
 // B[2k][l] = c_k cos(2 pi k l/N), B[2k+1][l] = -c_k sin(2 pi k l/N)  (c_0 = c_600 = 1/2, else 1;
 // the common factor 2/N is applied in FP32 in the epilogue so that lag 0 is exact in TF32).
 //
-// One CTA = 64 frames = 384 items (row = pair * 64 + frame) = 3 UMMA M-tiles of 128 rows, N = 64
-// lags, K = 1216 (608 bins).  Per chunk of 16 bins (K = 32):
-//   - all threads take the 4 channel spectra of (64 frames x 16 bins) from registers (loaded one
-//     chunk ahead), normalise each channel to unit modulus, form the 6 cross spectra and store them
-//     as the A operand in shared memory in the canonical K-major, no-swizzle UMMA layout (core
-//     matrix = 8 rows x 16 bytes); the B chunk (8 KB, precomputed in that layout) arrives by cp.async
-//   - fence.proxy.async + barrier; one thread issues 4 (k-steps) x 3 (M-tiles) tcgen05.mma and a
-//     tcgen05.commit on the stage's mbarrier.  Two stages: chunk c+1 is generated while the tensor
+// One CTA = 64 frames = 384 items = 3 UMMA M-tiles of 128 rows (tile = pair / 2, row = 2 frame +
+// (pair & 1)), N = 64 lags, K = 1216 (608 bins), 2 CTAs per SM.  Per chunk of 8 bins (K = 16):
+//   - cp.async stages the raw spectra two chunks ahead (3 stages); every thread copies exactly the
+//     16-byte pieces (channel pair x bin x frame) it later consumes, so they need no barrier
+//   - a lane normalises its two channels to unit modulus (one rsqrt.approx each; rare slow path for
+//     |x|^2 outside the FP32 range or zero), swaps them with its partner lane (the other two channels
+//     of the same bin) and forms three of the six cross spectra; they are rounded to TF32 and stored as
+//     the A operand in the canonical K-major, no-swizzle UMMA layout (core matrix = 8 rows x 16 bytes).
+//     The k-chunk pitch is skewed by 32 bytes and the two lanes of a bin always store pairs of opposite
+//     row parity, so the 16 stores of a half-warp hit 16 distinct 8-byte slots
+//   - the B chunk (4 KB, precomputed in the same layout) arrives by cp.async as well
+//   - fence.proxy.async + barrier; one thread issues 2 (k-steps) x 3 (M-tiles) tcgen05.mma and a
+//     tcgen05.commit on the A stage's mbarrier.  Two A stages: chunk c+1 is generated while the tensor
 //     core consumes chunk c; a stage is only waited for when it is about to be overwritten
-// Epilogue: all 8 warps tcgen05.ld (32x32b.x32) a 32-item x 32-lag block each, stage it through
+// Epilogue: all 8 warps tcgen05.ld (32x32b.x32) a 32-row x 32-lag block each, stage it through
 // shared memory and store standardised 128-byte row segments.
 // The MMA truncates FP32 operands to TF32, which biases a coherent peak low by ~6e-4; both operands
 // are therefore rounded to nearest first: measured max error 2.9e-5 absolute against the float64
 // oracle (gate 1e-3); all-(1,0) cross spectra (digital silence) give cc[0] = 1 exactly.
-// B200, 128 x 5-s clips: 0.57 ms (CUDA-core kernel this replaces) -> 0.22-0.24 ms; at 512 clips the
-// kernel streams the 1.97 GB of spectra at 2.7 TB/s (profiles/r01_ncu_gcc_tc.txt).
+// B200 (same box, CUDA events): 128 x 5-s clips 0.57 ms (CUDA-core kernel this replaces) -> 0.19 ms;
+// 512 clips: 0.775 ms with a one-chunk register prefetch -> 0.606 ms = 3.5 TB/s of spectra + output
+// (profiles/r01_ncu_gcc_tc.txt).
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -43,13 +49,24 @@ struct OutStrides {
 
 constexpr int GT_FRAMES = 64;                 // frames per CTA
 constexpr int GT_ITEMS = GT_FRAMES * 6;       // 384 rows = 3 M-tiles; row = pair * 64 + frame
-constexpr int GT_BINS = 16;                   // bins per chunk -> K = 32 per chunk
-constexpr int GT_CHUNKS = 38;                 // 608 bins >= 601
+constexpr int GT_BINS = 8;                    // bins per chunk -> K = 16 per chunk (2 MMA k-steps)
+constexpr int GT_CHUNKS = 76;                 // 608 bins >= 601
 constexpr int GT_THREADS = 256;
-constexpr int GT_STAGES = 2;
-constexpr int GT_A_BYTES = (GT_BINS * 2 / 4) * (GT_ITEMS / 8) * 128;   // 8 k-chunks x 48 m-groups x 128 B = 49152
-constexpr int GT_B_BYTES = (GT_BINS * 2 / 4) * (64 / 8) * 128;         // 8 x 8 x 128 = 8192
-constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;                // 56 KB
+constexpr int GT_STAGES = 2;                  // A-operand stages (generation of chunk c+1 overlaps the MMAs of chunk c)
+constexpr int GT_KCH = GT_BINS * 2 / 4;       // 16-byte k-chunks per stage (4)
+// A operand: k-chunk pitch (= LBO) padded by 32 B so that the 4 k-chunks a warp stores at once fall
+// into different bank groups (the stores of a warp then need the minimum of two wavefronts)
+constexpr int GT_A_LBO = (GT_ITEMS / 8) * 128 + 32;                    // 6176
+constexpr int GT_A_BYTES = GT_KCH * GT_A_LBO;                          // 24704
+constexpr int GT_B_LBO = (64 / 8) * 128;                               // 1024
+constexpr int GT_B_BYTES = GT_KCH * GT_B_LBO;                          // 4096
+constexpr int GT_B_SLOTS = 4;                 // B chunk c+2 is copied while the MMAs of chunk c-1 may still read theirs
+constexpr int GT_RAW_STAGES = 3;              // raw spectra: chunks c+1 and c+2 in flight while chunk c is consumed
+constexpr int GT_RAW_BYTES = GT_FRAMES * GT_BINS * 32;                 // 16384
+constexpr int GT_PIECES = GT_RAW_BYTES / 16 / GT_THREADS;              // 16-byte pieces per thread and chunk (4)
+constexpr int GT_OFF_B = GT_STAGES * GT_A_BYTES;
+constexpr int GT_OFF_RAW = GT_OFF_B + GT_B_SLOTS * GT_B_BYTES;
+constexpr int GT_SMEM = GT_OFF_RAW + GT_RAW_STAGES * GT_RAW_BYTES;     // 114944 B: two CTAs per SM
 constexpr uint32_t GT_TMEM_COLS = 256;        // 3 x 64 fp32 columns, power of two
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -101,35 +118,48 @@ __device__ __forceinline__ float2 unit(float2 a, bool& zero) {
     return make_float2(re * r, im * r);
 }
 
-struct SpecRegs {
-    float4 v01[4], v23[4];
-};
+// Piece ownership: piece q = tid + 256 j of a chunk is (frame q / 16, bin (q % 16) / 2, channel half
+// q % 2), i.e. consecutive lanes copy consecutive 16-byte pieces (one frame's 8 bins x 4 channels are
+// 256 contiguous bytes) and consume exactly what they copied; the partner holding the other two
+// channels of the same (frame, bin) is lane ^ 1.
+__device__ __forceinline__ int gt_half(int tid) { return tid & 1; }
+__device__ __forceinline__ int gt_kb(int tid) { return (tid & 15) >> 1; }
+__device__ __forceinline__ int gt_frame(int tid, int j) { return (tid + GT_THREADS * j) >> 4; }
 
-__device__ __forceinline__ void load_chunk(SpecRegs& R, const float2* __restrict__ spec, long long f0, long long n_frames,
-                                           int ch, int warp, int f_lo, int kb_lo) {
+// Asynchronous staging of one chunk: every thread copies the GT_PIECES 16-byte pieces (one channel
+// pair of one bin of one frame) that it will itself consume, so the raw data need no barrier at
+// all (cp.async.wait_group only), plus one piece of the B operand chunk.  Pieces past the last frame / bin 600 are zero-filled (src-size 0).
+__device__ __forceinline__ void issue_chunk_copy(unsigned char* smem, const float2* __restrict__ spec, const float* __restrict__ btab,
+                                                 long long f0, long long n_frames, int ch, int tid) {
+    if (ch < GT_CHUNKS) {
+        const uint32_t raw = smem_u32(smem + GT_OFF_RAW + (ch % GT_RAW_STAGES) * GT_RAW_BYTES) + tid * 16;
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int combo = it * 8 + warp, f = (combo & 3) * 16 + f_lo, kb = (combo >> 2) * 2 + kb_lo;
-        const int bin = ch * GT_BINS + kb;
-        const long long fr = f0 + f;
-        R.v01[it] = R.v23[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (fr < n_frames && bin < NBIN) {
-            const float4* s = reinterpret_cast<const float4*>(spec + (fr * NBIN + bin) * 4);
-            R.v01[it] = __ldg(s);
-            R.v23[it] = __ldg(s + 1);
+        for (int j = 0; j < GT_PIECES; ++j) {
+            const int f = gt_frame(tid, j), bin = ch * GT_BINS + gt_kb(tid);
+            const long long fr = f0 + f;
+            const bool live = fr < n_frames && bin < NBIN;
+            const float2* src = live ? spec + (fr * NBIN + bin) * 4 + gt_half(tid) * 2 : spec;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(raw + j * (GT_THREADS * 16)), "l"(src), "r"(live ? 16 : 0) : "memory");
         }
+        const uint32_t d = smem_u32(smem + GT_OFF_B + (ch % GT_B_SLOTS) * GT_B_BYTES) + tid * 16;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(btab + (size_t)ch * (GT_B_BYTES / 4) + tid * 4) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(GT_THREADS, 2)
 gcc_tc_kernel(const float2* __restrict__ spec, long long n_frames, int T, const float* __restrict__ btab,
               const float* __restrict__ mean, const float* __restrict__ istd, float* __restrict__ out, OutStrides os) {
-    extern __shared__ __align__(128) unsigned char smem[];      // GT_STAGES x (A 48 KB | B 8 KB)
+    extern __shared__ __align__(128) unsigned char smem[];      // A x2 | B x4 | raw x3
     __shared__ __align__(8) unsigned long long mbar[GT_STAGES];
     __shared__ uint32_t tmem_base_s;
+    static_assert(GT_B_BYTES == GT_THREADS * 16, "one 16-byte B piece per thread");
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long f0 = (long long)blockIdx.x * GT_FRAMES;
+
+    issue_chunk_copy(smem, spec, btab, f0, n_frames, 0, tid);
+    issue_chunk_copy(smem, spec, btab, f0, n_frames, 1, tid);
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(GT_TMEM_COLS));
@@ -145,72 +175,73 @@ gcc_tc_kernel(const float2* __restrict__ spec, long long n_frames, int T, const 
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = tmem_base_s;
 
-    // generation mapping: lane = (frame low 4 bits, bin parity); (warp, iteration) = (frame group, bin pair).
-    // Rows are pair-major, so the 16 frames of a warp store 16 consecutive 16-byte rows: conflict-free.
-    const int kb_lo = lane & 1, f_lo = lane >> 1;
+    const int half = gt_half(tid), kb = gt_kb(tid);
 
-    SpecRegs cur;
-    load_chunk(cur, spec, f0, n_frames, 0, warp, f_lo, kb_lo);
     for (int ch = 0; ch < GT_CHUNKS; ++ch) {
         const int stg = ch & (GT_STAGES - 1);
-        unsigned char* sA = smem + stg * GT_STAGE_BYTES;
-        unsigned char* sB = sA + GT_A_BYTES;
+        unsigned char* sA = smem + stg * GT_A_BYTES;
+        // A stage (and the B slot chunk ch+2 is about to overwrite) free once the MMAs of chunk ch-2 are done
         if (ch >= GT_STAGES) mbar_wait(smem_u32(&mbar[stg]), (uint32_t)(((ch - GT_STAGES) / GT_STAGES) & 1));
+        issue_chunk_copy(smem, spec, btab, f0, n_frames, ch + 2, tid);
+        asm volatile("cp.async.wait_group 2;" ::: "memory");            // this thread's pieces of chunk ch have landed
 
-        {   // B chunk (canonical layout, TF32-rounded on the host): asynchronous copy, 2 x 16 B per thread
-            const float4* src = reinterpret_cast<const float4*>(btab + (size_t)ch * (GT_B_BYTES / 4));
-            const uint32_t d = smem_u32(sB) + tid * 16;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + tid) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + GT_THREADS * 16), "l"(src + tid + GT_THREADS) : "memory");
-        }
-        SpecRegs nxt;                                      // next chunk's spectra are in flight during this chunk's math
-        if (ch + 1 < GT_CHUNKS) load_chunk(nxt, spec, f0, n_frames, ch + 1, warp, f_lo, kb_lo);
+        const float4* raw = reinterpret_cast<const float4*>(smem + GT_OFF_RAW + (ch % GT_RAW_STAGES) * GT_RAW_BYTES) + tid;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int combo = it * 8 + warp, f = (combo & 3) * 16 + f_lo, kb = (combo >> 2) * 2 + kb_lo;
-            const float2 x[4] = {make_float2(cur.v01[it].x, cur.v01[it].y), make_float2(cur.v01[it].z, cur.v01[it].w),
-                                 make_float2(cur.v23[it].x, cur.v23[it].y), make_float2(cur.v23[it].z, cur.v23[it].w)};
-            // fast path: |x|^2 comfortably inside the FP32 range for all four channels
-            float2 u[4];
-            bool ok = true;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const float sq = fmaf(x[c].x, x[c].x, x[c].y * x[c].y);
-                ok = ok && sq > 1e-30f && sq < 1e30f;
-                const float r = rsqrt_ftz(sq);
-                u[c] = make_float2(x[c].x * r, x[c].y * r);
+        for (int j = 0; j < GT_PIECES; ++j) {
+            const int f = gt_frame(tid, j);
+            const float4 v = raw[j * GT_THREADS];
+            // this lane's two channels (2 half, 2 half + 1) -> unit modulus
+            float2 ua = make_float2(v.x, v.y), ub = make_float2(v.z, v.w);
+            const float sa = fmaf(ua.x, ua.x, ua.y * ua.y), sb = fmaf(ub.x, ub.x, ub.y * ub.y);
+            unsigned zbits = 0;
+            if (sa > 1e-30f && sa < 1e30f && sb > 1e-30f && sb < 1e30f) {
+                const float ra = rsqrt_ftz(sa), rb = rsqrt_ftz(sb);
+                ua.x *= ra; ua.y *= ra; ub.x *= rb; ub.y *= rb;
+            } else {   // rare: silence, padding, extreme magnitudes, NaN
+                bool za, zb;
+                ua = unit(ua, za); ub = unit(ub, zb);
+                zbits = (za ? 1u : 0u) | (zb ? 2u : 0u);
             }
-            bool z[4] = {false, false, false, false};
-            if (!ok) {   // rare: silence, padding (rows / bins past the end load zeros), extreme magnitudes, NaN
-#pragma unroll
-                for (int c = 0; c < 4; ++c) u[c] = unit(x[c], z[c]);
+            // the partner lane holds the other two channels of the same (frame, bin)
+            const float2 oa = make_float2(__shfl_xor_sync(0xffffffffu, ua.x, 1), __shfl_xor_sync(0xffffffffu, ua.y, 1));
+            const float2 ob = make_float2(__shfl_xor_sync(0xffffffffu, ub.x, 1), __shfl_xor_sync(0xffffffffu, ub.y, 1));
+            const unsigned zo = __shfl_xor_sync(0xffffffffu, zbits, 1);
+            // even lane (channels 0,1): pairs (0,1) (0,2) (0,3) = p 0, 1, 2 = conj(ua) ub, conj(ua) oa, conj(ua) ob
+            // odd lane  (channels 2,3): pairs (2,3) (1,3) (1,2) = p 5, 4, 3 = conj(ua) ub, conj(ob) ub, conj(ob) ua
+            // (in this order the two lanes of a (frame, bin) always store pairs of opposite parity, see below)
+            const float2 X = half ? ob : ua, Y1 = half ? ub : oa, Y2 = half ? ua : ob;
+            const bool zX = half ? (zo & 2u) : (zbits & 1u), zY1 = half ? (zbits & 2u) : (zo & 1u), zY2 = half ? (zbits & 1u) : (zo & 2u);
+            float2 P0 = make_float2(ua.x * ub.x + ua.y * ub.y, ua.x * ub.y - ua.y * ub.x);
+            float2 P1 = make_float2(X.x * Y1.x + X.y * Y1.y, X.x * Y1.y - X.y * Y1.x);
+            float2 P2 = make_float2(X.x * Y2.x + X.y * Y2.y, X.x * Y2.y - X.y * Y2.x);
+            if (zbits | zo) {
+                if (zbits) P0 = make_float2(1.f, 0.f);
+                if (zX || zY1) P1 = make_float2(1.f, 0.f);
+                if (zX || zY2) P2 = make_float2(1.f, 0.f);
             }
-            // canonical layout: [k-chunk = kb/2][m-group = row/8] core matrices of 8 rows x 16 B
-            unsigned char* dst = sA + ((kb >> 1) * (GT_ITEMS / 8) + (f >> 3)) * 128 + (f & 7) * 16 + (kb & 1) * 8;
-            int p = 0;
-#pragma unroll
-            for (int m = 0; m < 4; ++m)
-#pragma unroll
-                for (int n = m + 1; n < 4; ++n) {
-                    float re = u[m].x * u[n].x + u[m].y * u[n].y, im = u[m].x * u[n].y - u[m].y * u[n].x;   // conj(u_m) u_n
-                    if (!ok && (z[m] || z[n])) { re = 1.f; im = 0.f; }
-                    *reinterpret_cast<float2*>(dst + p * (GT_FRAMES / 8) * 128) = make_float2(tf32_rn_bits(re), tf32_rn_bits(im));   // row = p * 64 + f
-                    ++p;
-                }
+            // canonical K-major layout: [k-chunk = kb/2][m-group = row/8] core matrices of 8 rows x 16 B.
+            // M-tile = p / 2, row in the tile = 2 f + (p & 1): 64-bit stores are served per half-warp (one frame:
+            // 8 bins x 2 channel halves); the two halves store pairs of opposite parity = adjacent rows, so with
+            // the 32-byte k-chunk skew the 16 lanes hit 16 distinct 8-byte slots.
+            const int r0 = 2 * f + half, r1 = 2 * f + 1 - half;            // rows of (p0) and of (p1, p2)
+            unsigned char* d0 = sA + (kb >> 1) * GT_A_LBO + (kb & 1) * 8 + (r0 >> 3) * 128 + (r0 & 7) * 16;
+            unsigned char* d1 = sA + (kb >> 1) * GT_A_LBO + (kb & 1) * 8 + (r1 >> 3) * 128 + (r1 & 7) * 16;
+            // tiles: p0 = 0 | 5 -> tile 0 | 2;  p1 = 1 | 4 -> tile 0 | 2;  p2 = 2 | 3 -> tile 1 | 1
+            *reinterpret_cast<float2*>(d0 + (half ? 2 : 0) * 2048) = make_float2(tf32_rn_bits(P0.x), tf32_rn_bits(P0.y));
+            *reinterpret_cast<float2*>(d1 + (half ? 2 : 0) * 2048) = make_float2(tf32_rn_bits(P1.x), tf32_rn_bits(P1.y));
+            *reinterpret_cast<float2*>(d0 + 2048) = make_float2(tf32_rn_bits(P2.x), tf32_rn_bits(P2.y));
         }
-        cur = nxt;
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy / cp.async writes -> async proxy (UMMA)
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(smem + GT_OFF_B + (ch % GT_B_SLOTS) * GT_B_BYTES);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {                            // K = 8 per MMA = 2 k-chunks
-                const uint64_t bd = umma_desc(b0 + ks * 2 * (64 / 8) * 128, (64 / 8) * 128, 128);
+            for (int ks = 0; ks < GT_KCH / 2; ++ks) {                   // K = 8 per MMA = 2 k-chunks
+                const uint64_t bd = umma_desc(b0 + ks * 2 * GT_B_LBO, GT_B_LBO, 128);
 #pragma unroll
                 for (int mt = 0; mt < 3; ++mt) {
-                    const uint64_t ad = umma_desc(a0 + ks * 2 * (GT_ITEMS / 8) * 128 + mt * 16 * 128, (GT_ITEMS / 8) * 128, 128);
+                    const uint64_t ad = umma_desc(a0 + ks * 2 * GT_A_LBO + mt * 16 * 128, GT_A_LBO, 128);
                     const uint32_t acc = (ch | ks) ? 1u : 0u;           // first MMA overwrites the accumulator
                     asm volatile(
                         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -221,26 +252,30 @@ gcc_tc_kernel(const float2* __restrict__ spec, long long n_frames, int T, const 
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar[stg])) : "memory");
         }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     // the last commit covers every MMA issued before it
     mbar_wait(smem_u32(&mbar[(GT_CHUNKS - 1) & (GT_STAGES - 1)]), (uint32_t)(((GT_CHUNKS - 1) / GT_STAGES) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;");
 
     // ---- epilogue.  A warp may read TMEM lanes 32 (w % 4) .. +31: warps w and w + 4 share a lane
-    // quarter and split the 64 lag columns.  TMEM lane = row of the M-tile = pair (mt*2 + q/2), frame
-    // (q & 1) * 32 + lane.  Natural output layout: the 32 x 32 block goes through shared memory so
-    // that global stores are 128-byte row segments; any other stride set is stored directly.
+    // quarter and split the 64 lag columns.  TMEM lane = row of the M-tile = 2 * frame + (pair & 1),
+    // pair = 2 * tile + (row & 1): a quarter holds 16 frames x the tile's two pairs.  Natural output
+    // layout: the 32 x 32 block goes through shared memory so that global stores are 128-byte row
+    // segments; any other stride set is stored directly.
     {
         constexpr float kScale = 2.0f / NFFT;               // B holds cos / -sin (x 1/2 at bins 0 and 600): exact at lag 0
         const int q = warp & 3, h = warp >> 2;
         const bool vec = os.sj == 1 && ((os.sb | os.sc | os.st) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
         float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);      // 32 rows, 144-byte pitch: conflict-free
-        long long off[8];                                                     // vec: this lane's 8 (row, 16-byte column) targets
+        // vec: this lane's 8 (row, 16-byte column) targets, row = 4 it + lane / 8; otherwise row = lane
+        const int pp = vec ? (lane >> 3) & 1 : lane & 1;                       // pair parity of the lane's row(s)
+        long long off[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-            const int f = (q & 1) * 32 + (vec ? 4 * it + (lane >> 3) : lane);
-            const long long fr = f0 + f;
+            const int row = vec ? 4 * it + (lane >> 3) : lane;
+            const long long fr = f0 + 16 * q + (row >> 1);
             const long long b = fr / T;
-            off[it] = fr < n_frames ? b * os.sb + (fr - b * T) * os.st + (vec ? h * 32 + (lane & 7) * 4 : 0) : -1;
+            off[it] = fr < n_frames ? b * os.sb + (fr - b * T) * os.st + pp * os.sc + (vec ? h * 32 + (lane & 7) * 4 : 0) : -1;
         }
 #pragma unroll 1
         for (int mt = 0; mt < 3; ++mt) {
@@ -251,7 +286,7 @@ gcc_tc_kernel(const float2* __restrict__ spec, long long n_frames, int T, const 
                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int p = mt * 2 + (q >> 1);
+            const int p = mt * 2 + pp;
             const float* mu = mean ? mean + p * NMEL + h * 32 : nullptr;
             const float* is = istd ? istd + p * NMEL + h * 32 : nullptr;
             if (vec) {
@@ -268,11 +303,11 @@ gcc_tc_kernel(const float2* __restrict__ spec, long long n_frames, int T, const 
                     float4 v = *reinterpret_cast<const float4*>(stage + (4 * it + (lane >> 3)) * 36 + c4);
                     v.x = (v.x * kScale - m4.x) * i4.x; v.y = (v.y * kScale - m4.y) * i4.y;
                     v.z = (v.z * kScale - m4.z) * i4.z; v.w = (v.w * kScale - m4.w) * i4.w;
-                    if (off[it] >= 0) *reinterpret_cast<float4*>(out + off[it] + p * os.sc) = v;
+                    if (off[it] >= 0) *reinterpret_cast<float4*>(out + off[it] + (2 * mt) * os.sc) = v;
                 }
                 __syncwarp();
             } else if (off[0] >= 0) {
-                float* o = out + off[0] + p * os.sc + (long long)(h * 32) * os.sj;
+                float* o = out + off[0] + (2 * mt) * os.sc + (long long)(h * 32) * os.sj;
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     o[j * os.sj] = (__uint_as_float(r[j]) * kScale - (mu ? mu[j] : 0.f)) * (is ? is[j] : 1.f);
@@ -284,7 +319,7 @@ gcc_tc_kernel(const float2* __restrict__ spec, long long n_frames, int T, const 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(GT_TMEM_COLS));
 }
 
-// B operand table: [38 chunks][8 k-chunks][8 lag-groups][8 lags][4 k'] floats (canonical K-major layout)
+// B operand table: [GT_CHUNKS][GT_KCH k-chunks][8 lag-groups][8 lags][4 k'] floats (canonical K-major layout)
 static int get_gcc_btab(const float** dev_tab) {
     static std::mutex mu;
     static float* cache[64] = {nullptr};
@@ -295,7 +330,7 @@ static int get_gcc_btab(const float** dev_tab) {
     if (!cache[dev]) {
         std::vector<float> h((size_t)GT_CHUNKS * GT_B_BYTES / 4, 0.f);
         for (int ch = 0; ch < GT_CHUNKS; ++ch)
-            for (int kp = 0; kp < 32; ++kp) {                     // k' within the chunk
+            for (int kp = 0; kp < 2 * GT_BINS; ++kp) {            // k' within the chunk
                 const int bin = ch * GT_BINS + (kp >> 1);
                 if (bin >= NBIN) continue;
                 const double ck = (bin == 0 || bin == 600) ? 0.5 : 1.0;    // x 2/N in the epilogue
@@ -304,6 +339,7 @@ static int get_gcc_btab(const float** dev_tab) {
                     const double ang = 2.0 * M_PI * (double)((bin * (long long)((lag + NFFT) % NFFT)) % NFFT) / NFFT;
                     const double v = (kp & 1) ? -ck * sin(ang) : ck * cos(ang);
                     const size_t off = (size_t)ch * (GT_B_BYTES / 4) + ((size_t)(kp >> 2) * 8 + (n >> 3)) * 32 + (n & 7) * 4 + (kp & 3);
+                    static_assert(GT_B_LBO == 8 * 128, "B k-chunk pitch");
                     float fv = (float)v;                          // round to TF32 (nearest, ties away) like cvt.rna
                     uint32_t u;
                     memcpy(&u, &fv, 4);
@@ -332,7 +368,7 @@ int launch_gcc_from_stft(const float2* spec, int B, long long T, const float* me
     static int configured_dev = -1;
     int dev = 0;
     ADY_CUDA_CHECK(cudaGetDevice(&dev));
-    const int shmem = GT_STAGES * GT_STAGE_BYTES;
+    const int shmem = GT_SMEM;
     if (configured_dev != dev) {
         ADY_CUDA_CHECK(cudaFuncSetAttribute(gcc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, shmem));
         configured_dev = dev;
