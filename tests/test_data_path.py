@@ -93,3 +93,10 @@ def test_view_features_equal_materialised_chunks(A, gold, scaler2021):
     assert torch.equal(via_views, A.features_batched(dense, sd, rot_comb=rot))
     rows = A.label_rows_batched(events, nlf, A.labels.GridSpec(12, 5, [45, 45], 0.5), rot_comb=rot)
     assert rows.shape[1] == 7 and rows.shape[0] > 0
+
+
+def test_cpulist_parser_for_numa_binding(A):
+    from adyolo_b200.pipeline import _parse_cpulist
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("") == set()
+    assert _parse_cpulist("5") == {5}
