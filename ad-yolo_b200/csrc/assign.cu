@@ -12,11 +12,13 @@
 // kernels call (tanhf, sinf, cosf, acosf, expf).  Everything downstream of the masks (BCE sums,
 // gradients) only has to match to ~1e-5 and is accumulated in FP64.
 //
-// Three launches per call, no host synchronisation:
+// Launches per call, no host synchronisation:
 //   assign_rows_kernel  : 1 thread / target row  -> D, masks, argmin; atomicOr label bits into a
 //                         per-anchor 64-bit state word; unnormalised angular gradients
-//   loss_anchor_kernel  : element-wise float4 pass over the logits -> BCE sums and/or d loss/d logit
+//   loss_weights_kernel : normalisers of the means from the final positive counts
+//   loss_anchor_kernel  : warp-autonomous pass over the anchors -> BCE sums and (when asked) d loss/d logit
 //   loss_finalize_kernel: scalar loss
+//   grad_scale_kernel   : backward of the autograd wrapper: grad *= grad_output unless it is exactly 1
 #include "assign_host.h"
 #include "common.cuh"
 
