@@ -1,4 +1,5 @@
-"""Validate the tcgen05 GCC-PHAT kernel against the CUDA-core one and the numpy oracle; time both."""
+"""GCC-PHAT tensor-core kernel: check against the numpy oracle, time the MIC pipeline and the kernel alone
+(GT_B = clips, default 128); `python tools/prof_gcc.py tc` is the ncu target used for profiles/r01_ncu_gcc_tc.txt."""
 import os, sys, subprocess, json
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
