@@ -113,23 +113,47 @@ def run_cpu_baseline(steps, warmup, sample_clips=None):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons sampled DURING the timed region.  In-process NVML (pynvml, the data
+    source nvidia-smi prints) every 10 ms, so that even a ~100 ms timed region yields a real median;
+    falls back to spawning nvidia-smi (one sample per ~0.3 s) when pynvml is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, pci_bus_id=None):
         super().__init__(daemon=True)
         self.gpu, self.samples, self._stop_evt = gpu_index, [], threading.Event()
+        self.nv = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = (pynvml.nvmlDeviceGetHandleByPciBusId(pci_bus_id.encode()) if pci_bus_id
+                           else pynvml.nvmlDeviceGetHandleByIndex(gpu_index))
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nv = pynvml
+        except Exception:
+            self.nv = self.handle = None
+
+    def _sample_nvml(self):
+        nv = self.nv
+        sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        r = int(get(self.handle))
+        flag = lambda bit: "Active" if r & bit else "Not Active"   # noqa: E731  (NVML reason bits)
+        self.samples.append([str(self.gpu), str(sm), str(self.max_sm), "", "", flag(0x8), flag(0x40), flag(0x20), flag(0x4)])
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self.nv is not None:
+                    self._sample_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.01 if self.nv is not None else 0.2)
 
     def stop(self):
         self._stop_evt.set()
@@ -143,7 +167,7 @@ class ClockSampler(threading.Thread):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+                "reasons": sorted(reasons), "samples": len(self.samples), "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------ ours
@@ -205,7 +229,12 @@ def main_ours(args):
     for _ in range(args.warmup):
         step(audio_d, events_d)
     barrier()
-    sampler = ClockSampler(local_rank)
+    props = torch.cuda.get_device_properties(dev)
+    try:
+        pci = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+    except AttributeError:
+        pci = None
+    sampler = ClockSampler(local_rank, pci)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
