@@ -16,6 +16,11 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
 
+# build knob (see csrc/frontend_core.cuh): frames per front-end tile, 3 (default) or 7
+if os.environ.get("ADY_TILE_FRAMES"):
+    NVCC_FLAGS = NVCC_FLAGS + ["-DADY_TILE_FRAMES=" + os.environ["ADY_TILE_FRAMES"]]
+
+
 def _nvcc():
     for p in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
         if p and (os.path.isabs(p) and os.path.exists(p) or not os.path.isabs(p)):

@@ -32,6 +32,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void issue_tile_copy(uint32_t* samples, const int16_t* __restrict__ audio,
                                                 long long clip_base, int t0, int nf) {
     const int tid = threadIdx.x;
+    if (tid >= COPY_THREADS) return;
     // element (idx = i0 + 80 i, pair), i = 0..14: lanes 0-15 of a warp copy the (W,Y) words of 16
     // consecutive samples, lanes 16-31 the (Z,X) words of the same samples (one 128-byte line)
     const int pair = (tid >> 4) & 1, i0 = (tid >> 5) * 16 + (tid & 15);
@@ -63,7 +64,7 @@ __device__ __forceinline__ void issue_tile_copy(uint32_t* samples, const int16_t
 //       channel spectra written to `spec` (B, T, 601, 4) complex64 for the GCC-PHAT kernel; no
 //       intensity vectors (ROT must be false).
 template <bool ROT, bool VIEW, bool MIC>
-__global__ void __launch_bounds__(NTHREADS, 2)
+__global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM)
 frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_per_clip, int ntiles,
                     const FrontendTables* __restrict__ tab, const float* __restrict__ mean,
                     const float* __restrict__ istd, float dc0, float dc1, const int8_t* __restrict__ rot,
@@ -94,9 +95,9 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
 
     // fixed roles
     const int q1 = tid / 25, n2 = tid - 25 * q1;             // stage 1 (tid < 150): lane group q1 -> fft g_of_q(q1)
-    const int f1 = q1 < 3 ? q1 : q1 - 3;                     // its frame
+    const int f1 = q1 < TF ? q1 : q1 - TF;                   // its frame
     const float cB = tab->wcs[2 * (n2 % 25)], sB = tab->wcs[2 * (n2 % 25) + 1];
-    const int L = min(tid, 6 * 25 - 1);                      // stage 2: lane pairs (A,B) adjacent
+    const int L = min(tid, NACT - 1);                        // stage 2: lane pairs (A,B) adjacent
     const int f2 = L / 50, t2 = (L % 50) >> 1, r2 = L & 1;
     const float c0 = r2 == 0 ? 1.0f : (1.0f / 3.0f);
     const int kt = (625 * t2) % 1200;
@@ -116,7 +117,7 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
             // spilled to local memory and re-loaded, which costs more than the two FMAs each)
             float cBt = cB, sBt = sB;
             asm volatile("" : "+f"(cBt), "+f"(sBt));
-            if (tid < 150 && f1 < nf) stage1_task(s_samples, s_x1, q1, n2, cBt, sBt);
+            if (tid < NACT && f1 < nf) stage1_task(s_samples, s_x1, q1, n2, cBt, sBt);
         }
         __syncthreads();
 
@@ -142,7 +143,7 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
 
         // ---- stage 2b
         {
-            const bool valid = tid < 150 && f2 < nf;
+            const bool valid = tid < NACT && f2 < nf;
             float2* const sp = MIC ? spec + ((long long)b * T + (t0 + f2)) * (NBIN * 4) + 2 * r2 : nullptr;
             int ktt = kt;
             if (MIC) asm volatile("" : "+r"(ktt));   // keep the 25 bin indices from being hoisted (and spilled)
@@ -176,7 +177,7 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
         // ---- mel projection + log + standardise + store (static schedule, balanced over warps)
         float* const out_tile = out + (((long long)b * NCH_OUT) * T + t0) * NMEL;
 #pragma unroll 1
-        for (int qq = 0; qq < 3; ++qq) {
+        for (int qq = 0; qq < MEL_SLOTS; ++qq) {
             const int code = mel_assign(warp, qq);
             if (code < 0) break;
             const int f = code >> 2, wt = code & 3;
@@ -329,7 +330,7 @@ int launch_features_foa(const int16_t* audio, int B, long long N, const float* m
     int dev = 0, sms = 0;
     ADY_CUDA_CHECK(cudaGetDevice(&dev));
     ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int grid = (int)(ntiles < 2LL * sms ? ntiles : 2LL * sms);
+    const int grid = (int)(ntiles < (long long)CTAS_PER_SM * sms ? ntiles : (long long)CTAS_PER_SM * sms);
     // window scale: 2^-15 (int16 -> [-1,1)) * 1/2 (channel split), DC terms scaled by the same 1/2
     const float dc0 = dc_offset * 300.0f, dc1 = -dc_offset * 150.0f;
     if (rot && clip_off)
@@ -363,7 +364,7 @@ int launch_features_mic_logmel(const int16_t* audio, int B, long long N, const f
     int dev = 0, sms = 0;
     ADY_CUDA_CHECK(cudaGetDevice(&dev));
     ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int grid = (int)(ntiles < 2LL * sms ? ntiles : 2LL * sms);
+    const int grid = (int)(ntiles < (long long)CTAS_PER_SM * sms ? ntiles : (long long)CTAS_PER_SM * sms);
     rc = launch_frontend_inst<false, false, true>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd,
                                                   dc_offset * 300.0f, -dc_offset * 150.0f, nullptr, nullptr, out, spec, flags);
     if (rc) return rc;

@@ -31,9 +31,19 @@ constexpr int NCH_IN = 4;
 constexpr int NCH_FOA = 7;
 
 // ---------------------------------------------------------------- tiling
-constexpr int TF = 3;              // frames per tile
-constexpr int NTHREADS = 160;      // 150 active in the FFT stages (3 frames x 2 packed FFTs x 25)
-constexpr int NFFT_TILE = 2 * TF;  // packed complex FFTs per tile
+// ADY_TILE_FRAMES = 3: two CTAs of 5 warps per SM (150 of 160 lanes active in the FFT stages);
+// ADY_TILE_FRAMES = 7: one CTA of 11 warps per SM (350 of 352 lanes), the four schedulers hold 3/3/3/2
+// warps instead of 3/3/2/2, 231.5 KB of shared memory, 168 x 352 registers.
+#ifndef ADY_TILE_FRAMES
+#define ADY_TILE_FRAMES 3
+#endif
+constexpr int TF = ADY_TILE_FRAMES;        // frames per tile
+constexpr int NFFT_TILE = 2 * TF;          // packed complex FFTs per tile
+constexpr int NACT = NFFT_TILE * 25;       // threads with an FFT task (one per (packed FFT, n2) / (frame, residue pair, role))
+constexpr int NTHREADS = ((NACT + 31) / 32) * 32;
+constexpr int CTAS_PER_SM = TF == 3 ? 2 : 1;
+constexpr int COPY_THREADS = 160;          // the staging map covers a frame with 5 warps x 16-sample columns x 15 steps
+static_assert(TF == 3 || TF == 7, "mel_assign() holds a unit table for 3- and 7-frame tiles");
 
 // sample planes: one per (frame, pair); word(idx) = idx + idx/16  (skew -> conflict-free
 // stride-48 reads); 1275 words per plane == 51*25 so that lane L = 25*fft + n2 reads word
@@ -53,9 +63,9 @@ constexpr int MEL_MAXNNZ = 1216;
 //   x1_base(2f+1) - x1_base(2f) == 8 (mod 16 float2) [stage 2a: adjacent A/B lanes, disjoint banks]
 // sample plane q starts at q*1275 words, the three (Z,X) planes shifted by 31 words so that the
 // A and B planes of one frame are 16 banks apart (conflict-free 2 x 16-lane cp.async stores)
-ADY_HD constexpr int splane_base(int q) { return q * SPLANE + (q >= 3 ? 31 : 0); }
-ADY_HD constexpr int g_of_q(int q) { return q < 3 ? 2 * q : 2 * (q - 3) + 1; }
-ADY_HD constexpr int q_of_g(int g) { return (g & 1) ? 3 + (g >> 1) : (g >> 1); }
+ADY_HD constexpr int splane_base(int q) { return q * SPLANE + (q >= TF ? 31 : 0); }
+ADY_HD constexpr int g_of_q(int q) { return q < TF ? 2 * q : 2 * (q - TF) + 1; }
+ADY_HD constexpr int q_of_g(int g) { return (g & 1) ? TF + (g >> 1) : (g >> 1); }
 ADY_HD constexpr int x1_base(int g) { return (g >> 1) * XFRAME + (g & 1) * FS; }
 ADY_HD constexpr int v_base(int f) { return ((f * XFRAME + 1) >> 1) << 1; }   // float2 units, 16-byte aligned
 
@@ -116,7 +126,7 @@ ADY_HD void stage1_task(const uint32_t* __restrict__ samples, float2* __restrict
         x[n1] = {lo * w, hi * w};
     }
     dft48(x);
-    float2* xo = x1 + x1_base(q < 3 ? 2 * q : 2 * (q - 3) + 1) + n2;
+    float2* xo = x1 + x1_base(g_of_q(q)) + n2;
 #pragma unroll
     for (int k1 = 0; k1 < 48; ++k1) xo[k1 * 25] = make_float2(x[k1].re, x[k1].im);
 }
@@ -247,9 +257,23 @@ ADY_HD void mel_task(const float4* __restrict__ vframe4, const MelEntry* __restr
 // 15 nibbles [warp][slot], 15 = none:  w0: (f0,wt3) (f0,wt0) | w1: (f1,wt3) (f1,wt0) | w2: (f2,wt3) (f2,wt0)
 //                                      | w3: (f0,wt2) (f1,wt2) (f0,wt1) | w4: (f2,wt2) (f1,wt1) (f2,wt1)
 constexpr unsigned long long MEL_ASSIGN_PACK = 0x95a162f8bf47f03ull;
+// 7-frame tile, 11 warps, 28 units (total 378 iterations, ideal 34.4 per warp; makespan 37):
+//   w0: (f0,wt3) (f0,wt1) | w1..w6: (fi,wt3) (fi,wt0) | w7: (f0,wt2) (f1,wt2) (f1,wt1) | w8: (f2,wt2) (f3,wt2) (f2,wt1)
+//   w9: (f4,wt2) (f5,wt2) (f3,wt1) | w10: (f6,wt2) (f4,wt1) (f5,wt1) (f6,wt1) (f0,wt0)
+constexpr int MEL_SLOTS = TF == 3 ? 3 : 5;
 ADY_HD int mel_assign(int warp, int slot) {
-    const int v = (int)((MEL_ASSIGN_PACK >> (4 * (warp * 3 + slot))) & 15ull);
-    return v == 15 ? -1 : v;
+    if (TF == 3) {
+        const int v = (int)((MEL_ASSIGN_PACK >> (4 * (warp * 3 + slot))) & 15ull);
+        return v == 15 ? -1 : v;
+    }
+    // (closed form instead of a table: a local array would live in local memory)
+    if (warp < 7) return slot == 0 ? 4 * warp + 3 : (slot == 1 ? (warp == 0 ? 1 : 4 * warp) : -1);
+    if (warp < 10) {
+        const int f = 2 * (warp - 7);
+        return slot == 0 ? 4 * f + 2 : (slot == 1 ? 4 * (f + 1) + 2 : (slot == 2 ? 4 * (warp - 6) + 1 : -1));
+    }
+    if (warp == 10) return slot == 0 ? 26 : (slot == 1 ? 17 : (slot == 2 ? 21 : (slot == 3 ? 25 : 0)));
+    return -1;
 }
 
 // librosa.power_to_db(ref=1, amin=1e-10) before the top_db clamp (datasets.py:265)

@@ -27,7 +27,7 @@ extern "C" int emu_features_foa(const int16_t* audio, int B, long long N, const 
   for (int tile = 0; tile < B * tpc; ++tile) {
     const int b = tile / tpc, tb = tile % tpc, t0 = tb * TF, nf = std::min(TF, T - t0);
     // ---- copy (same element mapping as issue_tile_copy)
-    for (int tid = 0; tid < NTHREADS; ++tid) {
+    for (int tid = 0; tid < COPY_THREADS; ++tid) {
       const int pair = (tid >> 4) & 1, i0 = (tid >> 5) * 16 + (tid & 15);
       const int16_t* clip = audio + (long long)b * N * 4 + pair * 2;
       for (int f = 0; f < nf; ++f) {
@@ -41,19 +41,19 @@ extern "C" int emu_features_foa(const int16_t* audio, int B, long long N, const 
       }
     }
     // ---- stage 1
-    for (int tid = 0; tid < 150; ++tid) { int q = tid / 25, n2 = tid % 25; int f1 = q < 3 ? q : q - 3; if (f1 < nf) stage1_task(s_samples, s_x1, q, n2, wcs[2 * n2], wcs[2 * n2 + 1]); }
+    for (int tid = 0; tid < NACT; ++tid) { int q = tid / 25, n2 = tid % 25; int f1 = q < TF ? q : q - TF; if (f1 < nf) stage1_task(s_samples, s_x1, q, n2, wcs[2 * n2], wcs[2 * n2 + 1]); }
     // ---- stage 2a (all threads, then "barrier")
     std::vector<Stage2Regs> R(NTHREADS);
-    for (int tid = 0; tid < NTHREADS; ++tid) { int L = std::min(tid, 149); stage2a_task(s_x1, L / 50, (L % 50) >> 1, L & 1, dc0, dc1, 1.f, 1.f, R[tid]); }
+    for (int tid = 0; tid < NTHREADS; ++tid) { int L = std::min(tid, NACT - 1); stage2a_task(s_x1, L / 50, (L % 50) >> 1, L & 1, dc0, dc1, 1.f, 1.f, R[tid]); }
     // ---- stage 2b: lane pairs exchange
     for (int tid = 0; tid < NTHREADS; tid += 2) {
       for (int k2 = 0; k2 < 25; ++k2) {
         SlotMine m[2]; SlotOut o[2];
-        for (int s = 0; s < 2; ++s) { int L = std::min(tid + s, 149); int r = L & 1; slot_split(R[tid + s].P[k2], R[tid + s].Q[(25 - k2) % 25], r == 0 ? 1.0f : 1.0f / 3.0f, m[s], o[s]); }
+        for (int s = 0; s < 2; ++s) { int L = std::min(tid + s, NACT - 1); int r = L & 1; slot_split(R[tid + s].P[k2], R[tid + s].Q[(25 - k2) % 25], r == 0 ? 1.0f : 1.0f / 3.0f, m[s], o[s]); }
         for (int s = 0; s < 2; ++s) {
-          int L = std::min(tid + s, 149); int f2 = L / 50, t2 = (L % 50) >> 1, r2 = L & 1;
+          int L = std::min(tid + s, NACT - 1); int f2 = L / 50, t2 = (L % 50) >> 1, r2 = L & 1;
           float iva, ivb; slot_finish(m[s], o[s], o[1 - s], r2, iva, ivb);
-          if (tid + s < 150 && f2 < nf) slot_store(s_x1 + v_base(f2) + 50 * t2 + r2, k2, m[s].P0, m[s].P1, iva, ivb);
+          if (tid + s < NACT && f2 < nf) slot_store(s_x1 + v_base(f2) + 50 * t2 + r2, k2, m[s].P0, m[s].P1, iva, ivb);
         }
       }
     }
