@@ -300,7 +300,12 @@ def main_ours(args):
         roof = {"bound": "hbm", "kernel": "frontend_foa_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": fe_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,
+                # the north star also asks for the FP32 (CUDA-core) roofline: algorithmic 6.5 MFLOP per audio-second
+                #  against 148 SM x 128 lanes x 2 FLOP x the sampled SM clock
+                "fp32": {"achieved": BATCH * CLIP_S * 6.5e6 / (fe_ms / 1e3) / 1e12,
+                         "peak": 148 * 128 * 2 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12, "unit": "TFLOP/s"},
                 "note": "FP32-issue-bound kernel (25 FLOP/B vs ~11 FLOP/B ridge); see DESIGN.md / profiles/"}
+        roof["fp32"]["frac"] = roof["fp32"]["achieved"] / roof["fp32"]["peak"]
     if rank == 0:
         line = {"metric": "audio-hours of 4-ch features/sec", "value": value, "unit": "audio-hours/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
