@@ -328,3 +328,18 @@ def test_long_clips_batch_equals_per_clip_and_oracle(A, scaler2021):
     refm = F.features_mic_stack(audio[2].cpu().numpy())
     m = mic[2].cpu().numpy()
     assert _mel_err(m[:4], refm[:4]) < 1e-4 and np.abs(m[4:] - refm[4:]).max() < 1e-3
+
+
+def test_mic_standardisation_with_a_10_channel_scaler(A):
+    """MIC path with a (10, 64) scaler (4 log-mel + 6 GCC rows, the layout the new `scaler` action writes
+    for the MIC format): equals standardising the raw output (the top_db clamp commutes with it)."""
+    from adyolo_b200.features import features_mic_batched
+    rng = np.random.default_rng(44)
+    clips = torch.from_numpy(np.clip(rng.standard_normal((3, 24000 * 2, 4)) * 2500, -32768, 32767).astype(np.int16)).cuda()
+    mean = torch.from_numpy(np.concatenate([rng.uniform(-60, -20, (4, 64)), rng.normal(0, 0.01, (6, 64))]).astype(np.float32)).cuda()
+    istd = torch.from_numpy(np.concatenate([rng.uniform(0.05, 0.2, (4, 64)), rng.uniform(5, 30, (6, 64))]).astype(np.float32)).cuda()
+    raw = features_mic_batched(clips)
+    std = features_mic_batched(clips, (mean, istd))
+    want = (raw - mean[None, :, None, :]) * istd[None, :, None, :]
+    err = (std - want).abs().amax(dim=(0, 2, 3)) / want.abs().amax(dim=(0, 2, 3))
+    assert float(err.max()) < 1e-5
