@@ -343,3 +343,20 @@ def test_mic_standardisation_with_a_10_channel_scaler(A):
     want = (raw - mean[None, :, None, :]) * istd[None, :, None, :]
     err = (std - want).abs().amax(dim=(0, 2, 3)) / want.abs().amax(dim=(0, 2, 3))
     assert float(err.max()) < 1e-5
+
+
+def test_scaler_action_mic_format(A):
+    """`scaler` action for the MIC format: the pickle schema gains a GCC key (1, 64, 6) (SURVEY 8(c));
+    statistics equal float64 numpy statistics of the per-file features."""
+    from adyolo_b200.features import features_mic_batched
+    rng = np.random.default_rng(6)
+    clips = [np.clip(rng.standard_normal((24000 * 2, 4)) * (800 + 500 * i), -32768, 32767).astype(np.int16) for i in range(4)]
+    got = A.preprocess_scaler(clips, fmt="mic", batch_clips=2)
+    assert set(got) == {"MEL", "GCC"} and got["GCC"]["mean"].shape == (1, 64, 6) and got["MEL"]["std"].shape == (1, 64, 4)
+    feats = np.concatenate([features_mic_batched(torch.from_numpy(c[None]).cuda())[0].double().cpu().numpy() for c in clips], axis=1)  # (10, sumT, 64)
+    for key, sl in (("MEL", slice(0, 4)), ("GCC", slice(4, 10))):
+        x = feats[sl]                                            # (C, frames, 64)
+        mean, std = x.mean(axis=1).T[None], x.std(axis=1).T[None]   # (1, 64, C)
+        assert np.abs(got[key]["mean"] - mean).max() <= 1e-6 * max(1.0, np.abs(mean).max())
+        assert np.abs(got[key]["std"] - std).max() <= 1e-6 * max(1.0, np.abs(std).max())
+        assert np.array_equal(got[key]["max"], x.max(axis=1).T[None]) and np.array_equal(got[key]["min"], x.min(axis=1).T[None])
