@@ -360,3 +360,14 @@ def test_scaler_action_mic_format(A):
         assert np.abs(got[key]["mean"] - mean).max() <= 1e-6 * max(1.0, np.abs(mean).max())
         assert np.abs(got[key]["std"] - std).max() <= 1e-6 * max(1.0, np.abs(std).max())
         assert np.array_equal(got[key]["max"], x.max(axis=1).T[None]) and np.array_equal(got[key]["min"], x.min(axis=1).T[None])
+
+
+def test_nan_intensity_raises_instead_of_exit(A):
+    """utility.py:211-213 prints and calls exit() when the intensity features contain NaN; the
+    replacement reports it through the kernel's flag word and raises FloatingPointError."""
+    rng = np.random.default_rng(1)
+    spec = (rng.standard_normal((6, 601, 4)) + 1j * rng.standard_normal((6, 601, 4))).astype(np.complex128)
+    assert np.isfinite(A.stft2iv(spec, 24000, 1200, 64)).all()
+    spec[3, 100, 2] = np.nan
+    with pytest.raises(FloatingPointError):
+        A.stft2iv(spec, 24000, 1200, 64)
