@@ -50,6 +50,55 @@ __device__ __forceinline__ RowGeom read_row(const float* __restrict__ target, lo
     return g;
 }
 
+// Decode + great-circle distance of one anchor (loss.py:196-213, :184-187) with the intermediates
+// its backward needs.  noinline: one copy of the libdevice chains in the kernel.
+struct AnchorEval {
+    float D, thu, thv, Vp, sov, cov, du, cdu, dist, cl;
+};
+struct ChainK {   // the constants of the chain, by value (a reference to the kernel's AssignCfg would spill it to local memory)
+    float ovl_scale, gs_u, gs_v, deg2rad, rad2deg, clip_lo, clip_hi;
+};
+
+__device__ __noinline__ AnchorEval eval_anchor(float xu, float xv, const ChainK cfg, float off_u, float off_v,
+                                               float tur, float stv, float ctv) {
+    AnchorEval e;
+    // loss.py:196-198 tanh; :203-205 three separately rounded ops
+    e.thu = tanhf(xu); e.thv = tanhf(xv);
+    float U = __fadd_rn(__fmul_rn(__fmul_rn(e.thu, cfg.ovl_scale), cfg.gs_u), off_u);
+    e.Vp = __fadd_rn(__fmul_rn(__fmul_rn(e.thv, cfg.ovl_scale), cfg.gs_v), off_v);
+    const float V = clamp_torch(e.Vp, -90.f, 90.f);       // :208
+    if (U >= 180.f) U = __fadd_rn(U, -360.f);              // :209-210
+    if (U < -180.f) U = __fadd_rn(U, 360.f);               // :211-212
+    // :184-187
+    const float our = __fmul_rn(U, cfg.deg2rad), ovr = __fmul_rn(V, cfg.deg2rad);
+    e.sov = sinf(ovr); e.cov = cosf(ovr);
+    e.du = __fadd_rn(our, -tur);
+    e.cdu = cosf(fabsf(e.du));
+    e.dist = __fadd_rn(__fmul_rn(e.sov, stv), __fmul_rn(__fmul_rn(e.cov, ctv), e.cdu));
+    e.cl = clamp_torch(e.dist, cfg.clip_lo, cfg.clip_hi);
+    e.D = __fmul_rn(acosf(e.cl), cfg.rad2deg);
+    return e;
+}
+
+// backward of the chain (only needs ~1e-5): dD/d(xu), dD/d(xv)
+__device__ __forceinline__ float anchor_dD_ddist(const AnchorEval& e, const ChainK& cfg) {
+    const float pass = (e.dist >= cfg.clip_lo && e.dist <= cfg.clip_hi) ? 1.f : 0.f;
+    // acos backward as ATen evaluates it: grad * -rsqrt(-x*x + 1), two roundings (no FMA):
+    // 1 - x^2 cancels badly for small angles, so the op order matters at the 1e-5 level
+    const float om = __fadd_rn(1.f, -__fmul_rn(e.cl, e.cl));
+    return -cfg.rad2deg * rsqrtf(fmaxf(om, 1e-30f)) * pass;
+}
+__device__ __forceinline__ float anchor_grad_u(const AnchorEval& e, const ChainK& cfg, float ctv) {
+    const float sgn = e.du > 0.f ? 1.f : (e.du < 0.f ? -1.f : 0.f);
+    const float ddist_dou = -(e.cov * ctv) * sinf(fabsf(e.du)) * sgn;
+    return anchor_dD_ddist(e, cfg) * ddist_dou * (cfg.deg2rad * cfg.ovl_scale) * cfg.gs_u * (1.f - e.thu * e.thu);
+}
+__device__ __forceinline__ float anchor_grad_v(const AnchorEval& e, const ChainK& cfg, float stv, float ctv) {
+    const float ddist_dov = e.cov * stv - e.sov * ctv * e.cdu;
+    const float vpass = (e.Vp >= -90.f && e.Vp <= 90.f) ? 1.f : 0.f;
+    return anchor_dD_ddist(e, cfg) * ddist_dov * (cfg.deg2rad * cfg.ovl_scale) * cfg.gs_v * vpass * (1.f - e.thv * e.thv);
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 assign_rows_kernel(const float* __restrict__ logit, const float* __restrict__ target, long long M_host,
@@ -80,61 +129,37 @@ assign_rows_kernel(const float* __restrict__ logit, const float* __restrict__ ta
             // target side of loss.py:184-186 (deg2rad, sin, cos) — computed once per row
             const float tur = __fmul_rn(g.tu, cfg.deg2rad), tvr = __fmul_rn(g.tv, cfg.deg2rad);
             const float stv = sinf(tvr), ctv = cosf(tvr);
-            float Dv[ADY_MAX_ANCHORS], gu[ADY_MAX_ANCHORS], gv[ADY_MAX_ANCHORS];
+            // Two rolled passes keep the code small (the 5x unrolled chain with its inlined libdevice calls was
+            // 8.2 k SASS instructions and the kernel spent its time on instruction fetch): pass 1 evaluates D for
+            // every anchor, pass 2 sets the responsibility bits and re-evaluates the chain, now with its gradient,
+            // only for the anchors that enter the angular term.
+            const ChainK ck{cfg.ovl_scale, cfg.gs_u, cfg.gs_v, cfg.deg2rad, cfg.rad2deg, cfg.clip_lo, cfg.clip_hi};
+            float Dv[ADY_MAX_ANCHORS];
             float dmin = 0.f;
             int amin = 0;
-#pragma unroll
-            for (int a = 0; a < ADY_MAX_ANCHORS; ++a) {
-                if (a >= A) break;
-                const float xu = lp[a * CH], xv = lp[a * CH + 1];
-                // loss.py:196-198 tanh; :203-205 three separately rounded ops
-                const float thu = tanhf(xu), thv = tanhf(xv);
-                float U = __fadd_rn(__fmul_rn(__fmul_rn(thu, cfg.ovl_scale), cfg.gs_u), off_u);
-                float Vp = __fadd_rn(__fmul_rn(__fmul_rn(thv, cfg.ovl_scale), cfg.gs_v), off_v);
-                const float V = clamp_torch(Vp, -90.f, 90.f);       // :208
-                if (U >= 180.f) U = __fadd_rn(U, -360.f);            // :209-210
-                if (U < -180.f) U = __fadd_rn(U, 360.f);             // :211-212
-                // :184-187
-                const float our = __fmul_rn(U, cfg.deg2rad), ovr = __fmul_rn(V, cfg.deg2rad);
-                const float sov = sinf(ovr), cov = cosf(ovr);
-                const float du = __fadd_rn(our, -tur);
-                const float adu = fabsf(du);
-                const float cdu = cosf(adu);
-                const float dist = __fadd_rn(__fmul_rn(sov, stv), __fmul_rn(__fmul_rn(cov, ctv), cdu));
-                const float cl = clamp_torch(dist, cfg.clip_lo, cfg.clip_hi);
-                const float Dd = __fmul_rn(acosf(cl), cfg.rad2deg);
-                Dv[a] = Dd;
-                if (a == 0 || Dd < dmin) { dmin = Dd; amin = a; }   // first minimum (torch.min)
-                // ---- backward of the chain (only needs ~1e-5): dD/d(xu), dD/d(xv)
-                const float pass = (dist >= cfg.clip_lo && dist <= cfg.clip_hi) ? 1.f : 0.f;
-                // acos backward as ATen evaluates it: grad * -rsqrt(-x*x + 1), two roundings (no FMA):
-                // 1 - x^2 cancels badly for small angles, so the op order matters at the 1e-5 level
-                const float om = __fadd_rn(1.f, -__fmul_rn(cl, cl));
-                const float dD_ddist = -cfg.rad2deg * rsqrtf(fmaxf(om, 1e-30f)) * pass;
-                const float sgn = du > 0.f ? 1.f : (du < 0.f ? -1.f : 0.f);
-                const float ddist_dou = -(cov * ctv) * sinf(adu) * sgn;
-                const float ddist_dov = cov * stv - sov * ctv * cdu;
-                const float vpass = (Vp >= -90.f && Vp <= 90.f) ? 1.f : 0.f;
-                const float k = cfg.deg2rad * cfg.ovl_scale;
-                gu[a] = dD_ddist * ddist_dou * k * cfg.gs_u * (1.f - thu * thu);
-                gv[a] = dD_ddist * ddist_dov * k * cfg.gs_v * vpass * (1.f - thv * thv);
+#pragma unroll 1
+            for (int a = 0; a < A; ++a) {
+                const AnchorEval e = eval_anchor(lp[a * CH], lp[a * CH + 1], ck, off_u, off_v, tur, stv, ctv);
+                Dv[a] = e.D;
+                if (a == 0 || e.D < dmin) { dmin = e.D; amin = a; }   // first minimum (torch.min)
             }
             if (argmin_out) argmin_out[m] = amin;
-#pragma unroll
-            for (int a = 0; a < ADY_MAX_ANCHORS; ++a) {
-                if (a >= A) break;
-                if (D_out) D_out[m * A + a] = Dv[a];
+#pragma unroll 1
+            for (int a = 0; a < A; ++a) {
+                const float Da = Dv[a];
+                if (D_out) D_out[m * A + a] = Da;
                 unsigned long long bits = 0ull;
                 for (int i = 0; i < cfg.n_thr; ++i) {
-                    const bool resp = (Dv[a] < cfg.thr[i]) || (a == amin);   // :223-224
+                    const bool resp = (Da < cfg.thr[i]) || (a == amin);   // :223-224
                     if (mask_out) mask_out[((long long)i * M + m) * A + a] = resp ? 1 : 0;
                     if (resp) bits |= (1ull | (2ull << g.cls)) << (16 * i);
                     if (i == 0 && resp) {                                    // :244-246 angular term
-                        ang_sum += (double)Dv[a];
+                        ang_sum += (double)Da;
                         ang_cnt += 1;
                         if (ang_grad) {
-                            atomicAdd(&ang_grad[cell * A + a].x, gu[a]);
-                            atomicAdd(&ang_grad[cell * A + a].y, gv[a]);
+                            const AnchorEval e = eval_anchor(lp[a * CH], lp[a * CH + 1], ck, off_u, off_v, tur, stv, ctv);
+                            atomicAdd(&ang_grad[cell * A + a].x, anchor_grad_u(e, ck, ctv));
+                            atomicAdd(&ang_grad[cell * A + a].y, anchor_grad_v(e, ck, stv, ctv));
                         }
                     }
                 }
