@@ -167,8 +167,8 @@ frontend_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int t
                     k = k >= 1200 ? k - 1200 : k;
                     const float sg = k > 600 ? -1.f : 1.f;
                     const int kb = k > 600 ? 1200 - k : k;
-                    sp[kb * 4] = make_float2(m.S0.re, sg * m.S0.im);
-                    sp[kb * 4 + 1] = make_float2(m.S1.re, sg * m.S1.im);
+                    // (lane's two channels are adjacent and 16-byte aligned: one 128-bit store)
+                    *reinterpret_cast<float4*>(sp + kb * 4) = make_float4(m.S0.re, sg * m.S0.im, m.S1.re, sg * m.S1.im);
                 }
             }
         }
