@@ -66,8 +66,8 @@ class FrontendCfg(C.Structure):
 
 
 class GridCfg(C.Structure):
-    _fields_ = [("nb_classes", C.c_int32), ("nb_anchors", C.c_int32), ("grid_size", C.c_float * 2),
-                ("g_overlap", C.c_float), ("n_thr", C.c_int32), ("train_unify", C.c_float * 4),
+    _fields_ = [("nb_classes", C.c_int32), ("nb_anchors", C.c_int32), ("grid_size", C.c_double * 2),
+                ("g_overlap", C.c_double), ("n_thr", C.c_int32), ("train_unify", C.c_float * 4),
                 ("angular_gain", C.c_float), ("object_gain", C.c_float), ("nonobj_gain", C.c_float),
                 ("class_gain", C.c_float)]
 
@@ -94,8 +94,10 @@ _SIGS = {
                                        C.POINTER(C.c_int64), _P]),
     "adyolo_scaler_partials": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, _P]),
     "adyolo_label_workspace_bytes": (C.c_size_t, [C.c_int64]),
-    "adyolo_label_cells": (C.c_int, [_P, C.c_int64, C.c_int, C.POINTER(GridCfg), _P, _P, _P, _P, _P]),
-    "adyolo_label_rows": (C.c_int, [_P, C.c_int64, C.POINTER(GridCfg), _P, _P, _P, _P, C.c_int64, _P]),
+    "adyolo_label_cells": (C.c_int, [_P, C.c_int64, C.c_int, C.POINTER(GridCfg), _P, C.c_int64, _P, _P, _P, _P]),
+    "adyolo_label_rows": (C.c_int, [_P, C.c_int64, C.POINTER(GridCfg), _P, C.c_int64, _P, _P, _P, C.c_int64, _P]),
+    "adyolo_launch_count": (C.c_longlong, []),
+    "adyolo_loss_bad_rows_offset": (C.c_size_t, []),
     "adyolo_assign": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.POINTER(GridCfg), _P, _P, _P, _P]),
     "adyolo_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.POINTER(GridCfg)]),
     "adyolo_loss": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.POINTER(GridCfg), _P, _P, _P, _P, _P, _P, _P]),

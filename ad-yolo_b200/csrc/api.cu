@@ -1,5 +1,6 @@
 // extern "C" surface of libadyolo_b200.so (declared in include/adyolo_b200.h).
 #include <math.h>
+#include <stddef.h>
 
 #include "../../include/adyolo_b200.h"
 #include "assign_host.h"
@@ -44,8 +45,8 @@ static int make_cfgs(const adyolo_grid_cfg* g, AssignCfg* a, CellCfg* cc) {
     if (ga > ADY_MAX_GRID || ge > ADY_MAX_GRID) return set_error(ADY_ERR_UNSUPPORTED, "grid %dx%d too large", ga, ge);
     if (a) {
         a->nb_classes = g->nb_classes; a->nb_anchors = g->nb_anchors; a->ga = ga; a->ge = ge; a->n_thr = g->n_thr;
-        a->gs_u = g->grid_size[0]; a->gs_v = g->grid_size[1];
-        a->ovl_scale = (float)(0.5 + (double)g->g_overlap);
+        a->gs_u = (float)g->grid_size[0]; a->gs_v = (float)g->grid_size[1];   // torch.Tensor(grid_size): float32
+        a->ovl_scale = (float)(0.5 + g->g_overlap);   // python float (0.5 + g_overlap) cast by the f32 tensor multiply
         for (int i = 0; i < ADY_MAX_GRID; ++i) {
             // torch: arange(int64)*grid_size(f32) - Tensor([180,90]) + grid_size*0.5, all float32 ops
             a->off_u[i] = ((float)i * a->gs_u - 180.0f) + a->gs_u * 0.5f;
@@ -61,7 +62,7 @@ static int make_cfgs(const adyolo_grid_cfg* g, AssignCfg* a, CellCfg* cc) {
     }
     if (cc) {
         cc->ga = ga; cc->ge = ge;
-        const double ov = (double)g->g_overlap;
+        const double ov = g->g_overlap;
         for (int i = 0; i < ADY_MAX_GRID; ++i) {
             const double ca = i * gs0 - 180.0 + gs0 * 0.5, ce = i * gs1 - 90.0 + gs1 * 0.5;
             cc->lb_a[i] = ca - gs0 * (0.5 + ov);
@@ -80,7 +81,9 @@ using namespace ady;
 extern "C" {
 
 const char* adyolo_last_error(void) { return last_error_buf(); }
-int adyolo_version(void) { return 100; }
+int adyolo_version(void) { return 200; }
+long long adyolo_launch_count(void) { return launch_counter().load(); }
+size_t adyolo_loss_bad_rows_offset(void) { return offsetof(LossAccum, bad_rows); }
 
 int adyolo_mel_filterbank(int sr, int n_fft, int n_mels, float* out_host) {
     if (!out_host || sr <= 0 || n_fft <= 0 || n_mels <= 0) return set_error(ADY_ERR_INVALID, "mel_filterbank: bad args");
@@ -197,23 +200,24 @@ int adyolo_scaler_partials(const float* feats, int B, int C, int64_t T, double* 
 size_t adyolo_label_workspace_bytes(int64_t E) { return label_workspace_bytes((long long)E); }
 
 int adyolo_label_cells(const double* events, int64_t E, int nb_label_frames, const adyolo_grid_cfg* cfg,
-                       const int8_t* rot_comb, uint32_t* cellmask, int64_t* total_rows, void* workspace, void* stream) {
+                       const int8_t* rot_comb, int64_t n_rot, uint32_t* cellmask, int64_t* total_rows, void* workspace,
+                       void* stream) {
     CellCfg cc;
     int rc = make_cfgs(cfg, nullptr, &cc);
     if (rc) return rc;
     if (E > 0 && (!events || !cellmask || !workspace)) return set_error(ADY_ERR_INVALID, "label_cells: NULL pointer");
     if (!total_rows) return set_error(ADY_ERR_INVALID, "label_cells: total_rows is NULL");
-    return launch_label_cells(events, (long long)E, nb_label_frames, cc, rot_comb, cellmask, (long long*)total_rows,
+    return launch_label_cells(events, (long long)E, nb_label_frames, cc, rot_comb, (long long)n_rot, cellmask, (long long*)total_rows,
                               workspace, (cudaStream_t)stream);
 }
 
-int adyolo_label_rows(const double* events, int64_t E, const adyolo_grid_cfg* cfg, const int8_t* rot_comb,
+int adyolo_label_rows(const double* events, int64_t E, const adyolo_grid_cfg* cfg, const int8_t* rot_comb, int64_t n_rot,
                       const uint32_t* cellmask, const void* workspace, float* rows, int64_t max_rows, void* stream) {
     CellCfg cc;
     int rc = make_cfgs(cfg, nullptr, &cc);
     if (rc) return rc;
     if (E > 0 && max_rows > 0 && (!events || !cellmask || !workspace || !rows)) return set_error(ADY_ERR_INVALID, "label_rows: NULL pointer");
-    return launch_label_rows(events, (long long)E, cc, rot_comb, cellmask, workspace, rows, (long long)max_rows,
+    return launch_label_rows(events, (long long)E, cc, rot_comb, (long long)n_rot, cellmask, workspace, rows, (long long)max_rows,
                              (cudaStream_t)stream);
 }
 

@@ -196,9 +196,16 @@ assign_rows_kernel(const float* __restrict__ logit, const float* __restrict__ ta
 // evaluated with the fast MUFU paths (ex2 / rcp / lg2): these terms only enter sums and
 // gradients gated at 1e-5 relative (the bit-exact part is the assignment above); saturation
 // behaves identically (p == 1 -> log(0) = -inf -> clamped to -100).
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// plain division: __fdividef returns 0 for denominators above 2^126 (logits below about -87), which would turn the
+// BCE term into the -100 clamp instead of ATen's ~-88
+__device__ __forceinline__ float sigmoid_fast(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// log for the BCE: MUFU.LG2 flushes subnormal arguments to zero, ATen's logf does not -- sigmoid of a logit in
+// (-103, -87) is subnormal and ATen's term is ~-88..-100 rather than the -100 clamp (never taken in practice)
+__device__ __forceinline__ float log_bce(float p) {
+    return (p > 0.f && p < 1.17549435e-38f) ? logf(p) : __logf(p);
+}
 __device__ __forceinline__ float bce_fwd(float p, float t) {
-    const float lp = fmaxf(__logf(p), -100.f), l1 = fmaxf(__logf(1.0f - p), -100.f);
+    const float lp = fmaxf(log_bce(p), -100.f), l1 = fmaxf(__logf(1.0f - p), -100.f);
     return (t - 1.f) * l1 - t * lp;
 }
 __device__ __forceinline__ float bce_bwd_logit(float p, float t) {

@@ -57,9 +57,9 @@ struct CellCfg {
     double lb_a[ADY_MAX_GRID], ub_a[ADY_MAX_GRID], lb_e[ADY_MAX_GRID], ub_e[ADY_MAX_GRID];
 };
 size_t label_workspace_bytes(long long E);
-int launch_label_cells(const double* events, long long E, int nb_label_frames, const CellCfg& cfg, const int8_t* rot,
+int launch_label_cells(const double* events, long long E, int nb_label_frames, const CellCfg& cfg, const int8_t* rot, long long n_rot,
                        uint32_t* cellmask, long long* total_rows_dev, void* ws, cudaStream_t stream);
-int launch_label_rows(const double* events, long long E, const CellCfg& cfg, const int8_t* rot, const uint32_t* cellmask,
+int launch_label_rows(const double* events, long long E, const CellCfg& cfg, const int8_t* rot, long long n_rot, const uint32_t* cellmask,
                       const void* ws, float* rows, long long max_rows, cudaStream_t stream);
 
 }  // namespace ady

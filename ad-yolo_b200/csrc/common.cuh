@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
+
 namespace ady {
 
 enum : int {
@@ -14,6 +16,8 @@ enum : int {
 };
 
 char* last_error_buf();
+// kernels launched by this library in this process (adyolo_launch_count; bench.py's gpu_launches)
+std::atomic<long long>& launch_counter();
 int set_error(int code, const char* fmt, ...);
 
 #define ADY_CUDA_CHECK(expr)                                                                   \
@@ -26,6 +30,7 @@ int set_error(int code, const char* fmt, ...);
 
 #define ADY_LAUNCH_CHECK(name)                                                                 \
     do {                                                                                       \
+        ::ady::launch_counter().fetch_add(1, std::memory_order_relaxed);                       \
         cudaError_t _e = cudaGetLastError();                                                   \
         if (_e != cudaSuccess)                                                                 \
             return ::ady::set_error(::ady::ADY_ERR_CUDA, "launch of %s failed: %s", name,      \

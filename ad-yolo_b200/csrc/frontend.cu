@@ -298,13 +298,14 @@ template <bool ROT, bool VIEW, bool MIC>
 static int launch_frontend_inst(int grid, cudaStream_t stream, const int16_t* audio, long long N, int T, int tpc, int ntiles,
                                 const FrontendTables* tab, const float* mean, const float* istd, float dc0, float dc1,
                                 const int8_t* rot, const long long* clip_off, float* out, float2* spec, int* flags) {
-    static int configured_dev = -1;
+    // once per (instantiation, device); a racing second thread at worst repeats the idempotent call
+    static std::atomic<unsigned long long> configured{0};
     int dev = 0;
     ADY_CUDA_CHECK(cudaGetDevice(&dev));
-    if (configured_dev != dev) {
+    if (!((configured.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
         ADY_CUDA_CHECK(cudaFuncSetAttribute(frontend_foa_kernel<ROT, VIEW, MIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             SmemLayout::total));
-        configured_dev = dev;
+        configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     frontend_foa_kernel<ROT, VIEW, MIC><<<grid, NTHREADS, SmemLayout::total, stream>>>(
         audio, N, T, tpc, ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, spec, flags);

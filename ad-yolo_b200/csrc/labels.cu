@@ -34,7 +34,7 @@ __device__ __forceinline__ void rotate_label(int comb, double& azi, double& ele)
 }
 
 __global__ void __launch_bounds__(LB)
-label_cells_kernel(const double* __restrict__ ev, long long E, int nlf, CellCfg cfg, const int8_t* __restrict__ rot,
+label_cells_kernel(const double* __restrict__ ev, long long E, int nlf, CellCfg cfg, const int8_t* __restrict__ rot, long long n_rot,
                    uint32_t* __restrict__ cellmask, uint32_t* __restrict__ local_off, long long* __restrict__ block_tot) {
     __shared__ uint32_t wsum[LB / 32];
     const long long e = (long long)blockIdx.x * LB + threadIdx.x;
@@ -43,7 +43,10 @@ label_cells_kernel(const double* __restrict__ ev, long long E, int nlf, CellCfg 
         const double frame = ev[e * 5 + 1];
         double azi = ev[e * 5 + 3];
         double ele = ev[e * 5 + 4];
-        if (rot) rotate_label(rot[(long long)ev[e * 5]], azi, ele);
+        if (rot) {   // batch ids outside rot_comb (caller bug) are left unrotated instead of read out of bounds
+            const long long bi = (long long)ev[e * 5];
+            if (bi >= 0 && bi < n_rot) rotate_label(rot[bi], azi, ele);
+        }
         if (azi == 180.0) azi = -180.0;                                  // :470
         if (frame < (double)nlf) {                                       // :468
             uint32_t am = 0, em = 0;
@@ -103,7 +106,7 @@ __global__ void label_scan_kernel(long long* __restrict__ block_tot, long long n
 }
 
 __global__ void __launch_bounds__(LB)
-label_rows_kernel(const double* __restrict__ ev, long long E, CellCfg cfg, const int8_t* __restrict__ rot,
+label_rows_kernel(const double* __restrict__ ev, long long E, CellCfg cfg, const int8_t* __restrict__ rot, long long n_rot,
                   const uint32_t* __restrict__ cellmask, const uint32_t* __restrict__ local_off,
                   const long long* __restrict__ block_off, float* __restrict__ rows, long long max_rows) {
     const long long e = (long long)blockIdx.x * LB + threadIdx.x;
@@ -112,7 +115,10 @@ label_rows_kernel(const double* __restrict__ ev, long long E, CellCfg cfg, const
     if (!mask) return;
     long long o = block_off[blockIdx.x] + local_off[e];
     double azi = ev[e * 5 + 3], ele = ev[e * 5 + 4];
-    if (rot) rotate_label(rot[(long long)ev[e * 5]], azi, ele);
+    if (rot) {
+        const long long bi = (long long)ev[e * 5];
+        if (bi >= 0 && bi < n_rot) rotate_label(rot[bi], azi, ele);
+    }
     if (azi == 180.0) azi = -180.0;
     const float fb = (float)ev[e * 5 + 0], ff = (float)ev[e * 5 + 1], fc = (float)ev[e * 5 + 2];
     const float fu = (float)azi, fv = (float)ele;
@@ -133,7 +139,7 @@ size_t label_workspace_bytes(long long E) {
     return (size_t)(E * 4 + (nb + 1) * 8 + 64);
 }
 
-int launch_label_cells(const double* events, long long E, int nb_label_frames, const CellCfg& cfg, const int8_t* rot,
+int launch_label_cells(const double* events, long long E, int nb_label_frames, const CellCfg& cfg, const int8_t* rot, long long n_rot,
                        uint32_t* cellmask, long long* total_rows_dev, void* ws, cudaStream_t stream) {
     if (cfg.ga * cfg.ge > 32 || cfg.ga > ADY_MAX_GRID || cfg.ge > ADY_MAX_GRID)
         return set_error(ADY_ERR_UNSUPPORTED, "label cells: grid %dx%d exceeds the 32-cell mask", cfg.ga, cfg.ge);
@@ -144,20 +150,20 @@ int launch_label_cells(const double* events, long long E, int nb_label_frames, c
     const long long nb = (E + LB - 1) / LB;
     uint32_t* local_off = reinterpret_cast<uint32_t*>(ws);
     long long* block_tot = reinterpret_cast<long long*>(reinterpret_cast<char*>(ws) + ((E * 4 + 7) / 8) * 8);
-    label_cells_kernel<<<(int)nb, LB, 0, stream>>>(events, E, nb_label_frames, cfg, rot, cellmask, local_off, block_tot);
+    label_cells_kernel<<<(int)nb, LB, 0, stream>>>(events, E, nb_label_frames, cfg, rot, n_rot, cellmask, local_off, block_tot);
     ADY_LAUNCH_CHECK("label_cells_kernel");
     label_scan_kernel<<<1, 1024, 0, stream>>>(block_tot, nb, total_rows_dev);
     ADY_LAUNCH_CHECK("label_scan_kernel");
     return ADY_OK;
 }
 
-int launch_label_rows(const double* events, long long E, const CellCfg& cfg, const int8_t* rot, const uint32_t* cellmask,
+int launch_label_rows(const double* events, long long E, const CellCfg& cfg, const int8_t* rot, long long n_rot, const uint32_t* cellmask,
                       const void* ws, float* rows, long long max_rows, cudaStream_t stream) {
     if (E <= 0) return ADY_OK;
     const long long nb = (E + LB - 1) / LB;
     const uint32_t* local_off = reinterpret_cast<const uint32_t*>(ws);
     const long long* block_off = reinterpret_cast<const long long*>(reinterpret_cast<const char*>(ws) + ((E * 4 + 7) / 8) * 8);
-    label_rows_kernel<<<(int)nb, LB, 0, stream>>>(events, E, cfg, rot, cellmask, local_off, block_off, rows, max_rows);
+    label_rows_kernel<<<(int)nb, LB, 0, stream>>>(events, E, cfg, rot, n_rot, cellmask, local_off, block_off, rows, max_rows);
     ADY_LAUNCH_CHECK("label_rows_kernel");
     return ADY_OK;
 }

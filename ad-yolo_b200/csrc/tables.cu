@@ -14,6 +14,10 @@ namespace ady {
 
 static thread_local char g_err[512] = "";
 char* last_error_buf() { return g_err; }
+std::atomic<long long>& launch_counter() {
+    static std::atomic<long long> n{0};
+    return n;
+}
 int set_error(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);

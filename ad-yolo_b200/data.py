@@ -32,20 +32,18 @@ def load_wav2npy(wav_pth):
 
 
 def load_csv2dict(csv_pth):
-    """datasets.py:103-118 / utility.py:233-246."""
-    label = {}
-    with open(csv_pth, "r") as fid:
-        for line in fid:
-            words = line.strip().split(",")
-            if len(words) < 5:
-                continue
-            frame_idx = int(words[0])
-            label.setdefault(frame_idx, [])
-            if len(words) == 5:
-                label[frame_idx].append([int(words[1]), int(words[2]), float(words[3]), float(words[4])])
-            elif len(words) == 6:
-                label[frame_idx].append([int(words[1]), int(words[2]), float(words[3]), float(words[4]), float(words[5])])
-    return label
+    """The reference's metadata format (datasets.py:103-118 / utility.py:233-246): one event per line,
+    ``frame,class,source,azi,ele`` (polar) or ``frame,class,source,x,y,z`` (Cartesian) ->
+    {frame: [[class, source, coords...], ...]} in file order.  A frame whose line has another
+    column count still gets its (possibly empty) list, as in the reference."""
+    table: dict[int, list] = {}
+    with open(csv_pth, "r") as fh:
+        for raw in fh:
+            cols = raw.strip().split(",")
+            events = table.setdefault(int(cols[0]), [])
+            if len(cols) in (5, 6):
+                events.append([int(cols[1]), int(cols[2])] + [float(c) for c in cols[3:]])
+    return table
 
 
 def chunk_plan(n_samples: int, sr=24000, chunk_window_s=20, chunk_stride_s=1, label_hop_len_s=0.1):
@@ -118,7 +116,7 @@ class ResidentClips:
             p = self._plans[fi]
             if not 0 <= ci < p["n_chunks"]:
                 raise IndexError(cn)
-            offs.append(start + ci * p["wav_stride"])
+            offs.append(start + ci * p["wav_stride"])        # in range by construction: ci < n_chunks of the padded file
             ev = self._events[fi]
             f0 = ci * p["csv_stride"]
             sel = (ev[:, 0] >= f0) & (ev[:, 0] < f0 + p["csv_window"])
@@ -133,17 +131,34 @@ class ResidentClips:
                 torch.from_numpy(events.reshape(-1, 5)).to(self.device), p0["wav_window"], p0["csv_window"])
 
 
-def features_batched_views(audio_resident: torch.Tensor, offsets: torch.Tensor, n_samples: int, scaler_dev=None,
-                           rot_comb: torch.Tensor | None = None, apply_topdb: bool = True) -> torch.Tensor:
-    """Features of B clip *views* of a resident int16 (S, 4) buffer -> (B, 7, T, 64) float32."""
+def features_batched_views(audio_resident: torch.Tensor, offsets, n_samples: int, scaler_dev=None,
+                           rot_comb: torch.Tensor | None = None, apply_topdb: bool = True,
+                           validate: bool | None = None) -> torch.Tensor:
+    """Features of B clip *views* of a resident int16 (S, 4) buffer -> (B, 7, T, 64) float32.
+
+    ``offsets``: first sample of each view.  A python sequence / CPU tensor is range-checked on the
+    host before upload (no device synchronisation); a CUDA tensor (e.g. from ``ResidentClips.batch``,
+    which has already checked its own values on the host) is trusted unless ``validate=True``, which
+    costs one host sync."""
     from .features import _cfg, _workspace
     require_cuda(audio_resident, "features_batched_views")
     if audio_resident.dtype != torch.int16 or audio_resident.dim() != 2 or audio_resident.shape[1] != 4:
         raise ValueError("resident audio must be an int16 tensor of shape (S, 4)")
+    S = audio_resident.shape[0]
+    if not torch.is_tensor(offsets):
+        offsets = torch.as_tensor(list(offsets), dtype=torch.int64)
+    if validate is None:
+        validate = not offsets.is_cuda
+    if validate and offsets.numel():
+        lo, hi = (int(v) for v in torch.stack([offsets.min(), offsets.max()]).tolist())
+        if lo < 0 or hi + n_samples > S:
+            raise IndexError("clip view out of range")
     offsets = offsets.to(audio_resident.device, torch.int64).contiguous()
     B = offsets.shape[0]
-    if B and (int(offsets.min()) < 0 or int(offsets.max()) + n_samples > audio_resident.shape[0]):
-        raise IndexError("clip view out of range")
+    if rot_comb is not None:
+        if rot_comb.dtype != torch.int8 or rot_comb.shape != (B,) or not rot_comb.is_cuda:
+            raise ValueError("rot_comb must be an int8 CUDA tensor of shape (B,)")
+        rot_comb = rot_comb.contiguous()
     cfg = _cfg()
     L = _lib.lib()
     T = n_samples // 600
@@ -157,38 +172,49 @@ def features_batched_views(audio_resident: torch.Tensor, offsets: torch.Tensor, 
     return out
 
 
+def _take(pool: list, picks: list) -> list:
+    """``pool`` minus one occurrence of every element of ``picks``, order preserved (what a
+    sequence of ``list.remove`` calls leaves behind)."""
+    budget: dict = {}
+    for name in picks:
+        budget[name] = budget.get(name, 0) + 1
+    kept = []
+    for name in pool:
+        if budget.get(name, 0):
+            budget[name] -= 1
+        else:
+            kept.append(name)
+    return kept
+
+
 class EpochSampler:
-    """datasets.py:67-98: ``nb_samples`` names per epoch drawn without replacement from a pool
-    that is carried across epochs (and checkpoints) and refilled when it runs dry."""
+    """Without-replacement epoch sampling of the reference Dataset (datasets.py:67-98): every epoch
+    draws ``nb_samples`` names from a pool that survives across epochs (and checkpoints); when the
+    pool cannot cover an epoch, what is left is used up first and the rest comes from a fresh copy
+    of the full list.  The sequence of ``random.sample`` / ``random.shuffle`` calls and their
+    arguments is the reference's, so a seeded ``random`` reproduces its file lists
+    (golden ``chunking.npz::sampler_epochs``)."""
 
     def __init__(self, total_filelist, nb_samples: int):
         self.total_filelist = list(total_filelist)
-        self.remaining_file = copy.deepcopy(self.total_filelist)
-        self.nb_samples = nb_samples
-        self.filelist = []
+        self.remaining_file = list(self.total_filelist)
+        self.nb_samples = int(nb_samples)
+        self.filelist: list = []
 
     def sample_filelist_for_train_iter(self):
-        self.filelist = []
-        if len(self.remaining_file) >= self.nb_samples:
-            self.filelist = random.sample(self.remaining_file, self.nb_samples)
-            for fnm in self.filelist:
-                self.remaining_file.remove(fnm)
-        else:
-            if len(self.remaining_file) <= 0:
-                self.remaining_file = copy.deepcopy(self.total_filelist)
-                self.filelist = random.sample(self.remaining_file, self.nb_samples)
-                for fnm in self.filelist:
-                    self.remaining_file.remove(fnm)
-            else:
-                random.shuffle(self.remaining_file)
-                pre_sampled = copy.deepcopy(self.remaining_file)
-                self.remaining_file = copy.deepcopy(self.total_filelist)
-                self.filelist = random.sample(self.remaining_file, (self.nb_samples - len(pre_sampled)))
-                for fnm in self.filelist:
-                    self.remaining_file.remove(fnm)
-                self.filelist.extend(pre_sampled)
+        leftovers: list = []
+        pool = self.remaining_file
+        if len(pool) < self.nb_samples:
+            if pool:                                   # use up the tail of the old pool, in shuffled order
+                random.shuffle(pool)
+                leftovers = list(pool)
+            pool = list(self.total_filelist)           # and top up from a fresh pool
+        drawn = random.sample(pool, self.nb_samples - len(leftovers))
+        self.remaining_file = _take(pool, drawn)
+        self.filelist = drawn + leftovers
         return self.filelist
 
+    # checkpoint hooks (train.py:150,247)
     def init_remaining_file_from_list(self, remaining_file):
         self.remaining_file = remaining_file
 

@@ -21,6 +21,7 @@ from . import _lib
 from ._lib import FrontendCfg, check, ptr, require_cuda, stream_ptr
 
 _SCALER_KEYS = ("MEL", "IV")
+FRONTEND_KERNEL = "frontend_foa_kernel"     # name of the fused front-end kernel (bench.py's roofline / ncu filters)
 
 
 def _cfg(sr=24000, n_fft=1200, hop_length=600, win_length=1200, mel_bins=64, n_channels=4,

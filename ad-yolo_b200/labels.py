@@ -33,7 +33,7 @@ class GridSpec:
         self.train_unify = [float(t) for t in train_unify]
         self.loss_gains = dict(loss_gains)
         tu = (C.c_float * 4)(*(self.train_unify + [0.0] * (4 - len(self.train_unify))))
-        self.c = GridCfg(self.nb_classes, self.nb_anchors, (C.c_float * 2)(*gs), self.g_overlap,
+        self.c = GridCfg(self.nb_classes, self.nb_anchors, (C.c_double * 2)(*gs), self.g_overlap,
                          len(self.train_unify), tu, float(loss_gains["angular_gain"]),
                          float(loss_gains["object_gain"]), float(loss_gains["nonobj_gain"]),
                          float(loss_gains["class_gain"]))
@@ -55,8 +55,16 @@ class DeviceRows:
     def __init__(self, rows: torch.Tensor, n_rows: torch.Tensor):
         self.rows, self.n_rows = rows, n_rows
 
+    def overflowed(self) -> bool:
+        """True when more rows were produced than ``rows`` can hold (one host sync)."""
+        return int(self.n_rows.item()) > self.rows.shape[0]
+
     def materialize(self) -> torch.Tensor:
-        return self.rows[: int(self.n_rows.item())]
+        n = int(self.n_rows.item())
+        if n > self.rows.shape[0]:
+            raise RuntimeError(f"label rows overflow: {n} rows produced, capacity {self.rows.shape[0]} "
+                               "(size max_rows as E * Ga * Ge; 4 * E only holds for g_overlap <= 0.5)")
+        return self.rows[:n]
 
 
 def label_rows_batched(events: torch.Tensor, nb_label_frames: int, grid: GridSpec, return_cellmask=False,
@@ -65,8 +73,9 @@ def label_rows_batched(events: torch.Tensor, nb_label_frames: int, grid: GridSpe
     -> target rows (M, 7) float32 on CUDA [batch, frame, Gi, Gj, class, U, V]
     (== get_yolo_label per clip followed by collate_fn's label half).
 
-    With ``max_rows`` (e.g. ``E * Ga * Ge``, or ``4 * E`` for the reference's g_overlap = 0.5) the
-    result is a ``DeviceRows`` and nothing synchronises with the host.
+    With ``max_rows`` (``E * Ga * Ge`` always suffices; ``4 * E`` does for the reference's g_overlap = 0.5)
+    the result is a ``DeviceRows`` and nothing synchronises with the host; rows beyond the capacity are
+    dropped and ``DeviceRows.overflowed()`` / ``materialize()`` report it.
     ``rot_comb`` (int8 CUDA tensor, one RotationAug combination 0..15 per clip / batch index): the
     label half of the rotation augmentation is applied before the cell test."""
     require_cuda(events, "label_rows_batched")
@@ -83,17 +92,18 @@ def label_rows_batched(events: torch.Tensor, nb_label_frames: int, grid: GridSpe
             if rot_comb.dtype != torch.int8 or not rot_comb.is_cuda:
                 raise ValueError("rot_comb must be an int8 CUDA tensor")
             rot_comb = rot_comb.contiguous()
-        check(L.adyolo_label_cells(ptr(events), E, int(nb_label_frames), C.byref(grid.c), ptr(rot_comb), ptr(cellmask),
-                                   ptr(total), ptr(ws), stream_ptr()), "adyolo_label_cells")
+        n_rot = 0 if rot_comb is None else rot_comb.numel()
+        check(L.adyolo_label_cells(ptr(events), E, int(nb_label_frames), C.byref(grid.c), ptr(rot_comb), n_rot,
+                                   ptr(cellmask), ptr(total), ptr(ws), stream_ptr()), "adyolo_label_cells")
         if max_rows is not None:
             rows = torch.empty((int(max_rows), 7), dtype=torch.float32, device=events.device)
-            check(L.adyolo_label_rows(ptr(events), E, C.byref(grid.c), ptr(rot_comb), ptr(cellmask), ptr(ws), ptr(rows),
-                                      int(max_rows), stream_ptr()), "adyolo_label_rows")
+            check(L.adyolo_label_rows(ptr(events), E, C.byref(grid.c), ptr(rot_comb), n_rot, ptr(cellmask), ptr(ws),
+                                      ptr(rows), int(max_rows), stream_ptr()), "adyolo_label_rows")
             return DeviceRows(rows, total)
         M = int(total.item())   # the one host sync of the label path (sizes the output)
         rows = torch.empty((M, 7), dtype=torch.float32, device=events.device)
-        check(L.adyolo_label_rows(ptr(events), E, C.byref(grid.c), ptr(rot_comb), ptr(cellmask), ptr(ws), ptr(rows), M,
-                                  stream_ptr()), "adyolo_label_rows")
+        check(L.adyolo_label_rows(ptr(events), E, C.byref(grid.c), ptr(rot_comb), n_rot, ptr(cellmask), ptr(ws),
+                                  ptr(rows), M, stream_ptr()), "adyolo_label_rows")
     if return_cellmask:
         return rows, cellmask[:E]
     return rows

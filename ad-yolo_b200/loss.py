@@ -74,6 +74,7 @@ class _ADYOLOFn(torch.autograd.Function):
             else:
                 check(L.adyolo_loss_devcount(ptr(logit), ptr(target), M, ptr(n_rows_dev), B, T, C.byref(grid.c),
                                              ptr(loss), ptr(grad), ptr(ws), stream_ptr()), "adyolo_loss_devcount")
+        grid._last_ws = ws                  # ADYOLOloss.last_bad_rows() reads the skipped-row counter from it
         ctx.grid = grid
         ctx.grad = grad                     # consumed (scaled in place and handed out) by the first backward
         ctx.save_for_backward(logit, ws)
@@ -99,7 +100,16 @@ class _ADYOLOFn(torch.autograd.Function):
 class ADYOLOloss(object):
     """loss.py:156-251.  Reads the same ``params`` keys as the reference."""
 
-    def __init__(self, params: dict):
+    def __init__(self, params: dict, check_rows: bool | None = None):
+        """``check_rows`` (default: env ``ADYOLO_CHECK_ROWS=1`` or ``params['args']['check_rows']``): read the
+        kernel's skipped-row counter back after every call (one host sync) and raise ``IndexError`` when a
+        target row indexed outside the logit tensor -- what the reference's indexing does on such rows
+        (loss.py:216,228-232).  Off by default to keep the step free of host syncs; ``last_bad_rows()``
+        gives the same counter on demand (e.g. every N steps)."""
+        import os
+        if check_rows is None:
+            check_rows = bool(params["args"].get("check_rows", False)) or os.environ.get("ADYOLO_CHECK_ROWS", "0") == "1"
+        self.check_rows = bool(check_rows)
         self.device = torch.device(params["args"]["device"])
         if self.device.type != "cuda":
             raise RuntimeError("adyolo_b200.ADYOLOloss needs params['args']['device'] to be a CUDA device "
@@ -137,7 +147,21 @@ class ADYOLOloss(object):
             logit = logit.float()
         logit = logit.contiguous()
         target = target.to(logit.device, torch.float32).contiguous()   # loss.py:199
-        return _ADYOLOFn.apply(logit, target, self.grid, n_rows)
+        loss = _ADYOLOFn.apply(logit, target, self.grid, n_rows)
+        if self.check_rows:
+            bad = self.last_bad_rows()
+            if bad:
+                raise IndexError(f"ADYOLOloss: {bad} target rows index outside the logit tensor "
+                                 f"(batch/frame/Gi/Gj/class out of range for logit {tuple(logit.shape)})")
+        return loss
+
+    def last_bad_rows(self) -> int:
+        """Target rows the most recent call skipped as out of range (host sync)."""
+        ws = getattr(self.grid, "_last_ws", None)
+        if ws is None:
+            return 0
+        off = _lib.lib().adyolo_loss_bad_rows_offset()
+        return int(ws[off:off + 4].view(torch.int32).item())
 
 
 class WrapperCriterion(object):

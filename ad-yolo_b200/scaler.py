@@ -49,25 +49,36 @@ class ScalerAccumulator:
                   "adyolo_scaler_partials")
         self.count += B * T
 
+    def update_from_audio(self, audio_i16: torch.Tensor):
+        """int16 clips (B, N, 4) on the device -> statistics of their un-standardised features (top_db clamp per
+        clip = per file, preprocess.py:111).  FOA when the accumulator has 7 channels, MIC (GCC-PHAT) for 10."""
+        feats = features_batched(audio_i16, None) if self.C == 7 else features_mic_batched(audio_i16, None)
+        self.update(feats)
+
     # ---- combination across ranks + finalisation (pure tensor plumbing; also used by gloo tests)
     @staticmethod
     def combine(count: int, sums: torch.Tensor, ext: torch.Tensor):
-        """All-reduce partials over the default process group (no-op when not initialised)."""
+        """All-reduce partials over the default process group (no-op when not initialised): one SUM over
+        {sum, sumsq, count} and one MAX over {max, -min}, both enqueued on the current stream right after the
+        partials kernels (torch.distributed's NCCL backend is stream-ordered: no host round trip here; the
+        frame count stays a device scalar until ``finalize`` reads the results back)."""
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            packed = torch.cat([sums.reshape(-1), torch.tensor([float(count)], dtype=torch.float64, device=sums.device)])
+            packed = torch.cat([sums.reshape(-1), torch.full((1,), float(count), dtype=torch.float64, device=sums.device)])
             dist.all_reduce(packed, op=dist.ReduceOp.SUM)
             mx = torch.stack([ext[0], -ext[1]])              # max and max(-x) == -min
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             sums = packed[:-1].reshape(sums.shape)
-            count = int(round(packed[-1].item()))
+            count = packed[-1]
             ext = torch.stack([mx[0], -mx[1]])
         return count, sums, ext
 
     @staticmethod
     def finalize(count: int, sums: torch.Tensor, ext: torch.Tensor):
         """-> mean, std (ddof=0), max, min as (C, 64) float64 numpy arrays."""
-        n = float(count)
+        n = float(count)                                     # (device scalar after an all-reduce: the one sync)
+        if n <= 0:
+            raise ValueError("scaler statistics over zero frames (empty shard and no all-reduce?)")
         mean = sums[0] / n
         var = torch.clamp(sums[1] / n - mean * mean, min=0.0)
         return (mean.cpu().numpy(), torch.sqrt(var).cpu().numpy(), ext[0].cpu().numpy(), ext[1].cpu().numpy())
@@ -95,9 +106,13 @@ def preprocess_scaler(clips, fmt: str = "foa", batch_clips: int = 8, out_path: s
     """
     import torch.distributed as dist
     require_cuda(None, "preprocess_scaler")
+    if (rank is None) != (world_size is None):
+        raise ValueError("preprocess_scaler: pass rank and world_size together (or neither: both come from torch.distributed)")
     if rank is None:
         rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
         world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    if not 0 <= rank < world_size:
+        raise ValueError(f"preprocess_scaler: rank {rank} outside world_size {world_size}")
     nC = 7 if fmt == "foa" else 10
     acc = ScalerAccumulator(nC, "cuda")
     mine = list(clips)[rank::world_size]

@@ -25,6 +25,12 @@ import sys
 import threading
 import time
 
+# BLAS / OpenMP pools must be sized BEFORE numpy / torch are imported: the CPU arm runs one worker process
+# per host core, each single-threaded (the reference's DataLoader-worker model).
+# Setting the variables after the import (round 1) had no effect and oversubscribed the cores 16x.
+for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+    os.environ[_v] = "1"
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -60,6 +66,13 @@ def synth_events(rng, n_clips):
     return np.stack([b, t, cls, az, el], 1).astype(np.float64)
 
 
+def config_dict(world):
+    """`config` of the JSON line -- identical in both arms (the CPU arm's sample goes in cpu_baseline.sample)."""
+    return {"workload": WORKLOAD, "clips_per_gpu": BATCH, "clip_s": CLIP_S, "nb_classes": NB_CLASSES,
+            "l2": "inputs larger than L2 (246 MB int16 audio + 123 MB logits per step)",
+            "parallelism": f"clip-sharded x{world}, no collective"}
+
+
 def load_scaler():
     z = np.load(os.path.join(ROOT, "tests", "golden", "scaler_DCASE2021.npz"))
     return {"MEL": {k: z[f"MEL_{k}"] for k in ("mean", "std")}, "IV": {k: z[f"IV_{k}"] for k in ("mean", "std")}}
@@ -78,13 +91,13 @@ def cpu_reference_step(pool, clips, events, scaler, logit):
     import torch
     from oracle import assign_np
     from oracle.loss_torch import ADYOLOlossOracle, default_params
-    feats = pool.map(_cpu_features_one, [(c, scaler) for c in clips])
+    feats = pool.map(_cpu_features_one, [(c, scaler) for c in clips], chunksize=1)
     rows = torch.from_numpy(assign_np.events_to_rows(events, T_LABEL).astype(np.float32))
     crit = ADYOLOlossOracle(default_params(NB_CLASSES, "cpu"))
     logit.grad = None
     loss = crit(logit, rows)
     loss.backward()
-    return feats, float(loss)
+    return feats, float(loss.detach())
 
 
 def run_cpu_baseline(steps, warmup, sample_clips=None):
@@ -92,15 +105,15 @@ def run_cpu_baseline(steps, warmup, sample_clips=None):
     import multiprocessing as mp
     import torch
     cores = os.cpu_count() or 1
-    n = sample_clips or min(max(2 * cores, 16), 128)
+    n = sample_clips or BATCH               # the whole config[1] batch: a step of the CPU arm is a step of ours
     rng = np.random.default_rng(123)
     clips = synth_audio(rng, n)
     events = synth_events(rng, n)
     scaler = load_scaler()
     logit = torch.randn(n, T_LABEL, 160 * (NB_CLASSES + 3), generator=torch.Generator().manual_seed(0)).requires_grad_(True)
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
+    with ctx.Pool(cores) as pool:           # forked before torch starts its own thread pool
+        torch.set_num_threads(cores)        # the loss runs in this process with all cores
         for _ in range(warmup):
             cpu_reference_step(pool, clips[:cores], events[events[:, 0] < cores], scaler, logit[:cores].detach().requires_grad_(True))
         t0 = time.perf_counter()
@@ -108,7 +121,8 @@ def run_cpu_baseline(steps, warmup, sample_clips=None):
             cpu_reference_step(pool, clips, events, scaler, logit)
         dt = time.perf_counter() - t0
     hours = steps * n * CLIP_S / 3600.0
-    return hours / dt, cores, f"{n} x 5-s clips/step x {steps} steps, {cores} worker processes (numpy f64 oracle port) + torch-CPU loss", dt / steps
+    return (hours / dt, cores, f"{n} x 5-s clips/step x {steps} steps; features: {cores} single-threaded worker processes "
+            f"(numpy f64 oracle port, OMP/MKL threads = 1), label rows numpy, loss: torch-CPU with {cores} threads", dt / steps)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -169,6 +183,115 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(self.samples), "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
+
+
+# ------------------------------------------------------------------------------------------------ side configs
+def _dev_audio(torch, dev, seed, B, N):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    return (torch.randn((B, N, 4), device=dev, generator=g) * 3000).clamp_(-32768, 32767).to(torch.int16)
+
+
+def side_configs(A, torch, dist, dev, rank, world, scaler_dev, crit, peak_gbs):
+    """The BASELINE.json configs that are not the headline, measured in the same process (device-resident,
+    CUDA events, max over ranks): config[0] one 60-s clip, the reference-default step shape (B=16 x 20 s),
+    config[2] MIC log-mel + GCC-PHAT on 512 chunks sharded over the ranks, config[3] the scaler action with
+    its all-reduce (>= 1 audio-hour per rank; at N>1 checked against a single-rank pass over the same clips)."""
+    from adyolo_b200.features import features_mic_batched
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    out = {}
+    # ---- config[0]: one 60-s clip through the preprocess.py feature path (raw log-mel + IV), per rank
+    a60 = _dev_audio(torch, dev, 7 + rank, 1, 1_440_000)
+    ms = timed(lambda: A.features_batched(a60, None), 20, 5)
+    out["config0_one_60s_clip"] = {"ms": ms, "audio_h_per_s": world * 60 / 3600 / (ms / 1e3), "n_gpus": world,
+                                   "hbm_frac": 60 * BYTES_PER_AUDIO_S / (ms / 1e3) / 1e9 / peak_gbs,
+                                   "note": "latency case: 2400 frames cannot fill 148 SMs"}
+    del a60
+    # ---- the reference's default training shape: B=16 x 20-s chunks (hyp_train.yaml:1-5, hyp_data_DCASE2021.yaml:16-17)
+    a20 = _dev_audio(torch, dev, 11 + rank, 16, 480_000)
+    rng = np.random.default_rng(99 + rank)
+    ev = synth_events(rng, 16)
+    ev = np.concatenate([ev + np.array([0, 50 * k, 0, 0, 0]) for k in range(4)])       # 200 label frames
+    ev_d = torch.from_numpy(ev).to(dev)
+    lg = torch.randn((16, 200, 160 * (NB_CLASSES + 3)), device=dev, generator=torch.Generator(device=dev).manual_seed(5)).requires_grad_(True)
+
+    def ref_shape_step():
+        A.features_batched(a20, scaler_dev)
+        rows = A.label_rows_batched(ev_d, 200, crit.grid, max_rows=4 * ev_d.shape[0])
+        lg.grad = None
+        crit(lg, rows).backward()
+    ms = timed(ref_shape_step, 20, 5)
+    out["reference_default_16x20s"] = {"ms": ms, "audio_h_per_s": world * 320 / 3600 / (ms / 1e3), "n_gpus": world,
+                                       "note": "features + label rows + loss fwd/bwd per step, per rank"}
+    del a20, lg
+    # ---- config[2]: MIC log-mel + GCC-PHAT (10 ch), 512 x 5-s chunks sharded over the ranks
+    Bm = 512 // world
+    am = _dev_audio(torch, dev, 13 + rank, Bm, N_SAMPLES)
+    ms = timed(lambda: features_mic_batched(am), 5, 2)
+    mic_bytes = 24000 * 4 * 2 + 40 * 64 * 10 * 4
+    out["config2_mic_gcc_512x5s"] = {"ms": ms, "audio_h_per_s": 512 * 5 / 3600 / (ms / 1e3), "n_gpus": world, "scaling": "strong",
+                                     "clips_per_gpu": Bm, "hbm_frac_per_gpu": Bm * 5 * mic_bytes / (ms / 1e3) / 1e9 / peak_gbs,
+                                     "parity": "unpinned (no GCC-PHAT in the reference, SURVEY F1)"}
+    del am
+    torch.cuda.empty_cache()
+    # ---- config[3]: scaler action.  Rank r owns the 60-s clips with global ids 8r..8r+7 and streams them 8 times
+    # (64 clips = 1.07 audio-hours per rank and pass); partials FP64 on the device, one SUM + one MAX all-reduce.
+    def pool_of(r):
+        return torch.cat([_dev_audio(torch, dev, 1000 + 8 * r + i, 1, 1_440_000) for i in range(8)])
+    pool = pool_of(rank)
+    ar_events = []
+
+    def scaler_pass(pools, reps=8, time_allreduce=False):
+        acc = A.ScalerAccumulator(7, dev)
+        for _ in range(reps):
+            for pl in pools:
+                acc.update_from_audio(pl)
+        if time_allreduce:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            c = A.ScalerAccumulator.combine(acc.count, acc.sums, acc.ext)
+            e1.record()
+            ar_events.append((e0, e1))
+            return c
+        return acc.count, acc.sums, acc.ext
+    ms = timed(lambda: scaler_pass([pool], time_allreduce=True), 3, 1)
+    torch.cuda.synchronize()
+    ar_us = float(np.median([a.elapsed_time(b) for a, b in ar_events[1:]])) * 1e3
+    rec = {"ms_per_pass": ms, "audio_h_per_pass_per_gpu": 64 / 60, "audio_h_per_s": world * (64 / 60) / (ms / 1e3), "n_gpus": world,
+           "scaling": "weak", "allreduce_us": ar_us if world > 1 else None,
+           "collective": "torch.distributed NCCL all_reduce SUM (897 f64) + MAX (896 f64), stream-ordered" if world > 1 else "none (1 rank)",
+           "hbm_frac_per_gpu": 64 * 60 * 192000 / (ms / 1e3) / 1e9 / peak_gbs}
+    if world > 1:
+        cnt, sums, ext = scaler_pass([pool], time_allreduce=True)
+        if rank == 0:       # the same clips in one process: every rank's pool, no collective
+            c1, s1, x1 = scaler_pass([pool_of(r) for r in range(world)])
+            rel = ((sums - s1).abs() / s1.abs().clamp_min(1e-300)).max().item()
+            same = float(cnt) == float(c1) and rel <= 1e-12 and torch.equal(ext, x1)
+            rec["check_vs_single_rank"] = {"max_rel_diff_sums": rel, "count_equal": float(cnt) == float(c1),
+                                           "extrema_equal": bool(torch.equal(ext, x1)), "ok": bool(same)}
+            if not same:
+                raise AssertionError(f"sharded scaler statistics differ from the single-rank pass: {rec['check_vs_single_rank']}")
+        dist.barrier()
+    out["config3_scaler"] = rec
+    return out
 
 # ------------------------------------------------------------------------------------------------ ours
 def main_ours(args):
@@ -236,11 +359,14 @@ def main_ours(args):
         pci = None
     sampler = ClockSampler(local_rank, pci)
     sampler.start()
+    L = A._lib.lib()
+    launches0 = L.adyolo_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step(audio_d, events_d, record=True)
     e1.record()
+    launches = L.adyolo_launch_count() - launches0       # counted by the library at every launch site
     barrier()
     ms = e0.elapsed_time(e1)
     fe_ms = float(np.mean([a.elapsed_time(b) for a, b in fe_events])) if fe_events else None
@@ -272,13 +398,63 @@ def main_ours(args):
     e2e_ms = x0.elapsed_time(x1)
     clocks = sampler.stop()
 
+    # ---- what bounds e2e: the plain pinned-host -> device copy of one step's inputs (same buffers, one stream)
+    barrier()
+    scratch = torch.empty_like(audio_d)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scratch.copy_(audio_h, non_blocking=True)
+    torch.cuda.synchronize()
+    c0.record()
+    for _ in range(5):
+        scratch.copy_(audio_h, non_blocking=True)
+    c1.record()
+    barrier()
+    copy_ms = c0.elapsed_time(c1) / 5
+    del scratch
+
+    # ---- e2e, resident variant (training as this framework runs it: the chunk pool lives in HBM as int16
+    # -- ResidentClips -- and a step ships the chunk index list + the event table, reads the loss back)
+    resident = audio_d.reshape(-1, 4)
+    offs_h = (torch.arange(BATCH, dtype=torch.int64) * N_SAMPLES).pin_memory()
+    pipe2 = A.HostBatchPipeline(dev)
+
+    def step_views(offs, events):
+        f = A.features_batched_views(resident, offs, N_SAMPLES, scaler_dev)
+        rows = A.label_rows_batched(events, T_LABEL, grid, max_rows=4 * events.shape[0])
+        logit.grad = None
+        loss = crit(logit, rows)
+        loss.backward()
+        return loss, f
+
+    def e2e_resident(n):
+        pipe2.submit(offs_h, events_h)
+        last = None
+        for i in range(n):
+            o_d, e_d = pipe2.get()
+            if i + 1 < n:
+                pipe2.submit(offs_h, events_h)
+            loss, _ = step_views(o_d, e_d)
+            pipe2.release()
+            last = loss.item()
+        return last
+
+    e2e_resident(3)
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    e2e_resident(args.steps)
+    r1.record()
+    barrier()
+    res_ms = r0.elapsed_time(r1)
+
     if world > 1:
-        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_ms, copy_ms, res_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = t.tolist()
+        ms, e2e_ms, copy_ms, res_ms = t.tolist()
     hours_per_step = world * BATCH * CLIP_S / 3600.0
     value = hours_per_step * args.steps / (ms / 1e3)
     e2e_value = hours_per_step * args.steps / (e2e_ms / 1e3)
+    h2d_bytes = int(audio_h.numel() * 2 + events_h.numel() * 8)
 
     peaks, peak_src = None, "fallback"
     try:
@@ -291,13 +467,15 @@ def main_ours(args):
     if fe_ms:
         alg_bytes = BATCH * CLIP_S * BYTES_PER_AUDIO_S
         ach = alg_bytes / (fe_ms / 1e3) / 1e9
-        traffic = None
+        traffic, kname = None, A.features.FRONTEND_KERNEL
         try:
             with open(os.path.join(ROOT, "profiles", "frontend_traffic.json")) as f:
-                traffic = json.load(f)["dram_bytes_total"]      # ncu --set full capture of the same launch shape
+                tj = json.load(f)
+            if kname in tj.get("kernel", ""):                   # only a capture of THIS kernel (same launch shape) counts
+                traffic = tj["dram_bytes_total"]
         except Exception:
             pass
-        roof = {"bound": "hbm", "kernel": "frontend_foa_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": fe_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 # the north star also asks for the FP32 (CUDA-core) roofline: algorithmic 6.5 MFLOP per audio-second
@@ -306,17 +484,28 @@ def main_ours(args):
                          "peak": 148 * 128 * 2 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12, "unit": "TFLOP/s"},
                 "note": "FP32-issue-bound kernel (25 FLOP/B vs ~11 FLOP/B ridge); see DESIGN.md / profiles/"}
         roof["fp32"]["frac"] = roof["fp32"]["achieved"] / roof["fp32"]["peak"]
+    side = None
+    if not args.no_side_configs:
+        side = side_configs(A, torch, dist, dev, rank, world, scaler_dev, crit, peak)
     if rank == 0:
         line = {"metric": "audio-hours of 4-ch features/sec", "value": value, "unit": "audio-hours/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "clips_per_gpu": BATCH, "clip_s": CLIP_S, "nb_classes": NB_CLASSES,
-                           "l2": "inputs larger than L2 (246 MB int16 audio + 123 MB logits per step)",
-                           "parallelism": f"clip-sharded x{world}, no collective"},
+                "config": config_dict(world),
                 "e2e": {"value": e2e_value, "unit": "audio-hours/s", "ms_per_step": e2e_ms / args.steps,
-                        "h2d_bytes_per_step": int(audio_h.numel() * 2 + events_h.numel() * 8), "d2h_bytes_per_step": 4 + 8},
-                "gpu_launches": args.steps * 10, "roofline": roof, "cpu_baseline": cpu_base, "clocks": clocks, "host_numa": numa,
-                "loss": lv}
+                        "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                        "h2d_gbs_per_gpu": h2d_bytes / (e2e_ms / args.steps / 1e3) / 1e9,
+                        "h2d_ceiling_gbs_per_gpu": audio_h.numel() * 2 / (copy_ms / 1e3) / 1e9,
+                        "frac_of_h2d_ceiling": (h2d_bytes / (e2e_ms / args.steps)) / (audio_h.numel() * 2 / copy_ms),
+                        "note": "PCIe-bound: every step copies its int16 batch from pinned host memory (double-buffered); the "
+                                "ceiling is a bare copy_ of the same buffer on all ranks at once",
+                        "resident_variant": {"value": hours_per_step * args.steps / (res_ms / 1e3), "unit": "audio-hours/s",
+                                             "ms_per_step": res_ms / args.steps,
+                                             "h2d_bytes_per_step": int(offs_h.numel() * 8 + events_h.numel() * 8), "d2h_bytes_per_step": 4,
+                                             "note": "chunk pool resident in HBM (ResidentClips views); a step ships the index list + events"}},
+                "gpu_launches": int(launches * world), "gpu_launches_per_step_per_gpu": launches / args.steps,
+                "roofline": roof, "cpu_baseline": cpu_base, "clocks": clocks, "host_numa": numa,
+                "configs": side, "loss": lv}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -331,7 +520,7 @@ def main_reference(args):
     line = {"impl": "reference", "metric": "audio-hours of 4-ch features/sec", "value": v, "unit": "audio-hours/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD + " (bounded sample on host cores)"},
+            "config": config_dict(world),
             "cpu_baseline": {"value": v, "unit": "audio-hours/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "audio-hours/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -344,6 +533,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-configs", action="store_true", help="skip config[0]/[2]/[3] and the reference-default shape")
     a = ap.parse_args()
     if a.impl == "reference":
         main_reference(a)

@@ -34,6 +34,9 @@ extern "C" {
 
 const char* adyolo_last_error(void);
 int adyolo_version(void);
+/* Number of kernels this library has launched in the calling process so far (every launch site
+ * counts itself): what bench.py reports as `gpu_launches`.                                       */
+long long adyolo_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Feature front end.  Geometry of src/configs/hyp_data_DCASE20xx.yaml:5-12 (the only one the
@@ -84,8 +87,9 @@ int adyolo_features_foa_views(const int16_t* audio, const int64_t* clip_offsets,
                               const int8_t* rot_comb, float* out, void* workspace, int apply_topdb, void* stream);
 
 /* Second half of adyolo_features_foa when it was called with apply_topdb = 0: applies the
- * power_to_db top_db clamp (datasets.py:265) from the per-(clip,channel) maxima left in
- * `workspace` by that call.  Exposed separately so the two kernels can be timed individually. */
+ * power_to_db top_db clamp (datasets.py:265).  The per-(clip,channel) maximum is recomputed from
+ * `out` itself (one block per plane, pass 1 max, pass 2 rewrite of the values below max - top_db);
+ * `workspace` is unused.  Exposed separately so the two kernels can be timed individually.   */
 int adyolo_features_foa_clamp(float* out, int B, int64_t N, const adyolo_frontend_cfg* cfg, const float* mean,
                               const float* inv_std, void* workspace, void* stream);
 
@@ -140,8 +144,8 @@ int adyolo_scaler_partials(const float* feats, int B, int C, int64_t T, double* 
 typedef struct adyolo_grid_cfg {
     int32_t nb_classes;                 /* data_config.nb_classes (<= 15)                         */
     int32_t nb_anchors;                 /* train_config.nb_anchors (<= 8)                         */
-    float grid_size[2];                 /* train_config.grid_size                                 */
-    float g_overlap;                    /* train_config.g_overlap                                 */
+    double grid_size[2];                /* train_config.grid_size -- double: the label path        */
+    double g_overlap;                   /* train_config.g_overlap    (datasets.py:229-233) is float64 */
     int32_t n_thr;                      /* len(train_config.train_unify) (<= 4)                   */
     float train_unify[ADYOLO_MAX_THR];
     float angular_gain, object_gain, nonobj_gain, class_gain; /* train_config.loss_gains          */
@@ -156,11 +160,15 @@ size_t adyolo_label_workspace_bytes(int64_t E);
 /* rot_comb: device int8 (n_clips) rotation combination per batch index, or NULL: the label half
  * of RotationAug._rotate (augmentations.py:98-109) is applied to (azi, ele) before the cell test. */
 int adyolo_label_cells(const double* events, int64_t E, int nb_label_frames, const adyolo_grid_cfg* cfg,
-                       const int8_t* rot_comb, uint32_t* cellmask, int64_t* total_rows, void* workspace,
-                       void* stream);
+                       const int8_t* rot_comb, int64_t n_rot, uint32_t* cellmask, int64_t* total_rows,
+                       void* workspace, void* stream);
+/* Rows past max_rows are not written; *total_rows (from adyolo_label_cells) still holds the full
+ * count, so `*total_rows > max_rows` is the overflow test (DeviceRows.materialize raises on it).
+ * n_rot = number of entries of rot_comb: events whose batch id lies outside [0, n_rot) are left
+ * unrotated rather than read out of bounds.                                                      */
 int adyolo_label_rows(const double* events, int64_t E, const adyolo_grid_cfg* cfg, const int8_t* rot_comb,
-                      const uint32_t* cellmask, const void* workspace, float* rows, int64_t max_rows,
-                      void* stream);
+                      int64_t n_rot, const uint32_t* cellmask, const void* workspace, float* rows,
+                      int64_t max_rows, void* stream);
 
 /* ADYOLOloss decode + distance_between_polar_coordinates + responsibility (loss.py:193-226):
  *   logit  device float32 (B, T, Ga*Ge*A*(C+3));  target device float32 (M, 7)
@@ -178,6 +186,11 @@ int adyolo_assign(const float* logit, const float* target, int64_t M, int B, int
  *            label bits, counts and angular partials of the forward call; do not reuse it in
  *            between).  D / mask / argmin as in adyolo_assign, may be NULL.                     */
 size_t adyolo_loss_workspace_bytes(int B, int T, const adyolo_grid_cfg* cfg);
+/* Byte offset, inside the loss workspace, of an int32 that counts the target rows the last
+ * adyolo_loss / adyolo_loss_devcount call skipped because (batch, frame, Gi, Gj, class) fell outside
+ * the logit tensor.  The reference raises IndexError / a device assert on such rows
+ * (loss.py:216,228-232); read it back (ADYOLOloss(check_rows=True) does) to get the same error. */
+size_t adyolo_loss_bad_rows_offset(void);
 int adyolo_loss(const float* logit, const float* target, int64_t M, int B, int T,
                 const adyolo_grid_cfg* cfg, float* loss_out, float* grad_out, float* D, uint8_t* mask,
                 int32_t* argmin, void* workspace, void* stream);

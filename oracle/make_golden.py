@@ -93,6 +93,30 @@ def synth_labels(seed: int, nb_label_frames: int, nb_classes: int, max_events=3)
     return label
 
 
+def gen_overlap_cells():
+    """Cell masks of every integer (azi, ele) for g_overlap values that are NOT exact in float32
+    (0.2, 0.4): the unmodified reference get_yolo_label (datasets.py:219-238,457-482) with
+    train_config.g_overlap changed.  Pins the float64 grid bounds of the C ABI."""
+    ref_shims.install()
+    import datasets as ref_datasets
+    out = {}
+    az = np.arange(-180, 181, dtype=np.float64)
+    el = np.arange(-90, 91, dtype=np.float64)
+    AZ, EL = [a.ravel() for a in np.meshgrid(az, el, indexing="ij")]
+    for ov in (0.2, 0.4):
+        params = ref_shims.ref_params(12)
+        params["train_config"]["g_overlap"] = ov
+        flp = ref_datasets.FeatureLabelProcessor(params)
+        masks = np.zeros(len(AZ), dtype=np.uint32)
+        for i, (a, e) in enumerate(zip(AZ, EL)):
+            m = 0
+            for row in flp.get_yolo_label({0: [[0, 0, float(a), float(e)]]}, 1):
+                m |= 1 << (int(row[1]) * 4 + int(row[2]))
+            masks[i] = m
+        out["mask_%02d" % int(round(ov * 10))] = masks
+    np.savez_compressed(os.path.join(GOLD, "assign_cells_overlap.npz"), sweep_az=AZ, sweep_el=EL, **out)
+
+
 def main():
     ref_shims.install()
     import torch
@@ -299,4 +323,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "overlap":
+        gen_overlap_cells()
+    else:
+        main()
+        gen_overlap_cells()

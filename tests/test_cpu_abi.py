@@ -79,7 +79,16 @@ def _emu():
     return L
 
 
-@pytest.mark.parametrize("name,tol_iv", [("noise", 1e-3), ("bursts", 1e-3), ("harsh", 5e-3)])
+# Intensity gates.  BASELINE.json: "1e-3 absolute on intensity channels" -- met on the raw channel values with
+# a 20x margin for every fixture (RAW_IV_TOL).  The stricter reading of SURVEY H5 (1e-3 on the STANDARDISED output,
+# i.e. raw error / std with std 0.005..0.015) holds for 'noise' and 'bursts'; the synthetic 'harsh' clip (full-scale
+# tones over a 2-LSB dither, 75 dB inside one frame) cannot meet it in float32 at all: rounding the windowed int16
+# frame to float32 alone costs 5.0e-4 there and a float32 pocketfft costs 2.1e-3 whichever way channels or frames
+# are paired (tools/fp32_floor.py -> profiles/r02_fp32_floor.txt; exception recorded in BASELINE.md section 5).
+RAW_IV_TOL = 5e-5
+
+
+@pytest.mark.parametrize("name,tol_iv", [("noise", 1e-3), ("bursts", 1e-3), ("harsh", 2.5e-3)])
 def test_emulated_kernel_matches_golden(built, gold, scaler2021, name, tol_iv):
     g = gold("features_foa.npz")
     clip = np.ascontiguousarray(g[f"{name}_audio"])
@@ -93,6 +102,8 @@ def test_emulated_kernel_matches_golden(built, gold, scaler2021, name, tol_iv):
     ref = np.concatenate([g[f"{name}_MEL"].transpose(2, 0, 1), g[f"{name}_IV"].transpose(2, 0, 1)], 0)
     assert (np.abs(out[0, :4] - ref[:4]) / np.maximum(np.abs(ref[:4]), 1.0)).max() < 1e-4
     assert np.abs(out[0, 4:] - ref[4:]).max() < tol_iv
+    istd_iv = istd[4:, None, :]
+    assert np.abs((out[0, 4:] - ref[4:]) / istd_iv).max() < RAW_IV_TOL
 
 
 def test_emulated_kernel_ragged_batch(built):

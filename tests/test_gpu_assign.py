@@ -72,6 +72,19 @@ def test_cells_golden_sweep_and_dict_api(A, gold):
         A.collate_fn([(feat, []), (feat, [])])           # reference: torch.cat of an empty list raises
 
 
+@pytest.mark.parametrize("ov,key", [(0.2, "mask_02"), (0.4, "mask_04")])
+def test_cells_inexact_overlap_bit_exact(A, gold, ov, key):
+    """g_overlap crosses the C ABI as a double: cell masks for 0.2 / 0.4 (not exact in float32) equal the
+    unmodified reference's (a float32 g_overlap moved ~10 integer-degree bound cases)."""
+    g = gold("assign_cells_overlap.npz")
+    grid = A.labels.GridSpec(12, 5, [45, 45], ov)
+    az, el = g["sweep_az"], g["sweep_el"]
+    ev = np.stack([np.zeros_like(az), np.zeros_like(az), np.zeros_like(az), az, el], 1)
+    rows, cm = A.label_rows_batched(torch.from_numpy(ev).cuda(), 1, grid, return_cellmask=True)
+    assert np.array_equal(cm.cpu().numpy().astype(np.uint32), g[key])
+    assert np.array_equal(rows.cpu().numpy(), assign_np.events_to_rows(ev, 1, g_overlap=ov).astype(np.float32))
+
+
 @pytest.mark.parametrize("C", [12, 13, 14])
 def test_assign_bitexact_vs_torch_on_gpu(A, C):
     rng = np.random.default_rng(100 + C)
@@ -238,3 +251,62 @@ def test_stress_one_million_frames_bitexact(A, C):
         total_rows += len(rows)
         del logit, D, Dr, masks, mr
     assert total_rows > 3_000_000
+
+
+# ---------------------------------------------------------------- error behaviour
+def test_out_of_range_rows_raise_like_the_reference(A):
+    """A target row indexing outside the logit tensor: the reference's advanced indexing raises
+    (loss.py:216); here the kernel skips and counts it, and check_rows=True turns the count into IndexError."""
+    p = default_params(12, "cuda")
+    logit = torch.randn(2, 10, 2400, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+    good = torch.tensor([[0, 1, 2, 1, 3, 10., 5.], [1, 9, 7, 3, 11, -170., -60.]], device="cuda")
+    bad = torch.tensor([[0, 1, 2, 1, 3, 10., 5.], [1, 10, 7, 3, 11, -170., -60.],      # frame 10 of 10
+                        [2, 0, 0, 0, 0, 0., 0.], [0, 0, 0, 0, 12, 0., 0.]], device="cuda")  # batch 2 of 2, class 12 of 12
+    crit = A.ADYOLOloss(p, check_rows=True)
+    crit(logit, good)
+    assert crit.last_bad_rows() == 0
+    with pytest.raises(IndexError):
+        crit(logit, bad)
+    lazy = A.ADYOLOloss(p)                      # default: no host sync, counter on demand
+    lazy(logit, bad)
+    assert lazy.last_bad_rows() == 3
+
+
+def test_device_rows_overflow_is_reported(A):
+    grid = _grid(A)
+    ev = torch.tensor([[0, 0, 1, 10., 0.], [0, 1, 2, -100., 30.], [0, 2, 3, 50., -30.]], dtype=torch.float64, device="cuda")
+    full = A.label_rows_batched(ev, 5, grid)
+    assert full.shape[0] == 12
+    dr = A.label_rows_batched(ev, 5, grid, max_rows=8)
+    assert dr.overflowed()
+    with pytest.raises(RuntimeError):
+        dr.materialize()
+    ok = A.label_rows_batched(ev, 5, grid, max_rows=ev.shape[0] * 32)
+    assert not ok.overflowed() and torch.equal(ok.materialize(), full)
+
+
+def test_short_rot_comb_is_not_read_out_of_bounds(A):
+    """Batch ids beyond rot_comb are left unrotated (guarded in the kernel) instead of indexing past it."""
+    grid = _grid(A)
+    ev = torch.tensor([[0, 0, 1, 10., 20.], [3, 0, 1, 10., 20.]], dtype=torch.float64, device="cuda")
+    rot = torch.tensor([5], dtype=torch.int8, device="cuda")            # only clip 0 has an entry
+    rows = A.label_rows_batched(ev, 1, grid, rot_comb=rot)
+    plain = A.label_rows_batched(ev[1:], 1, grid)
+    sel = rows[rows[:, 0] == 3]
+    assert torch.equal(sel[:, 1:], plain[:, 1:])
+
+
+def test_extreme_logits_match_aten_bce(A):
+    """Logits around -87.5: 1 + exp(87.5) exceeds 2^126 (where __fdividef returns 0) and the sigmoid is a
+    subnormal float; ATen's BCE term is then ~-87.5, not the -100 clamp.  The kernel uses a true division and
+    a subnormal-safe log for exactly this range."""
+    p = default_params(12, "cuda")
+    logit = torch.full((1, 2, 2400), -87.5, device="cuda")
+    logit[0, 0, :15] = torch.tensor([-87.5] * 13 + [0.3, -0.2], device="cuda")
+    logit[0, 1, :15] = -95.0
+    rows = torch.tensor([[0, 0, 0, 0, 3, -160., -70.]], device="cuda")
+    l1 = logit.clone().requires_grad_(True)
+    l2 = logit.clone().requires_grad_(True)
+    a = A.ADYOLOloss(p)(l1, rows)
+    b = ADYOLOlossOracle(p)(l2, rows)
+    assert abs(a.item() - b.item()) <= 1e-5 * abs(b.item()), (a.item(), b.item())

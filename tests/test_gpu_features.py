@@ -33,7 +33,16 @@ def _mel_err(a, b):
     return (np.abs(a - b) / np.maximum(np.abs(b), 1.0)).max()
 
 
-@pytest.mark.parametrize("name,tol_iv", [("noise", 1e-3), ("bursts", 1e-3), ("harsh", 5e-3)])
+# Intensity gates.  BASELINE.json: "1e-3 absolute on intensity channels" -- met on the raw channel values with
+# a 20x margin for every fixture (RAW_IV_TOL).  The stricter reading of SURVEY H5 (1e-3 on the STANDARDISED output,
+# i.e. raw error / std with std 0.005..0.015) holds for 'noise' and 'bursts'; the synthetic 'harsh' clip (full-scale
+# tones over a 2-LSB dither, 75 dB inside one frame) cannot meet it in float32 at all: rounding the windowed int16
+# frame to float32 alone costs 5.0e-4 there and a float32 pocketfft costs 2.1e-3 whichever way channels or frames
+# are paired (tools/fp32_floor.py -> profiles/r02_fp32_floor.txt; exception recorded in BASELINE.md section 5).
+RAW_IV_TOL = 5e-5
+
+
+@pytest.mark.parametrize("name,tol_iv", [("noise", 1e-3), ("bursts", 1e-3), ("harsh", 2.5e-3)])
 def test_fused_features_vs_reference_golden(A, gold, scaler2021, name, tol_iv):
     g = gold("features_foa.npz")
     clip = torch.from_numpy(g[f"{name}_audio"]).cuda()
@@ -41,7 +50,7 @@ def test_fused_features_vs_reference_golden(A, gold, scaler2021, name, tol_iv):
     ref_raw = np.concatenate([g[f"{name}_mel_raw"].transpose(2, 0, 1), g[f"{name}_iv_raw"].transpose(2, 0, 1)], 0)
     assert raw.shape == ref_raw.shape
     assert _mel_err(raw[:4], ref_raw[:4]) < 1e-4
-    assert np.abs(raw[4:] - ref_raw[4:]).max() < tol_iv * 5e-3      # raw IV, scaled by the smallest std
+    assert np.abs(raw[4:] - ref_raw[4:]).max() < RAW_IV_TOL         # BASELINE.json's gate is 1e-3 on these values
     std = A.features_batched(clip[None], _scaler_dev(A, scaler2021)).cpu().numpy()[0]
     ref = np.concatenate([g[f"{name}_MEL"].transpose(2, 0, 1), g[f"{name}_IV"].transpose(2, 0, 1)], 0)
     assert _mel_err(std[:4], ref[:4]) < 1e-4
@@ -231,6 +240,28 @@ def test_scaler_action_single_gpu(A):
         assert (np.abs(got[grp]["std"] - ref[grp]["std"]) <= 1e-5 * scale + 1e-9).all()
         assert (np.abs(got[grp]["max"] - ref[grp]["max"]) <= 1e-4 * np.maximum(np.abs(ref[grp]["max"]), scale)).all()
         assert (np.abs(got[grp]["min"] - ref[grp]["min"]) <= 1e-4 * np.maximum(np.abs(ref[grp]["min"]), scale)).all()
+
+
+def test_scaler_action_rel_1e6_on_eight_minutes(A):
+    """statistics vs float64 numpy on a longer subset, relative 1e-6.  Mean / std are
+    compared relative to max(|value|, std) of that (mel, channel) -- the intensity means are ~0, so a plain
+    relative error is ill-posed there."""
+    rng = np.random.default_rng(40)
+    clips = []
+    for i in range(8):                                   # 8 x 60 s, levels from -50 to -10 dBFS, one with a silent stretch
+        x = rng.standard_normal((24000 * 60, 4)) * (100 * 2.0 ** i)
+        if i == 3:
+            x[200000:500000] = 0
+        clips.append(np.clip(np.round(x), -32768, 32767).astype(np.int16))
+    got = A.preprocess_scaler(clips, batch_clips=4)
+    ref = F.scaler_stats(clips)
+    worst = {}
+    for grp in ("MEL", "IV"):
+        scale = np.maximum(np.abs(ref[grp]["mean"]), ref[grp]["std"])
+        worst[grp + ".mean"] = (np.abs(got[grp]["mean"] - ref[grp]["mean"]) / scale).max()
+        worst[grp + ".std"] = (np.abs(got[grp]["std"] - ref[grp]["std"]) / scale).max()
+    print("scaler rel errors:", worst)
+    assert max(worst.values()) <= 1e-6, worst
 
 
 def test_fused_rotation_augmentation_all_16_combinations(A, scaler2021):

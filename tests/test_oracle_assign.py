@@ -52,6 +52,22 @@ def test_sphere_sweep_masks(gold):
     assert set(np.unique(resp_counts[integer])) <= {0, 2, 4}
 
 
+@pytest.mark.parametrize("ov,key", [(0.2, "mask_02"), (0.4, "mask_04")])
+def test_sweep_masks_inexact_overlap(gold, ov, key):
+    """g_overlap values that are not exact in float32: the oracle follows the reference's float64
+    bounds (golden from the unmodified get_yolo_label with train_config.g_overlap changed)."""
+    g = gold("assign_cells_overlap.npz")
+    az, el, want = g["sweep_az"], g["sweep_el"], g[key]
+    ev = np.stack([np.zeros_like(az), np.zeros_like(az), np.zeros_like(az), az, el], 1)
+    rows = A.events_to_rows(ev, 1, g_overlap=ov)
+    counts = np.array([bin(int(m)).count("1") for m in want])
+    assert len(rows) == counts.sum()
+    got = np.zeros(len(az), np.uint32)
+    np.bitwise_or.at(got, np.repeat(np.arange(len(az)), counts),
+                     (1 << (rows[:, 2].astype(np.int64) * 4 + rows[:, 3].astype(np.int64))).astype(np.uint32))
+    np.testing.assert_array_equal(got, want)
+
+
 def test_collate_raises_when_empty():
     with pytest.raises(ValueError):
         A.collate_labels([[], []])

@@ -5,8 +5,22 @@ r = list(csv.reader(open(raw)))
 d = {h: (u, v) for h, u, v in zip(r[0], r[1], r[2])}
 def g(k):
     return d[k][1] if k in d else "n/a"
+_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+def nbytes(k):
+    """metric value in bytes: ncu auto-scales the unit per column (byte / Kbyte / Mbyte / Gbyte)"""
+    if k not in d:
+        return float("nan")
+    u, v = d[k]
+    return float(v.replace(",", "")) * _SCALE.get(u.strip(), 1.0)
 print("duration_us", g("gpu__time_duration.sum"), "| cycles", g("sm__cycles_elapsed.max"), "| regs", g("launch__registers_per_thread"))
-print("dram read MB", g("dram__bytes_read.sum"), "write MB", g("dram__bytes_write.sum"), "| dram %", g("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"))
+print("dram read MB %.3f write MB %.3f" % (nbytes("dram__bytes_read.sum") / 1e6, nbytes("dram__bytes_write.sum") / 1e6),
+      "| dram %", g("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"))
+if len(sys.argv) > 3:   # optional: write the traffic record bench.py reads (roofline.traffic)
+    import json
+    json.dump({"kernel": r[2][r[0].index("Kernel Name")] if "Kernel Name" in r[0] else "?", "capture": raw,
+               "dram_bytes_read": int(nbytes("dram__bytes_read.sum")), "dram_bytes_write": int(nbytes("dram__bytes_write.sum")),
+               "dram_bytes_total": int(nbytes("dram__bytes_read.sum") + nbytes("dram__bytes_write.sum"))},
+              open(sys.argv[3], "w"), indent=1)
 print("warp inst", g("smsp__inst_executed.sum"), "| issue active %", g("smsp__issue_active.avg.pct_of_peak_sustained_active"), "| warps active %", g("sm__warps_active.avg.pct_of_peak_sustained_active"))
 print("pipes % : fma", g("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"), "alu", g("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
       "lsu", g("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"), "xu", g("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"))
