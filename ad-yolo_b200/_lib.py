@@ -11,7 +11,7 @@ ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libadyolo_b200.so")
-SOURCES = ["frontend.cu", "frontend_aux.cu", "assign.cu", "labels.cu", "nms.cu", "gcc_tc.cu", "augment.cu", "tables.cu", "scaler.cu", "api.cu"]
+SOURCES = ["fe2.cu", "frontend.cu", "frontend_aux.cu", "assign.cu", "labels.cu", "nms.cu", "gcc_tc.cu", "augment.cu", "tables.cu", "scaler.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC"]
 

@@ -1,0 +1,260 @@
+// Fused SELD front end for FOA clips on sm_100a, second generation: int16 PCM -> standardised log-mel +
+// intensity vectors in one persistent kernel (+ the sparse top_db fix-up pass of frontend.cu).
+//
+// Reference behaviour replaced: /root/reference/src/datasets.py:147 (normalisation), :252-292
+// (get_stft_spectrogram, get_logmel_spectrogram, get_melscale_foa_intensity_vectors, get_feature) and the
+// (C,T,F) stacking of :158-160; == src/utils/utility.py:142-215.  The maths and the per-thread building blocks
+// are in fe2_core.cuh; this file is the CTA-level choreography.
+//
+// Per tile of 2 frames of one clip (160 threads, 3 CTAs per SM):
+//   global int16 (N,4) --cp.async(8 B / sample)--> 24 rows x 75 samples, columns permuted so that stage A is
+//                                                  bank-conflict free (3 hops, shared by the 2 frames)
+//   stage A  75 tasks / frame : window + DFT-16 of both packed FFTs (f32x2)          -> X1 (16 B / point)
+//   stage B  80 tasks / frame : DFT-15, in place                                      -> X2
+//   stage C 121 tasks / frame : twiddle + 2 x DFT-5, channel split, |X|^2, I / E, in place -> V
+//   mel     160 lane-jobs     : <= 9 non-zeros each, both frames per entry            -> 64-byte partial records
+//   epilogue 128 threads      : (frame, mel): add the filter's records, 10 log10, standardise, coalesced store
+// The copy of the next tile is issued right after stage A and overlaps everything else.
+#include <atomic>
+#include <mutex>
+
+#include "common.cuh"
+#include "fe2_core.cuh"
+#include "frontend_host.h"
+
+namespace ady {
+int build_fe2_tables_host(fe2::Tables* t);   // tables.cu
+namespace fe2 {
+
+constexpr int CTAS_PER_SM = 3;
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// Stage the 3 hops of frames t0, t0+1 of the clip starting at sample `clip0` of `audio` (see stage_col()).
+// thread (h = tid / 80, rem = tid % 80 < 75) copies column rem of rows 12 h .. 12 h + 11.
+__device__ __forceinline__ void issue_tile_copy(unsigned char* samp, const int16_t* __restrict__ audio, long long clip0, int t0, int nf,
+                                                int tid, int dst_off /* (12 h * ROWP + stage_col(rem)) * 8 or -1 */) {
+    if (dst_off < 0) return;
+    const int h = tid >= 80, rem = tid - 80 * h;
+    const int16_t* clip = audio + clip0 * 4;
+    const int nrows = 8 * (nf + 1) - 12 * h;                      // rows of this half that the tile needs
+    long long s = 600LL * (t0 - 1) + 900 * h + rem;               // clip sample of row 12 h
+    unsigned char* dst = samp + dst_off;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        if (i < nrows) {
+            const long long m = s < 0 ? -s : s;                   // reflect padding (frame 0 only)
+            cp_async8(dst + i * (ROWP * 8), clip + m * 4);
+        }
+        s += 75;
+    }
+}
+
+// ROT : fused rotation augmentation (utils/augmentations.py:46-111), one combination per clip.
+// VIEW: clip b starts at sample clip_off[b] of one resident buffer (on-the-fly chunking, preprocess.py:13-48).
+template <bool ROT, bool VIEW>
+__global__ void __launch_bounds__(NT, CTAS_PER_SM)
+fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_per_clip, int ntiles,
+               const Tables* __restrict__ tab, const float* __restrict__ mean, const float* __restrict__ istd,
+               float dc0, float dc1, const int8_t* __restrict__ rot, const long long* __restrict__ clip_off,
+               float* __restrict__ out, int* __restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned char* s_samp = smem + SmemLayout::off_samples;
+    unsigned char* s_x = smem + SmemLayout::off_x;
+    MelEnt* s_ent = reinterpret_cast<MelEnt*>(smem + SmemLayout::off_ent);
+    unsigned char* s_tw = smem + SmemLayout::off_tw;
+    float* s_win = reinterpret_cast<float*>(smem + SmemLayout::off_win);
+    float2* s_scale = reinterpret_cast<float2*>(smem + SmemLayout::off_scale);
+    uint8_t* s_meljobs = smem + SmemLayout::off_meljobs;
+
+    const int tid = threadIdx.x;
+    // fixed roles
+    const int fA = tid >= 80, lA = tid - 80 * fA;                                  // stages A / B: frame, lane
+    const StageAConst ka = stage_a_const(lA < 75 ? lA : 0);
+    const int copy_dst = lA < 75 ? (12 * fA * ROWP + stage_col(lA)) * 8 : -1;
+
+    int tile = blockIdx.x;
+    if (tile < ntiles) {
+        const int b = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * TFR;
+        issue_tile_copy(s_samp, audio, VIEW ? clip_off[b] : (long long)b * N, t0, min(TFR, T - t0), tid, copy_dst);
+    }
+    cp_async_commit();
+    // constant tables -> smem (once per persistent CTA)
+    {
+        const uint2* src = reinterpret_cast<const uint2*>(tab->ent);
+        uint2* dst = reinterpret_cast<uint2*>(s_ent);
+        for (int i = tid; i < MEL_L * NJOBS; i += NT) dst[i] = src[i];
+        for (int i = tid; i < 15 * 4 * 4; i += NT) reinterpret_cast<float*>(s_tw)[i] = tab->tw75[i];
+        for (int i = tid; i < 16 * 80; i += NT) s_win[i] = tab->win[i];
+        for (int i = tid; i < 7 * NMEL; i += NT) {   // standardisation as one FMA: x * is + (-mu * is)
+            const float mu = mean ? mean[i] : 0.f, is = istd ? istd[i] : 1.f;
+            s_scale[i] = make_float2(is, -mu * is);
+        }
+        if (tid < NMEL) s_meljobs[tid] = tab->mel_njobs[tid];
+    }
+    const int rec_off = tab->job_rec[tid] * 16;                                     // this lane-job's record slot
+
+    for (; tile < ntiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * TFR, nf = min(TFR, T - t0);
+        const unsigned rb = ROT ? rot_bits_rt(rot[b]) : 0u;
+        cp_async_wait_all();
+        __syncthreads();                                   // samples landed; previous tile's epilogue is done with X
+
+        // ---- stage A
+        if (lA < 75 && fA < nf) stage_a(s_samp, s_win, s_x, fA, lA, ka);
+        __syncthreads();
+
+        // samples are consumed: prefetch the next tile while the rest of this one runs
+        {
+            const int nt = tile + gridDim.x;
+            if (nt < ntiles) {
+                const int nb = nt / tiles_per_clip, nt0 = (nt % tiles_per_clip) * TFR;
+                issue_tile_copy(s_samp, audio, VIEW ? clip_off[nb] : (long long)nb * N, nt0, min(TFR, T - nt0), tid, copy_dst);
+            }
+            cp_async_commit();
+        }
+
+        // ---- stage B (in place)
+        if (fA < nf) stage_b(s_x, fA, lA);
+        __syncthreads();
+
+        // ---- stage C (in place): 224 regular pair-tasks + 18 c = 0 pair-tasks over two rounds
+#pragma unroll 1
+        for (int rd = 0; rd < 2; ++rd) {
+            const int slot = rd * NT + tid;
+            if (slot < 2 * NREG) {
+                const int f = slot >= NREG, task = slot - f * NREG;
+                if (f < nf) stage_c_foa<false>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, rb);
+            } else if (slot >= 256 && slot < 256 + 2 * NC0) {
+                const int i = slot - 256, f = i >= NC0, task = i - f * NC0;
+                if (f < nf) stage_c_foa<true>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, rb);
+            }
+        }
+        __syncthreads();
+
+        // ---- mel projection: lane-job tid, both frames
+        f2 acc[TFR][4];
+        mel_job<true>(s_x, s_ent + tid, nf, acc);
+        __syncthreads();                                   // every V read is done -> records may overwrite frame 0's buffer
+#pragma unroll
+        for (int f = 0; f < TFR; ++f) {
+            st_f4(s_x + (2 * f) * REC_PLANE + rec_off, lo2(acc[f][0]), hi2(acc[f][0]), lo2(acc[f][1]), hi2(acc[f][1]));
+            st_f4(s_x + (2 * f + 1) * REC_PLANE + rec_off, lo2(acc[f][2]), hi2(acc[f][2]), lo2(acc[f][3]), hi2(acc[f][3]));
+        }
+        __syncthreads();
+
+        // ---- epilogue: thread = (frame, mel)
+        if (tid < TFR * NMEL && (tid >> 6) < nf) {
+            const int f = tid >> 6, j = tid & 63;
+            const int nq = s_meljobs[j];
+            const unsigned char* ra = s_x + (2 * f) * REC_PLANE + j * 16;
+            float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
+            for (int i = 0; i < nq; ++i) {                  // fixed order: the result does not depend on scheduling
+                const float4 a = *reinterpret_cast<const float4*>(ra + i * (REC_PITCH * 16));
+                const float4 c = *reinterpret_cast<const float4*>(ra + REC_PLANE + i * (REC_PITCH * 16));
+                pa.x += a.x; pa.y += a.y; pa.z += a.z; pa.w += a.w;
+                pb.x += c.x; pb.y += c.y; pb.z += c.z;
+            }
+            // record order (|W|^2, |Z|^2, |Y|^2, |X|^2 | I_Y, I_Z, I_X) -> channels mel W,Y,Z,X, iv Y,Z,X
+            float v[7] = {power_to_db(pa.x), power_to_db(pa.z), power_to_db(pa.y), power_to_db(pa.w), pb.x, pb.y, pb.z};
+            if (!(pb.x == pb.x && pb.y == pb.y && pb.z == pb.z)) atomicOr(flags, 1);        // datasets.py:277
+            if (ROT) {
+                if (rb & 1u) v[4] = -v[4];
+                if (rb & 2u) v[5] = -v[5];
+                if (rb & 4u) v[6] = -v[6];
+                if (rb & 8u) { float t = v[1]; v[1] = v[3]; v[3] = t; t = v[4]; v[4] = v[6]; v[6] = t; }   // X <-> Y
+            }
+            float* o = out + (((long long)b * 7) * T + t0 + f) * NMEL + j;
+            const long long T64 = (long long)T * NMEL;
+#pragma unroll
+            for (int c = 0; c < 7; ++c) {
+                const float2 k = s_scale[c * NMEL + j];
+                o[c * T64] = fmaf(v[c], k.x, k.y);
+            }
+        }
+        // the barrier at the top of the next iteration orders these record reads before its stage A
+    }
+    cp_async_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static int get_fe2_tables(const Tables** dev_tables) {
+    static std::mutex mu;
+    static Tables* cache[64] = {nullptr};
+    int dev = 0;
+    ADY_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return set_error(ADY_ERR_INVALID, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (!cache[dev]) {
+        static Tables host;
+        static bool host_ok = false;
+        if (!host_ok) {
+            int rc = build_fe2_tables_host(&host);
+            if (rc) return rc;
+            host_ok = true;
+        }
+        Tables* d = nullptr;
+        ADY_CUDA_CHECK(cudaMalloc(&d, sizeof(Tables)));
+        ADY_CUDA_CHECK(cudaMemcpy(d, &host, sizeof(Tables), cudaMemcpyHostToDevice));
+        cache[dev] = d;
+    }
+    *dev_tables = cache[dev];
+    return ADY_OK;
+}
+
+template <bool ROT, bool VIEW>
+static int launch_inst(int grid, cudaStream_t stream, const int16_t* audio, long long N, int T, int tpc, int ntiles, const Tables* tab,
+                       const float* mean, const float* istd, float dc0, float dc1, const int8_t* rot, const long long* clip_off,
+                       float* out, int* flags) {
+    // once per (instantiation, device); a racing second thread at worst repeats the idempotent call
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0;
+    ADY_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!((configured.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
+        ADY_CUDA_CHECK(cudaFuncSetAttribute(fe2_foa_kernel<ROT, VIEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::total));
+        ADY_CUDA_CHECK(cudaFuncSetAttribute(fe2_foa_kernel<ROT, VIEW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
+    fe2_foa_kernel<ROT, VIEW><<<grid, NT, SmemLayout::total, stream>>>(audio, N, T, tpc, ntiles, tab, mean, istd, dc0, dc1, rot, clip_off,
+                                                                     out, flags);
+    ADY_LAUNCH_CHECK("fe2_foa_kernel");
+    return ADY_OK;
+}
+
+}  // namespace fe2
+
+int launch_features_foa_fe2(const int16_t* audio, int B, long long N, const float* mean, const float* istd, float dc_offset,
+                            const int8_t* rot, const long long* clip_off, float* out, void* ws, cudaStream_t stream) {
+    using namespace fe2;
+    const long long T = N / HOP;
+    if (B <= 0 || T <= 0) return set_error(ADY_ERR_INVALID, "features_foa: need B>0 and at least %d samples", HOP);
+    if (N <= HOP) return set_error(ADY_ERR_INVALID, "features_foa: reflect padding needs N > %d samples", HOP);
+    const Tables* tab = nullptr;
+    int rc = get_fe2_tables(&tab);
+    if (rc) return rc;
+    const long long tpc = (T + TFR - 1) / TFR;
+    const long long ntiles = (long long)B * tpc;
+    if (ntiles > 0x7fffffffLL) return set_error(ADY_ERR_INVALID, "features_foa: too many tiles");
+    int* flags = reinterpret_cast<int*>(ws);
+    ADY_CUDA_CHECK(cudaMemsetAsync(ws, 0, 16, stream));
+    int dev = 0, sms = 0;
+    ADY_CUDA_CHECK(cudaGetDevice(&dev));
+    ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = (int)(ntiles < (long long)CTAS_PER_SM * sms ? ntiles : (long long)CTAS_PER_SM * sms);
+    // window scale: 2^-15 (int16 -> [-1,1)) * 1/2 (channel split), DC terms scaled by the same 1/2
+    const float dc0 = dc_offset * 300.0f, dc1 = -dc_offset * 150.0f;
+    if (rot && clip_off)
+        return launch_inst<true, true>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, flags);
+    if (rot)
+        return launch_inst<true, false>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, flags);
+    if (clip_off)
+        return launch_inst<false, true>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, flags);
+    return launch_inst<false, false>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, flags);
+}
+
+}  // namespace ady

@@ -12,6 +12,8 @@
 // The per-(clip,channel) global max needed by librosa.power_to_db(top_db=80) (datasets.py:265)
 // is taken by clamp_topdb_kernel over the freshly written (L2-resident) log-mel planes, which
 // then rewrites only the rows that fall below max-80 dB.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "frontend_core.cuh"
 #include "frontend_host.h"
@@ -319,6 +321,15 @@ int launch_features_foa(const int16_t* audio, int B, long long N, const float* m
     const long long T = N / HOP;
     if (B <= 0 || T <= 0) return set_error(ADY_ERR_INVALID, "features_foa: need B>0 and at least %d samples", HOP);
     if (N <= HOP) return set_error(ADY_ERR_INVALID, "features_foa: reflect padding needs N > %d samples", HOP);
+    // The product path is the second-generation kernel (fe2.cu).  ADYOLO_FRONTEND=v1 selects the round-1 kernel of
+    // this file for A/B measurements (both are hand-written sm_100a kernels; neither is a fallback).
+    static const bool use_v1 = [] { const char* e = getenv("ADYOLO_FRONTEND"); return e && e[0] == 'v' && e[1] == '1'; }();
+    if (!use_v1) {
+        int rc2 = launch_features_foa_fe2(audio, B, N, mean, istd, dc_offset, rot, clip_off, out, ws, stream);
+        if (rc2) return rc2;
+        if (apply_topdb) return launch_features_foa_clamp(out, B, N, mean, istd, top_db, ws, stream);
+        return ADY_OK;
+    }
     const FrontendTables* tab = nullptr;
     int rc = get_frontend_tables(&tab);
     if (rc) return rc;

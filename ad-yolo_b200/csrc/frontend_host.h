@@ -28,6 +28,10 @@ int launch_features_foa(const int16_t* audio, int B, long long N, const float* m
                         float dc_offset, float top_db, int apply_topdb, const int8_t* rot, const long long* clip_off,
                         float* out, void* ws, cudaStream_t stream);
 
+// second-generation fused kernel (fe2.cu): FOA log-mel + IV, un-clamped; same arguments as launch_features_foa minus the clamp
+int launch_features_foa_fe2(const int16_t* audio, int B, long long N, const float* mean, const float* istd, float dc_offset,
+                            const int8_t* rot, const long long* clip_off, float* out, void* ws, cudaStream_t stream);
+
 int launch_features_mic_logmel(const int16_t* audio, int B, long long N, const float* mean, const float* istd,
                                float dc_offset, float top_db, int apply_topdb, float* out, float2* spec, void* ws,
                                cudaStream_t stream);

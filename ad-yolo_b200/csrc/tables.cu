@@ -9,6 +9,7 @@
 #include "frontend_core.cuh"
 #include "frontend_host.h"
 #include "frontend_tables.h"
+#include "fe2_tables.h"
 
 namespace ady {
 
@@ -113,6 +114,17 @@ int get_frontend_tables(const FrontendTables** dev_tables) {
         cache[dev] = d;
     }
     *dev_tables = cache[dev];
+    return ADY_OK;
+}
+
+// fe2 kernel tables (window, stage-C twiddles, balanced mel schedule): plain host code in fe2_tables.h
+int build_fe2_tables_host(fe2::Tables* t) {
+    std::vector<float> mel((size_t)fe2::NMEL * fe2::NBIN);
+    mel_filterbank_host(24000, fe2::NFFT, fe2::NMEL, mel.data());
+    fe2::MelPlan plan;
+    bool ok = false;
+    fe2::fill_tables(mel.data(), *t, plan, ok);
+    if (!ok) return set_error(ADY_ERR_INVALID, "fe2: the mel matrix does not fit %d lane-jobs of %d entries", fe2::NJOBS, fe2::MEL_L);
     return ADY_OK;
 }
 

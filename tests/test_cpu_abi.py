@@ -132,3 +132,55 @@ def test_codelets_against_numpy_fft(built):
     L.emu_fft1200(i.ctypes.data_as(ctypes.c_void_p), o.ctypes.data_as(ctypes.c_void_p))
     ref = np.fft.fft(x)
     assert np.abs((o[:, 0] + 1j * o[:, 1]) - ref).max() / np.abs(ref).max() < 1e-6
+
+
+# ---------------------------------------------------------------- second-generation kernel (fe2) on the CPU
+def _emu2():
+    L = ctypes.CDLL(os.path.join(ROOT, "build", "emu_fe2.so"))
+    L.emu_fe2_features_foa.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p]
+    return L
+
+
+@pytest.mark.parametrize("name,tol_iv", [("noise", 1e-3), ("bursts", 1e-3), ("harsh", 2.5e-3)])
+def test_emulated_fe2_kernel_matches_golden(built, gold, scaler2021, name, tol_iv):
+    """The per-thread code of the product kernel (fe2_core.cuh: staging map, 16 x 15 x 5 index maps, in-place V layout,
+    balanced mel schedule) run thread by thread on the CPU against the reference-derived golden features."""
+    g = gold("features_foa.npz")
+    clip = np.ascontiguousarray(g[f"{name}_audio"])
+    N = len(clip); T = N // 600
+    mel = built.mel_filterbank(24000, 1200, 64).copy()
+    mean = np.concatenate([scaler2021["MEL"]["mean"][0].T, scaler2021["IV"]["mean"][0].T], 0).astype(np.float32)
+    istd = (1.0 / np.concatenate([scaler2021["MEL"]["std"][0].T, scaler2021["IV"]["std"][0].T], 0)).astype(np.float32)
+    out = np.zeros((1, 7, T, 64), np.float32)
+    cost = (ctypes.c_long * 2)()
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    assert _emu2().emu_fe2_features_foa(vp(clip), 1, N, vp(mel), vp(mean), vp(istd), 1e-8, 80.0, None, vp(out), cost) == 0
+    ref = np.concatenate([g[f"{name}_MEL"].transpose(2, 0, 1), g[f"{name}_IV"].transpose(2, 0, 1)], 0)
+    assert (np.abs(out[0, :4] - ref[:4]) / np.maximum(np.abs(ref[:4]), 1.0)).max() < 1e-4
+    assert np.abs(out[0, 4:] - ref[4:]).max() < tol_iv
+    assert np.abs((out[0, 4:] - ref[4:]) / istd[4:, None, :]).max() < RAW_IV_TOL
+    assert cost[0] <= 2 * cost[1]          # mel gather: at most 2x the conflict-free wavefront count
+
+
+def test_emulated_fe2_ragged_batch_and_rotation(built):
+    """Odd frame count (last tile holds one frame), several clips, raw output, and the 16 rotation combinations
+    (channel signs / swap applied inside the kernel) against the oracle on explicitly rotated audio."""
+    from oracle import augment_np
+    rng = np.random.default_rng(6)
+    B, N = 16, 600 * 7 + 321
+    clips = np.clip(rng.standard_normal((B, N, 4)) * 2000, -32767, 32767).astype(np.int16)
+    clips[:, :900] = 0
+    T = N // 600
+    mel = built.mel_filterbank(24000, 1200, 64).copy()
+    out = np.zeros((B, 7, T, 64), np.float32)
+    bits = np.array([[0x0, 0x2, 0x1, 0x3, 0x5, 0x7, 0x4, 0x6, 0x9, 0xB, 0x8, 0xA, 0xC, 0xE, 0xD, 0xF][c] for c in range(16)], np.uint8)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    assert _emu2().emu_fe2_features_foa(vp(clips), B, N, vp(mel), None, None, 1e-8, 80.0, vp(bits), vp(out), None) == 0
+    for b in range(B):
+        rot, _ = augment_np.rotate(clips[b], {}, b)
+        ref = F.features_foa_stack(rot)
+        assert ref.shape == (7, T, 64)
+        assert (np.abs(out[b, :4] - ref[:4]) / np.maximum(np.abs(ref[:4]), 1.0)).max() < 1e-4, b
+        assert np.abs(out[b, 4:] - ref[4:]).max() < 1e-6, b
