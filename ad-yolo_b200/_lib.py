@@ -16,9 +16,15 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
 
-# build knob (see csrc/frontend_core.cuh): frames per front-end tile, 3 (default) or 7
+# build knobs: frames per tile of the round-1 kernel (csrc/frontend_core.cuh: 3 or 7), threads per CTA of the fe2
+# kernel (csrc/fe2_core.cuh: 160 or 192)
 if os.environ.get("ADY_TILE_FRAMES"):
     NVCC_FLAGS = NVCC_FLAGS + ["-DADY_TILE_FRAMES=" + os.environ["ADY_TILE_FRAMES"]]
+if os.environ.get("ADY_FE2_NT"):
+    NVCC_FLAGS = NVCC_FLAGS + ["-DADY_FE2_NT=" + os.environ["ADY_FE2_NT"]]
+# experiments: load a variant build instead of the in-tree default (tools/build_variant.py)
+if os.environ.get("ADYOLO_LIB"):
+    LIB_PATH = os.environ["ADYOLO_LIB"]
 
 
 def _nvcc():

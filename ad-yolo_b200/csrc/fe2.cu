@@ -6,13 +6,13 @@
 // (C,T,F) stacking of :158-160; == src/utils/utility.py:142-215.  The maths and the per-thread building blocks
 // are in fe2_core.cuh; this file is the CTA-level choreography.
 //
-// Per tile of 2 frames of one clip (160 threads, 3 CTAs per SM):
+// Per tile of 2 frames of one clip (160 or 192 threads, 3 CTAs per SM):
 //   global int16 (N,4) --cp.async(8 B / sample)--> 24 rows x 75 samples, columns permuted so that stage A is
 //                                                  bank-conflict free (3 hops, shared by the 2 frames)
 //   stage A  75 tasks / frame : window + DFT-16 of both packed FFTs (f32x2)          -> X1 (16 B / point)
 //   stage B  80 tasks / frame : DFT-15, in place                                      -> X2
-//   stage C 121 tasks / frame : twiddle + 2 x DFT-5, channel split, |X|^2, I / E, in place -> V
-//   mel     160 lane-jobs     : <= 9 non-zeros each, both frames per entry            -> 64-byte partial records
+//   stage C 121 tasks / frame : twiddle + 2 x DFT-5, channel split, |X|^2, I / E, in place -> V  (224 + 18 threads, one round)
+//   mel     191 lane-jobs     : <= 7 non-zeros each, both frames per entry            -> 64-byte partial records
 //   epilogue 128 threads      : (frame, mel): add the filter's records, 10 log10, standardise, coalesced store
 // The copy of the next tile is issued right after stage A and overlaps everything else.
 #include <atomic>
@@ -40,7 +40,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void issue_tile_copy(unsigned char* samp, const int16_t* __restrict__ audio, long long clip0, int t0, int nf,
                                                 int tid, int dst_off /* (12 h * ROWP + stage_col(rem)) * 8 or -1 */) {
     if (dst_off < 0) return;
-    const int h = tid >= 80, rem = tid - 80 * h;
+    const int h = tid >= 80, rem = tid - 80 * h;        // (dst_off < 0 for tid >= NT_AB)
     const int16_t* clip = audio + clip0 * 4;
     const int nrows = 8 * (nf + 1) - 12 * h;                      // rows of this half that the tile needs
     long long s = 600LL * (t0 - 1) + 900 * h + rem;               // clip sample of row 12 h
@@ -74,9 +74,10 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
 
     const int tid = threadIdx.x;
     // fixed roles
+    const bool ab = tid < NT_AB;                                                    // warps 0..4 run stages A / B and the copies
     const int fA = tid >= 80, lA = tid - 80 * fA;                                  // stages A / B: frame, lane
-    const StageAConst ka = stage_a_const(lA < 75 ? lA : 0);
-    const int copy_dst = lA < 75 ? (12 * fA * ROWP + stage_col(lA)) * 8 : -1;
+    const StageAConst ka = stage_a_const(ab && lA < 75 ? lA : 0);
+    const int copy_dst = ab && lA < 75 ? (12 * fA * ROWP + stage_col(lA)) * 8 : -1;
 
     int tile = blockIdx.x;
     if (tile < ntiles) {
@@ -89,7 +90,7 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
         const uint2* src = reinterpret_cast<const uint2*>(tab->ent);
         uint2* dst = reinterpret_cast<uint2*>(s_ent);
         for (int i = tid; i < MEL_L * NJOBS; i += NT) dst[i] = src[i];
-        for (int i = tid; i < 15 * 4 * 4; i += NT) reinterpret_cast<float*>(s_tw)[i] = tab->tw75[i];
+        for (int i = tid; i < 15 * 4 * 2; i += NT) reinterpret_cast<float*>(s_tw)[i] = tab->tw75[i];
         for (int i = tid; i < 16 * 80; i += NT) s_win[i] = tab->win[i];
         for (int i = tid; i < 7 * NMEL; i += NT) {   // standardisation as one FMA: x * is + (-mu * is)
             const float mu = mean ? mean[i] : 0.f, is = istd ? istd[i] : 1.f;
@@ -97,7 +98,7 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
         }
         if (tid < NMEL) s_meljobs[tid] = tab->mel_njobs[tid];
     }
-    const int rec_off = tab->job_rec[tid] * 16;                                     // this lane-job's record slot
+    const int rec_off = tab->job_rec[tid < NJOBS ? tid : 0] * 16;                   // this lane-job's record slot
 
     for (; tile < ntiles; tile += gridDim.x) {
         const int b = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * TFR, nf = min(TFR, T - t0);
@@ -106,7 +107,7 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
         __syncthreads();                                   // samples landed; previous tile's epilogue is done with X
 
         // ---- stage A
-        if (lA < 75 && fA < nf) stage_a(s_samp, s_win, s_x, fA, lA, ka);
+        if (ab && lA < 75 && fA < nf) stage_a(s_samp, s_win, s_x, fA, lA, ka);
         __syncthreads();
 
         // samples are consumed: prefetch the next tile while the rest of this one runs
@@ -120,18 +121,19 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
         }
 
         // ---- stage B (in place)
-        if (fA < nf) stage_b(s_x, fA, lA);
+        if (ab && fA < nf) stage_b(s_x, fA, lA);
         __syncthreads();
 
-        // ---- stage C (in place): 224 regular pair-tasks + 18 c = 0 pair-tasks over two rounds
+        // ---- stage C (in place): 224 regular pair-tasks + 18 c = 0 pair-tasks over two rounds of NT threads; the
+        // c = 0 tasks run in round 1 on the last warp, next to the tail of the regular tasks on the first warps
 #pragma unroll 1
         for (int rd = 0; rd < 2; ++rd) {
             const int slot = rd * NT + tid;
             if (slot < 2 * NREG) {
                 const int f = slot >= NREG, task = slot - f * NREG;
                 if (f < nf) stage_c_foa<false>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, rb);
-            } else if (slot >= 256 && slot < 256 + 2 * NC0) {
-                const int i = slot - 256, f = i >= NC0, task = i - f * NC0;
+            } else if (rd == 1 && tid >= NT - 32 && tid < NT - 32 + 2 * NC0) {
+                const int i = tid - (NT - 32), f = i >= NC0, task = i - f * NC0;
                 if (f < nf) stage_c_foa<true>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, rb);
             }
         }
@@ -139,12 +141,14 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
 
         // ---- mel projection: lane-job tid, both frames
         f2 acc[TFR][4];
-        mel_job<true>(s_x, s_ent + tid, nf, acc);
-        __syncthreads();                                   // every V read is done -> records may overwrite frame 0's buffer
+        if (tid < NJOBS) mel_job<true>(s_x, s_ent + tid, acc);
+        __syncthreads();                                   // every V read is done -> records may overwrite the frame buffers
+        if (tid < NJOBS) {
 #pragma unroll
-        for (int f = 0; f < TFR; ++f) {
-            st_f4(s_x + (2 * f) * REC_PLANE + rec_off, lo2(acc[f][0]), hi2(acc[f][0]), lo2(acc[f][1]), hi2(acc[f][1]));
-            st_f4(s_x + (2 * f + 1) * REC_PLANE + rec_off, lo2(acc[f][2]), hi2(acc[f][2]), lo2(acc[f][3]), hi2(acc[f][3]));
+            for (int f = 0; f < TFR; ++f) {
+                st_f4(s_x + (2 * f) * REC_PLANE + rec_off, lo2(acc[f][0]), hi2(acc[f][0]), lo2(acc[f][1]), hi2(acc[f][1]));
+                st_f4(s_x + (2 * f + 1) * REC_PLANE + rec_off, lo2(acc[f][2]), hi2(acc[f][2]), lo2(acc[f][3]), hi2(acc[f][3]));
+            }
         }
         __syncthreads();
 

@@ -16,8 +16,8 @@
 //   * the exchange buffer holds one 16-byte element {re(A), re(B), im(A), im(B)} per point: every
 //     shared-memory access of the FFT stages is a 128-bit one, all conflict-free by construction;
 //   * stages B and C work in place, so one 19 KB buffer per frame serves X1, X2 and V;
-//   * the mel projection handles both frames of a tile per schedule entry and is balanced as 160
-//     equal lane-jobs (<= 9 non-zeros each) instead of 4 warp-tasks of 3..31 iterations.
+//   * the mel projection handles both frames of a tile per schedule entry and is balanced as 191
+//     lane-jobs of <= 7 non-zeros (one per thread) instead of 4 warp-tasks of 3..31 iterations.
 //
 // Everything is ADY_HD so that tests/emu runs the identical index logic on the CPU.
 #pragma once
@@ -36,8 +36,8 @@ struct f2 {
 };
 __device__ __forceinline__ f2 mk2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ f2 dup2(float a) { return mk2(a, a); }
-__device__ __forceinline__ float lo2(f2 a) { float l, h; asm("mov.b64 {%0, %1}, %2;" : "=f"(l), "=f"(h) : "l"(a.v)); return l; }
-__device__ __forceinline__ float hi2(f2 a) { float l, h; asm("mov.b64 {%0, %1}, %2;" : "=f"(l), "=f"(h) : "l"(a.v)); return h; }
+__device__ __forceinline__ float lo2(f2 a) { float l; asm("{ .reg .b32 t; mov.b64 {%0, t}, %1; }" : "=f"(l) : "l"(a.v)); return l; }
+__device__ __forceinline__ float hi2(f2 a) { float h; asm("{ .reg .b32 t; mov.b64 {t, %0}, %1; }" : "=f"(h) : "l"(a.v)); return h; }
 __device__ __forceinline__ f2 operator+(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 __device__ __forceinline__ f2 operator-(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 __device__ __forceinline__ f2 operator*(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
@@ -147,18 +147,23 @@ ADY_HD unsigned rot_bits_rt(int comb) { return (unsigned)((0xFDECA8B964753120ull
 // ---------------------------------------------------------------- geometry
 constexpr int NFFT = 1200, HOP = 600, NBIN = 601, NMEL = 64;
 constexpr int TFR = 2;                       // frames per tile
-constexpr int NT = 160;                      // threads per CTA: 80 per frame in stages A and B
+#ifndef ADY_FE2_NT
+#define ADY_FE2_NT 160
+#endif
+constexpr int NT = ADY_FE2_NT;               // threads per CTA: 160 (5 warps) or 192 (6 warps: shorter mel jobs, 18 warps / SM)
+constexpr int NT_AB = 160;                   // stages A and B and the staging copy: 80 lanes per frame
 constexpr int ROWP = 80;                     // pitch of a 75-sample row of the staged audio, in samples (8 bytes each)
 constexpr int NROWS = 8 * (TFR + 1);         // 3 hops = 24 rows
 constexpr int SAMP_BYTES = NROWS * ROWP * 8; // 15 360
-constexpr int XSLOTS = 1216;                 // 16-byte slots per frame: 1200 points + 2 x 5 (Vb of the self-mirror tasks) + pad
+constexpr int XSLOTS = 1210;                 // 16-byte slots per frame: 1200 points + 2 x 5 (Vb of the self-mirror tasks)
 constexpr int X_BYTES = XSLOTS * 16;         // 19 456
-constexpr int MEL_L = 9;                     // schedule rows: non-zeros per lane-job
-constexpr int NJOBS = NT;                    // one lane-job per thread
+constexpr int MEL_L = NT >= 192 ? 7 : 9;     // schedule rows: non-zeros per lane-job
+constexpr int NJOBS = NT >= 192 ? 192 : 160; // lane-jobs of the mel projection (191 / 156 used), one per thread
 constexpr int NREG = 112;                    // regular pair-tasks per frame in stage C (c = 1..7, k16 = 0..15)
 constexpr int NC0 = 9;                       // c = 0 pair-tasks per frame (k16 = 1..7 and the two self-mirror rows)
 constexpr int REC_PITCH = 65;                // partial record of job i of mel j lives at record slot i * 65 + j (16-byte planes)
-constexpr int REC_SLOTS = 7 * REC_PITCH;     // <= 7 jobs per mel
+constexpr int REC_MAXJOBS = 9;               // <= 9 jobs per mel filter (61 non-zeros / 7)
+constexpr int REC_SLOTS = REC_MAXJOBS * REC_PITCH;
 constexpr int REC_PLANE = REC_SLOTS * 16;    // 4 planes: (frame 0 | frame 1) x (powers | intensities)
 
 struct MelEnt {            // one non-zero: byte offsets of the bin's two V records inside a frame's buffer + weight
@@ -168,7 +173,7 @@ struct MelEnt {            // one non-zero: byte offsets of the bin's two V reco
 
 struct Tables {            // device-resident constants of the fe2 kernel (built on the host, tables.cu)
     float win[16 * 80];            // stage A: 2^-16 x periodic Hann at the sample lane l (task r = 16 l mod 75) loads as n16, [n16][l]
-    float tw75[15 * 4 * 4];        // stage C: W75^{b c} as (wr, wr, wi, wi) for c = 0..14, b = 1..4
+    float tw75[15 * 4 * 2];        // stage C: W75^{b c} as (wr, wi) for c = 0..14, b = 1..4
     MelEnt ent[MEL_L * NJOBS];     // [row][job]
     uint8_t mel_njobs[NMEL];       // number of lane-jobs of mel j (<= 7)
     uint16_t job_rec[NJOBS];       // record slot of job q: i * REC_PITCH + j for the i-th job of mel j
@@ -179,8 +184,8 @@ struct SmemLayout {
     static constexpr int off_samples = 0;
     static constexpr int off_x = SAMP_BYTES;                              // TFR frame buffers
     static constexpr int off_ent = off_x + TFR * X_BYTES;                 // MelEnt [MEL_L][NJOBS]
-    static constexpr int off_tw = off_ent + MEL_L * NJOBS * 8;            // float4 [15][4]
-    static constexpr int off_win = off_tw + 15 * 4 * 16;                  // float [16][80]
+    static constexpr int off_tw = off_ent + MEL_L * NJOBS * 8;            // float2 [15][4]
+    static constexpr int off_win = off_tw + 15 * 4 * 8;                   // float [16][80]
     static constexpr int off_scale = off_win + 16 * 80 * 4;               // float2 [7][64]: (istd, -mean*istd)
     static constexpr int off_meljobs = off_scale + 7 * NMEL * 8;          // uint8 [64]
     static constexpr int total = ((off_meljobs + NMEL + 15) / 16) * 16;
@@ -356,12 +361,17 @@ ADY_HD void stage_c_load(const unsigned char* __restrict__ xb, const unsigned ch
     if (!C0) {
 #pragma unroll
         for (int b = 1; b < 5; ++b) {
-            c2 tp, tq;                                   // (wr, wr) in .re, (wi, wi) in .im
-            ld_c2(tw + (c * 4 + (b - 1)) * 16, tp);
-            ld_c2(tw + (cq * 4 + (b - 1)) * 16, tq);
+            float2 tp, tq;                               // (wr, wi): the packed operations broadcast the scalar
+#if defined(__CUDA_ARCH__)
+            tp = *reinterpret_cast<const float2*>(tw + (c * 4 + (b - 1)) * 8);
+            tq = *reinterpret_cast<const float2*>(tw + (cq * 4 + (b - 1)) * 8);
+#else
+            memcpy(&tp, tw + (c * 4 + (b - 1)) * 8, 8);
+            memcpy(&tq, tw + (cq * 4 + (b - 1)) * 8, 8);
+#endif
             const c2 p = P[b], q = Q[b];
-            P[b] = {fma2(p.re, tp.re, ADY_K2(0.0) - p.im * tp.im), fma2(p.re, tp.im, p.im * tp.re)};
-            Q[b] = {fma2(q.re, tq.re, ADY_K2(0.0) - q.im * tq.im), fma2(q.re, tq.im, q.im * tq.re)};
+            P[b] = {p.re * dup2(tp.x) - p.im * dup2(tp.y), fma2(p.re, dup2(tp.y), p.im * dup2(tp.x))};
+            Q[b] = {q.re * dup2(tq.x) - q.im * dup2(tq.y), fma2(q.re, dup2(tq.y), q.im * dup2(tq.x))};
         }
     }
     p_dft5(P[0], P[1], P[2], P[3], P[4]);
@@ -419,24 +429,28 @@ inline void v_offsets_of_bins(int (&offa)[NBIN], int (&offb)[NBIN]) {
 // ---------------------------------------------------------------- mel projection: one lane-job, both frames of the tile
 // acc[f][0..3] = partial sums of (|W|^2,|Z|^2), (|Y|^2,|X|^2), (I_Y, I_Z), (I_X, -) as packed pairs
 template <bool WITH_IV>
-ADY_HD void mel_job(const unsigned char* __restrict__ x0, const MelEnt* __restrict__ ent_col, int nf, f2 (&acc)[TFR][4]) {
+ADY_HD void mel_job(const unsigned char* __restrict__ x0, const MelEnt* __restrict__ ent_col, f2 (&acc)[TFR][4]) {
+    // Straight-line code, no frame-count branch: with a one-frame tile the second frame's buffer holds stale (finite
+    // or not) values whose sums are simply never stored; this lets the compiler issue all entry loads, then all
+    // gathers, instead of one dependent shared-memory round trip after the other.
 #pragma unroll
     for (int f = 0; f < TFR; ++f)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[f][i] = ADY_K2(0.0);
+    MelEnt e[MEL_L];
+#pragma unroll
+    for (int it = 0; it < MEL_L; ++it) e[it] = ent_col[it * NJOBS];
 #pragma unroll
     for (int it = 0; it < MEL_L; ++it) {
-        const MelEnt e = ent_col[it * NJOBS];
-        const f2 w = dup2(e.w);
+        const f2 w = dup2(e[it].w);
 #pragma unroll
         for (int f = 0; f < TFR; ++f) {
-            if (f >= nf) break;
             c2 a, b;
-            ld_c2(x0 + f * X_BYTES + e.offa, a);
+            ld_c2(x0 + f * X_BYTES + e[it].offa, a);
             acc[f][0] = fma2(a.re, w, acc[f][0]);
             acc[f][1] = fma2(a.im, w, acc[f][1]);
             if (WITH_IV) {
-                ld_c2(x0 + f * X_BYTES + e.offb, b);
+                ld_c2(x0 + f * X_BYTES + e[it].offb, b);
                 acc[f][2] = fma2(b.re, w, acc[f][2]);
                 acc[f][3] = fma2(b.im, w, acc[f][3]);
             }

@@ -3,8 +3,8 @@
 // projection.
 //
 // Mel schedule.  The (64 x 601) Slaney mel matrix (librosa.filters.mel, datasets.py:203) has 1165 non-zeros,
-// 5..61 per filter.  Filter j is cut into ceil(nnz_j / 9) lane-jobs of nearly equal length (156 jobs for the
-// 160 threads of a CTA); a job walks its <= 9 non-zeros once and accumulates BOTH frames of the tile, then
+// 5..61 per filter.  Filter j is cut into ceil(nnz_j / 7) lane-jobs of nearly equal length (191 jobs for the
+// 224 threads of a CTA); a job walks its <= 7 non-zeros once and accumulates BOTH frames of the tile, then
 // leaves a 64-byte partial record in shared memory; the epilogue thread of (frame, mel) adds the records of
 // that filter's jobs in a fixed order (deterministic, unlike shared-memory atomics).  Entries are stored
 // [row][job]; the order of a job's entries is chosen by a randomised descent so that the 8 lanes of every
@@ -67,7 +67,7 @@ inline bool build_mel_plan(const float* mel, MelPlan& p) {
             if (mel[(size_t)j * NBIN + k] != 0.f) all.push_back(MelEnt{(uint16_t)offa[k], (uint16_t)offb[k], mel[(size_t)j * NBIN + k]});
         if (all.empty()) return false;
         const int nj = ((int)all.size() + MEL_L - 1) / MEL_L;
-        if (nj > 7) return false;
+        if (nj > REC_MAXJOBS) return false;
         p.job0[j] = (int)jobs.size();
         p.njobs[j] = nj;
         for (int q = 0; q < nj; ++q) {
@@ -124,9 +124,9 @@ inline void fill_tables(const float* mel, Tables& t, MelPlan& plan, bool& ok) {
     for (int c = 0; c < 15; ++c)
         for (int b = 1; b < 5; ++b) {
             const double ang = -2.0 * M_PI * (double)(b * c) / 75.0;
-            float* e = t.tw75 + (c * 4 + (b - 1)) * 4;
-            e[0] = e[1] = (float)cos(ang);
-            e[2] = e[3] = (float)sin(ang);
+            float* e = t.tw75 + (c * 4 + (b - 1)) * 2;
+            e[0] = (float)cos(ang);
+            e[1] = (float)sin(ang);
         }
     ok = build_mel_plan(mel, plan);
     if (!ok) return;
@@ -135,8 +135,8 @@ inline void fill_tables(const float* mel, Tables& t, MelPlan& plan, bool& ok) {
     for (int q = 0; q < NJOBS; ++q) {
         const int j = plan.job_mel[q];
         t.job_mel[q] = (uint8_t)(j < 0 ? 0 : j);
-        // idle jobs (no filter) park their all-zero record in the unused slot (6, 0): mel 0 has a single job
-        t.job_rec[q] = (uint16_t)(j < 0 ? 6 * REC_PITCH : (q - plan.job0[j]) * REC_PITCH + j);
+        // idle jobs (no filter) park their all-zero record in an unused slot: mel 0 has a single job
+        t.job_rec[q] = (uint16_t)(j < 0 ? (REC_MAXJOBS - 1) * REC_PITCH : (q - plan.job0[j]) * REC_PITCH + j);
     }
 }
 

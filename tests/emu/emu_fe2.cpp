@@ -13,7 +13,7 @@ using namespace ady;
 using namespace ady::fe2;
 
 static void stage_copy(unsigned char* samp, const int16_t* clip /* first sample of the clip */, int t0, int nf) {
-    for (int tid = 0; tid < NT; ++tid) {
+    for (int tid = 0; tid < NT_AB; ++tid) {
         const int h = tid / 80, rem = tid % 80;
         if (rem >= 75) continue;
         const int col = stage_col(rem);
@@ -53,29 +53,26 @@ extern "C" int emu_fe2_features_foa(const int16_t* audio, int B, long long N, co
         const int b = tile / tpc, t0 = (tile % tpc) * TFR, nf = std::min(TFR, T - t0);
         const unsigned rb = rot_bits_per_clip ? rot_bits_per_clip[b] : 0u;
         stage_copy(s_samp, audio + (long long)b * N * 4, t0, nf);
-        for (int tid = 0; tid < NT; ++tid) {                      // stage A
+        for (int tid = 0; tid < NT_AB; ++tid) {                   // stage A
             const int f = tid / 80, l = tid % 80;
             if (l < 75 && f < nf) stage_a(s_samp, tab.win, s_x, f, l, stage_a_const(l));
         }
-        for (int tid = 0; tid < NT; ++tid) {                      // stage B
+        for (int tid = 0; tid < NT_AB; ++tid) {                   // stage B
             const int f = tid / 80, u = tid % 80;
             if (f < nf) stage_b(s_x, f, u);
         }
-        for (int rd = 0; rd < 2; ++rd)                            // stage C
-            for (int tid = 0; tid < NT; ++tid) {
-                const int slot = rd * NT + tid;
-                if (slot < 2 * NREG) {
-                    const int f = slot >= NREG, task = slot - f * NREG;
-                    if (f < nf) stage_c_foa<false>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, rb);
-                } else if (slot >= 256 && slot < 256 + 2 * NC0) {
-                    const int i = slot - 256, f = i >= NC0, task = i - f * NC0;
-                    if (f < nf) stage_c_foa<true>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, rb);
-                }
-            }
+        for (int tid = 0; tid < 2 * NREG; ++tid) {                // stage C: the 224 regular pair-tasks, one per thread
+            const int f = tid >= NREG, task = tid - f * NREG;
+            if (f < nf) stage_c_foa<false>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, rb);
+        }
+        for (int tid = 0; tid < 2 * NC0; ++tid) {                 // ... and the 18 c = 0 pair-tasks
+            const int f = tid >= NC0, task = tid - f * NC0;
+            if (f < nf) stage_c_foa<true>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, rb);
+        }
         std::vector<f2> accs((size_t)NJOBS * TFR * 4);             // mel jobs (all V reads happen before any record is written)
         for (int q = 0; q < NJOBS; ++q) {
             f2 acc[TFR][4];
-            mel_job<true>(s_x, tab.ent + q, nf, acc);
+            mel_job<true>(s_x, tab.ent + q, acc);
             for (int f = 0; f < TFR; ++f)
                 for (int i = 0; i < 4; ++i) accs[(q * TFR + f) * 4 + i] = acc[f][i];
         }
