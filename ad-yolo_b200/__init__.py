@@ -15,7 +15,7 @@ Mirrors (same names / argument meaning) of the reference call surface, SURVEY.md
 * ``augment.SpecAug`` (src/utils/augmentations.py:6-33); rotation is fused into features / labels
 """
 from . import _lib  # noqa: F401
-from .features import (FeatureLabelProcessor, audio2stft, stft2melscale, stft2iv,  # noqa: F401
+from .features import (FeatureLabelProcessor, FrontEndModule, audio2stft, stft2melscale, stft2iv,  # noqa: F401
                        features_batched, mel_filterbank)
 from .labels import DeviceRows, get_yolo_label, collate_fn, label_rows_batched  # noqa: F401
 from .loss import ADYOLOloss, WrapperCriterion, adyolo_assign  # noqa: F401
@@ -23,7 +23,7 @@ from .scaler import ScalerAccumulator, preprocess_scaler  # noqa: F401
 from .pipeline import HostBatchPipeline, bind_host_to_device  # noqa: F401
 from .postprocess import LabelPostProcessor, yolo_post_batched  # noqa: F401
 from .augment import RotationAug, SpecAug  # noqa: F401
-from .data import (ResidentClips, EpochSampler, chunk_plan, features_batched_views,  # noqa: F401
-                   load_wav2npy, load_csv2dict)
+from .data import (ResidentClips, EpochSampler, RawAudioDataset, collate_raw, chunk_plan,  # noqa: F401
+                   features_batched_views, load_wav2npy, load_csv2dict)
 
 __version__ = "0.1.0"

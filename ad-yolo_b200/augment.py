@@ -28,6 +28,9 @@ from . import _lib
 from ._lib import check, ptr, require_cuda, stream_ptr
 
 FOA_GROUPS = ((0, 4), (4, 7))       # [mel W,Y,Z,X | iv Y,Z,X]   datasets.py:158-161
+# RotationAug combination number (augmentations.py:46-70) -> bit0 = Y negated, bit1 = Z negated, bit2 = X negated,
+# bit3 = X <-> Y swap (the same table the kernels use, csrc/fe2_core.cuh::rot_bits_rt)
+ROT_BITS = (0x0, 0x2, 0x1, 0x3, 0x5, 0x7, 0x4, 0x6, 0x9, 0xB, 0x8, 0xA, 0xC, 0xE, 0xD, 0xF)
 MIC_GROUPS = ((0, 4), (4, 10))      # [mel x4 | gcc x6]
 
 
@@ -48,6 +51,29 @@ class RotationAug(object):
             return None
         comb = [int(random.uniform(0, 16)) for _ in range(n_clips)]
         return torch.tensor(comb, dtype=torch.int8).to(device, non_blocking=True)
+
+
+def rotate_host(audio_i16, events, comb_no: int):
+    """``RotationAug._rotate`` (augmentations.py:84-111) on the host for one clip: int16 (N, 4) FOA audio W,Y,Z,X
+    and the event table (E, 4) [frame, class, azi, ele] -> rotated copies.  numpy, a few hundred microseconds per
+    clip; used by ``RawAudioDataset`` inside DataLoader workers (the fused device form is ``rot_comb=``).  The int16
+    product wraps for -32768 exactly as the reference's numpy multiplication does."""
+    import numpy as np
+    bits = ROT_BITS[int(comb_no) & 15]
+    a = np.array(audio_i16, dtype=np.int16, copy=True)
+    if bits & 1: a[:, 1] = (a[:, 1] * np.int16(-1)).astype(np.int16)          # Y
+    if bits & 2: a[:, 2] = (a[:, 2] * np.int16(-1)).astype(np.int16)          # Z
+    if bits & 4: a[:, 3] = (a[:, 3] * np.int16(-1)).astype(np.int16)          # X
+    if bits & 8: a[:, [1, 3]] = a[:, [3, 1]]                                   # X <-> Y
+    ev = np.array(events, dtype=np.float64, copy=True).reshape(-1, 4)
+    if len(ev):
+        pw = -1.0 if comb_no & 2 else 1.0
+        dpi = (0.0, 180.0, 90.0, -90.0)[(comb_no >> 2) & 3]
+        tw = -1.0 if comb_no & 1 else 1.0
+        az = ev[:, 2] * pw + dpi
+        az = np.where(az < -180.0, az + 360.0, np.where(az > 180.0, az - 360.0, az))
+        ev[:, 2], ev[:, 3] = az, ev[:, 3] * tw
+    return a, ev
 
 
 class SpecAug(object):

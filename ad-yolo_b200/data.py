@@ -187,6 +187,91 @@ def _take(pool: list, picks: list) -> list:
     return kept
 
 
+class RawAudioDataset(torch.utils.data.Dataset):
+    """Drop-in for the reference ``datasets.Dataset`` (datasets.py:21-162) on the B200 path: same constructor
+    (``params, set_type, is_valid``), same directory layout, file listing, epoch sampling and checkpoint hooks,
+    same attributes the orchestration reads (``loss_nm``, ``get_filelist()``) -- but ``__getitem__`` stops before
+    the arithmetic: DataLoader workers cannot use CUDA, so an item is the raw material of the hot path,
+
+        (audio int16 (N, 4) tensor, events float64 (E, 4) tensor [frame, class, azi, ele])
+
+    and ``collate_raw`` stacks it.  Features, label rows and the loss then run on the device
+    (``FrontEndModule`` in front of the encoder, ``ADYOLOloss`` accepting the event table), which is what lets the
+    reference's own ``train_one_epoch`` / ``test_epoch`` (train.py:44-60, test.py:33-60) run unchanged.
+
+    Rotation augmentation: applied here, on the int16 clip and the event table, with the reference's draw
+    (``int(random.uniform(0, 16))``, augmentations.py:93) -- per-item host work of a few hundred microseconds; the
+    fused device variant (``features_batched(rot_comb=)``) is for pipelines that own their training loop."""
+
+    def __init__(self, params: dict, set_type: str, is_valid: bool = False):
+        import os
+        from .augment import RotationAug
+        dc, self.params = params["data_config"], params
+        self.is_valid, self.is_infer, self.set_type = is_valid, set_type == "infer", set_type
+        self.loss_nm = params["args"]["loss"]
+        if self.loss_nm != "adyolo":
+            raise NotImplementedError("loss: {} (only --loss adyolo is on the B200 hot path)".format(self.loss_nm))
+        opj = os.path.join
+        if set_type == "train":                                   # datasets.py:36-49
+            sub = "dev-train-chunked_{}s_{}s".format(dc["chunk_window_s"], dc["chunk_stride_s"])
+            self.wav_pth, self.csv_pth = opj(dc["data_pth"], "foa_dev", sub), opj(dc["data_pth"], "metadata_dev", sub)
+            names = [f.replace(".wav", "") for f in os.listdir(self.wav_pth)]
+            self.sampler = EpochSampler(names, params["train_config"]["batch_size"] * params["train_config"]["nb_iters"])
+            self.sampler.sample_filelist_for_train_iter()
+        else:                                                     # datasets.py:50-58
+            if self.is_infer:
+                self.wav_pth, self.csv_pth = str(params["args"]["infer_pth"]), None
+            else:
+                self.wav_pth = opj(dc["data_pth"], "foa_dev", "dev-{}".format(set_type))
+                self.csv_pth = opj(dc["data_pth"], "metadata_dev", "dev-{}".format(set_type))
+            self.sampler = None
+            self._filelist = [f.replace(".wav", "") for f in os.listdir(self.wav_pth)]
+        self.rotation = RotationAug(params, is_valid)
+
+    # ---- the orchestration's hooks (train.py:150,176,247; test.py:36)
+    @property
+    def filelist(self):
+        return self.sampler.filelist if self.sampler is not None else self._filelist
+
+    def sample_filelist_for_train_iter(self):
+        return self.sampler.sample_filelist_for_train_iter()
+
+    def init_remaining_file_from_list(self, remaining_file):
+        self.sampler.init_remaining_file_from_list(remaining_file)
+
+    def get_remaining_file(self):
+        return self.sampler.get_remaining_file()
+
+    def get_filelist(self):
+        return self.filelist
+
+    def __len__(self):
+        return len(self.filelist)
+
+    def __getitem__(self, index):
+        import os
+        name = self.filelist[index]
+        audio = np.ascontiguousarray(load_wav2npy(os.path.join(self.wav_pth, name + ".wav")), dtype=np.int16)
+        label = {} if self.is_infer else load_csv2dict(os.path.join(self.csv_pth, name + ".csv"))
+        ev = np.asarray([[fr, e[0], e[2], e[3]] for fr, evs in label.items() for e in evs], dtype=np.float64).reshape(-1, 4)
+        if self.rotation.apply_augment:
+            from .augment import rotate_host
+            audio, ev = rotate_host(audio, ev, int(random.uniform(0, 16)))
+        return torch.from_numpy(audio), torch.from_numpy(ev)
+
+
+def collate_raw(batch):
+    """collate_fn of the raw-audio path (mirror of datasets.py:164-184): items (audio (N,4) int16, events (E,4)) ->
+    (audio (B, N, 4) int16, events (E_total, 5) float32 [batch, frame, class, azi, ele]).  float32 is exact for the
+    integer-degree DCASE labels and survives the ``label.to(device).float()`` of train.py:48.  Like the reference
+    (torch.cat of an empty list, datasets.py:184) it raises when no clip of the batch has an event."""
+    audio, events = zip(*batch)
+    rows = [torch.cat([torch.full((len(e), 1), float(i), dtype=torch.float64), e], dim=1) for i, e in enumerate(events) if len(e)]
+    if not rows:
+        raise RuntimeError("collate_raw: no events in the batch (the reference's collate_fn raises here too)")
+    return torch.stack(audio, 0), torch.cat(rows, 0).to(torch.float32)
+
+
 class EpochSampler:
     """Without-replacement epoch sampling of the reference Dataset (datasets.py:67-98): every epoch
     draws ``nb_samples`` names from a pool that survives across epochs (and checkpoints); when the

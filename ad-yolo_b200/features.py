@@ -21,7 +21,7 @@ from . import _lib
 from ._lib import FrontendCfg, check, ptr, require_cuda, stream_ptr
 
 _SCALER_KEYS = ("MEL", "IV")
-FRONTEND_KERNEL = "frontend_foa_kernel"     # name of the fused front-end kernel (bench.py's roofline / ncu filters)
+FRONTEND_KERNEL = "fe2_foa_kernel"          # name of the fused front-end kernel (bench.py's roofline / ncu filters)
 
 
 def _cfg(sr=24000, n_fft=1200, hop_length=600, win_length=1200, mel_bins=64, n_channels=4,
@@ -333,3 +333,34 @@ class FeatureLabelProcessor:
     def get_yolo_label(self, label: dict, nb_label_frames: int):
         from .labels import get_yolo_label
         return get_yolo_label(label, nb_label_frames, self.grid)
+
+
+# ------------------------------------------------------------------------------------------------
+class FrontEndModule(torch.nn.Module):
+    """The feature extractor as the first layer of the network: ``nn.Sequential(FrontEndModule(params), encoder)``.
+
+    The reference extracts features inside ``Dataset.__getitem__`` (datasets.py:149-160) and its loops move the
+    result to the device (train.py:48 ``feat.to(device).float()``).  With ``RawAudioDataset`` / ``collate_raw`` the
+    batch that crosses that line is the int16 audio itself, (B, N, 4); ``.float()`` keeps every int16 value
+    exactly, so this module casts back and runs the fused kernel: -> (B, 7, T, 64) float32, standardised with
+    ``<data_pth>/scaler_wts.pkl`` (datasets.py:206,289-290).  In training mode SpecAug masks are drawn per clip and
+    group with the reference's RNG sequence (augmentations.py:28-33) and applied on the device.  No parameters."""
+
+    def __init__(self, params: dict, scaler: dict | None = None):
+        super().__init__()
+        from .augment import SpecAug
+        self.proc = FeatureLabelProcessor(params, scaler=scaler)
+        self.specaug = SpecAug(params, is_valid=False)
+
+    def extract(self, audio_i16: torch.Tensor) -> torch.Tensor:
+        return self.proc.features_batched(audio_i16)
+
+    def forward(self, audio: torch.Tensor) -> torch.Tensor:
+        if audio.dim() != 3 or audio.shape[-1] != 4:
+            raise ValueError("FrontEndModule expects raw audio (B, N, 4)")
+        if audio.dtype != torch.int16:
+            audio = audio.to(torch.int16)              # exact: the values are int16 samples carried as float
+        feat = self.extract(audio.contiguous())
+        if self.training:
+            feat = self.specaug.augment_batched(feat)
+        return feat

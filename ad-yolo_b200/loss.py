@@ -138,8 +138,18 @@ class ADYOLOloss(object):
     def assign(self, logit, target):
         return adyolo_assign(logit, target, self.grid)
 
+    def rows_from_events(self, events: torch.Tensor, nb_label_frames: int) -> DeviceRows:
+        """(E, 5) event table [batch, frame, class, azi, ele] (what ``collate_raw`` hands over) -> target rows on the
+        device (get_yolo_label + collate_fn, datasets.py:457-482,175-184), no host synchronisation."""
+        from .labels import label_rows_batched
+        ev = events.to(self.device, torch.float64)
+        return label_rows_batched(ev, nb_label_frames, self.grid,
+                                  max_rows=max(ev.shape[0], 1) * self.grid.nb_grids[0] * self.grid.nb_grids[1])
+
     def __call__(self, logit: torch.Tensor, target):
         n_rows = None
+        if torch.is_tensor(target) and target.dim() == 2 and target.shape[-1] == 5:
+            target = self.rows_from_events(target, logit.shape[1])          # raw-audio path: events, not rows
         if isinstance(target, DeviceRows):
             target, n_rows = target.rows, target.n_rows
         _check_inputs(logit, target, self.grid)
