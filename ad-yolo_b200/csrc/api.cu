@@ -22,6 +22,8 @@ int launch_spec_mask(float* feat, int B, int C, long long T, int F, const int* r
                      cudaStream_t stream);
 int launch_gcc_from_stft(const float2* spec, int B, long long T, const float* mean, const float* istd, float* out,
                          OutStrides os, cudaStream_t stream);
+int launch_gcc_from_phasors(const void* phasors, int B, long long T, const float* mean, const float* istd, float* out,
+                            OutStrides os, cudaStream_t stream);
 
 static int check_frontend_cfg(const adyolo_frontend_cfg* c) {
     if (!c) return set_error(ADY_ERR_INVALID, "frontend cfg is NULL");
@@ -138,12 +140,23 @@ size_t adyolo_mic_spec_bytes(int B, int64_t N) {
 int adyolo_features_mic_gcc(const int16_t* audio, int B, int64_t N, const adyolo_frontend_cfg* cfg, const float* mean,
                             const float* inv_std, float* out, void* spec_c64, void* workspace, int apply_topdb,
                             void* stream) {
-    int rc = adyolo_features_mic_logmel(audio, B, N, cfg, mean, inv_std, out, spec_c64, workspace, apply_topdb, stream);
+    // product path: fe2 kernel (log-mel + half2 unit phasors, 16 bytes per bin through the scratch) -> tcgen05 lag
+    // transform.  The scratch is the caller's `spec_c64` buffer (adyolo_mic_spec_bytes is sized for the larger
+    // complex64 layout of adyolo_features_mic_logmel, which remains as the materialising compatibility entry).
+    int rc = check_frontend_cfg(cfg);
     if (rc) return rc;
+    if (!audio || !out || !spec_c64 || !workspace) return set_error(ADY_ERR_INVALID, "features_mic_gcc: NULL pointer");
+    if ((mean == nullptr) != (inv_std == nullptr)) return set_error(ADY_ERR_INVALID, "features_mic_gcc: mean and inv_std must both be given or both NULL");
+    rc = launch_features_mic_fe2(audio, B, (long long)N, mean, inv_std, cfg->dc_offset, out, spec_c64, workspace, (cudaStream_t)stream);
+    if (rc) return rc;
+    if (apply_topdb) {
+        rc = launch_features_clamp_nch(out, B, (long long)N, mean, inv_std, cfg->top_db, 10, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
     const long long T = (long long)N / HOP;
-    return launch_gcc_from_stft((const float2*)spec_c64, B, T, mean ? mean + 4 * NMEL : nullptr,
-                                inv_std ? inv_std + 4 * NMEL : nullptr, out + 4 * T * NMEL,
-                                OutStrides{10 * T * NMEL, T * NMEL, NMEL, 1}, (cudaStream_t)stream);
+    return launch_gcc_from_phasors(spec_c64, B, T, mean ? mean + 4 * NMEL : nullptr,
+                                   inv_std ? inv_std + 4 * NMEL : nullptr, out + 4 * T * NMEL,
+                                   OutStrides{10 * T * NMEL, T * NMEL, NMEL, 1}, (cudaStream_t)stream);
 }
 
 int adyolo_features_foa_clamp(float* out, int B, int64_t N, const adyolo_frontend_cfg* cfg, const float* mean,

@@ -57,12 +57,16 @@ __device__ __forceinline__ void issue_tile_copy(unsigned char* samp, const int16
 
 // ROT : fused rotation augmentation (utils/augmentations.py:46-111), one combination per clip.
 // VIEW: clip b starts at sample clip_off[b] of one resident buffer (on-the-fly chunking, preprocess.py:13-48).
-template <bool ROT, bool VIEW>
+// MIC : microphone-array format (no counterpart in the reference): the 4 log-mel channels go into a
+//       (B, 10, T, 64) tensor and stage C writes one half2 unit phasor per channel and bin to `phasor`
+//       (B, T, 608) x 16 bytes for the GCC-PHAT lag transform (gcc_tc.cu); no intensity vectors (ROT must be false).
+template <bool ROT, bool VIEW, bool MIC>
 __global__ void __launch_bounds__(NT, CTAS_PER_SM)
 fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_per_clip, int ntiles,
                const Tables* __restrict__ tab, const float* __restrict__ mean, const float* __restrict__ istd,
                float dc0, float dc1, const int8_t* __restrict__ rot, const long long* __restrict__ clip_off,
-               float* __restrict__ out, int* __restrict__ flags) {
+               float* __restrict__ out, uint4* __restrict__ phasor, int* __restrict__ flags) {
+    constexpr int NCH = MIC ? 10 : 7;
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned char* s_samp = smem + SmemLayout::off_samples;
     unsigned char* s_x = smem + SmemLayout::off_x;
@@ -131,23 +135,29 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
             const int slot = rd * NT + tid;
             if (slot < 2 * NREG) {
                 const int f = slot >= NREG, task = slot - f * NREG;
-                if (f < nf) stage_c_foa<false>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, rb);
+                if (f < nf) {
+                    if (MIC) stage_c_mic<false>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, phasor + ((long long)b * T + t0 + f) * PH_K);
+                    else stage_c_foa<false>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, rb);
+                }
             } else if (rd == 1 && tid >= NT - 32 && tid < NT - 32 + 2 * NC0) {
                 const int i = tid - (NT - 32), f = i >= NC0, task = i - f * NC0;
-                if (f < nf) stage_c_foa<true>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, rb);
+                if (f < nf) {
+                    if (MIC) stage_c_mic<true>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, phasor + ((long long)b * T + t0 + f) * PH_K);
+                    else stage_c_foa<true>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, rb);
+                }
             }
         }
         __syncthreads();
 
         // ---- mel projection: lane-job tid, both frames
         f2 acc[TFR][4];
-        if (tid < NJOBS) mel_job<true>(s_x, s_ent + tid, acc);
+        if (tid < NJOBS) mel_job<!MIC>(s_x, s_ent + tid, acc);
         __syncthreads();                                   // every V read is done -> records may overwrite the frame buffers
         if (tid < NJOBS) {
 #pragma unroll
             for (int f = 0; f < TFR; ++f) {
                 st_f4(s_x + (2 * f) * REC_PLANE + rec_off, lo2(acc[f][0]), hi2(acc[f][0]), lo2(acc[f][1]), hi2(acc[f][1]));
-                st_f4(s_x + (2 * f + 1) * REC_PLANE + rec_off, lo2(acc[f][2]), hi2(acc[f][2]), lo2(acc[f][3]), hi2(acc[f][3]));
+                if (!MIC) st_f4(s_x + (2 * f + 1) * REC_PLANE + rec_off, lo2(acc[f][2]), hi2(acc[f][2]), lo2(acc[f][3]), hi2(acc[f][3]));
             }
         }
         __syncthreads();
@@ -160,23 +170,25 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
             float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
             for (int i = 0; i < nq; ++i) {                  // fixed order: the result does not depend on scheduling
                 const float4 a = *reinterpret_cast<const float4*>(ra + i * (REC_PITCH * 16));
-                const float4 c = *reinterpret_cast<const float4*>(ra + REC_PLANE + i * (REC_PITCH * 16));
                 pa.x += a.x; pa.y += a.y; pa.z += a.z; pa.w += a.w;
-                pb.x += c.x; pb.y += c.y; pb.z += c.z;
+                if (!MIC) {
+                    const float4 c = *reinterpret_cast<const float4*>(ra + REC_PLANE + i * (REC_PITCH * 16));
+                    pb.x += c.x; pb.y += c.y; pb.z += c.z;
+                }
             }
             // record order (|W|^2, |Z|^2, |Y|^2, |X|^2 | I_Y, I_Z, I_X) -> channels mel W,Y,Z,X, iv Y,Z,X
             float v[7] = {power_to_db(pa.x), power_to_db(pa.z), power_to_db(pa.y), power_to_db(pa.w), pb.x, pb.y, pb.z};
-            if (!(pb.x == pb.x && pb.y == pb.y && pb.z == pb.z)) atomicOr(flags, 1);        // datasets.py:277
+            if (!MIC && !(pb.x == pb.x && pb.y == pb.y && pb.z == pb.z)) atomicOr(flags, 1);   // datasets.py:277
             if (ROT) {
                 if (rb & 1u) v[4] = -v[4];
                 if (rb & 2u) v[5] = -v[5];
                 if (rb & 4u) v[6] = -v[6];
                 if (rb & 8u) { float t = v[1]; v[1] = v[3]; v[3] = t; t = v[4]; v[4] = v[6]; v[6] = t; }   // X <-> Y
             }
-            float* o = out + (((long long)b * 7) * T + t0 + f) * NMEL + j;
+            float* o = out + (((long long)b * NCH) * T + t0 + f) * NMEL + j;
             const long long T64 = (long long)T * NMEL;
 #pragma unroll
-            for (int c = 0; c < 7; ++c) {
+            for (int c = 0; c < (MIC ? 4 : 7); ++c) {
                 const float2 k = s_scale[c * NMEL + j];
                 o[c * T64] = fmaf(v[c], k.x, k.y);
             }
@@ -211,39 +223,39 @@ static int get_fe2_tables(const Tables** dev_tables) {
     return ADY_OK;
 }
 
-template <bool ROT, bool VIEW>
+template <bool ROT, bool VIEW, bool MIC>
 static int launch_inst(int grid, cudaStream_t stream, const int16_t* audio, long long N, int T, int tpc, int ntiles, const Tables* tab,
                        const float* mean, const float* istd, float dc0, float dc1, const int8_t* rot, const long long* clip_off,
-                       float* out, int* flags) {
+                       float* out, uint4* phasor, int* flags) {
     // once per (instantiation, device); a racing second thread at worst repeats the idempotent call
     static std::atomic<unsigned long long> configured{0};
     int dev = 0;
     ADY_CUDA_CHECK(cudaGetDevice(&dev));
     if (!((configured.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
-        ADY_CUDA_CHECK(cudaFuncSetAttribute(fe2_foa_kernel<ROT, VIEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::total));
-        ADY_CUDA_CHECK(cudaFuncSetAttribute(fe2_foa_kernel<ROT, VIEW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        ADY_CUDA_CHECK(cudaFuncSetAttribute(fe2_foa_kernel<ROT, VIEW, MIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::total));
+        ADY_CUDA_CHECK(cudaFuncSetAttribute(fe2_foa_kernel<ROT, VIEW, MIC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
-    fe2_foa_kernel<ROT, VIEW><<<grid, NT, SmemLayout::total, stream>>>(audio, N, T, tpc, ntiles, tab, mean, istd, dc0, dc1, rot, clip_off,
-                                                                     out, flags);
+    fe2_foa_kernel<ROT, VIEW, MIC><<<grid, NT, SmemLayout::total, stream>>>(audio, N, T, tpc, ntiles, tab, mean, istd, dc0, dc1, rot,
+                                                                          clip_off, out, phasor, flags);
     ADY_LAUNCH_CHECK("fe2_foa_kernel");
     return ADY_OK;
 }
 
 }  // namespace fe2
 
-int launch_features_foa_fe2(const int16_t* audio, int B, long long N, const float* mean, const float* istd, float dc_offset,
-                            const int8_t* rot, const long long* clip_off, float* out, void* ws, cudaStream_t stream) {
+static int launch_fe2(const int16_t* audio, int B, long long N, const float* mean, const float* istd, float dc_offset,
+                      const int8_t* rot, const long long* clip_off, float* out, uint4* phasor, void* ws, cudaStream_t stream) {
     using namespace fe2;
     const long long T = N / HOP;
-    if (B <= 0 || T <= 0) return set_error(ADY_ERR_INVALID, "features_foa: need B>0 and at least %d samples", HOP);
-    if (N <= HOP) return set_error(ADY_ERR_INVALID, "features_foa: reflect padding needs N > %d samples", HOP);
+    if (B <= 0 || T <= 0) return set_error(ADY_ERR_INVALID, "features: need B>0 and at least %d samples", HOP);
+    if (N <= HOP) return set_error(ADY_ERR_INVALID, "features: reflect padding needs N > %d samples", HOP);
     const Tables* tab = nullptr;
     int rc = get_fe2_tables(&tab);
     if (rc) return rc;
     const long long tpc = (T + TFR - 1) / TFR;
     const long long ntiles = (long long)B * tpc;
-    if (ntiles > 0x7fffffffLL) return set_error(ADY_ERR_INVALID, "features_foa: too many tiles");
+    if (ntiles > 0x7fffffffLL) return set_error(ADY_ERR_INVALID, "features: too many tiles");
     int* flags = reinterpret_cast<int*>(ws);
     ADY_CUDA_CHECK(cudaMemsetAsync(ws, 0, 16, stream));
     int dev = 0, sms = 0;
@@ -252,13 +264,25 @@ int launch_features_foa_fe2(const int16_t* audio, int B, long long N, const floa
     const int grid = (int)(ntiles < (long long)CTAS_PER_SM * sms ? ntiles : (long long)CTAS_PER_SM * sms);
     // window scale: 2^-15 (int16 -> [-1,1)) * 1/2 (channel split), DC terms scaled by the same 1/2
     const float dc0 = dc_offset * 300.0f, dc1 = -dc_offset * 150.0f;
-    if (rot && clip_off)
-        return launch_inst<true, true>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, flags);
-    if (rot)
-        return launch_inst<true, false>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, flags);
-    if (clip_off)
-        return launch_inst<false, true>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, flags);
-    return launch_inst<false, false>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, flags);
+#define ADY_FE2_GO(R, V, M) return launch_inst<R, V, M>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, phasor, flags)
+    if (phasor) ADY_FE2_GO(false, false, true);
+    if (rot && clip_off) ADY_FE2_GO(true, true, false);
+    if (rot) ADY_FE2_GO(true, false, false);
+    if (clip_off) ADY_FE2_GO(false, true, false);
+    ADY_FE2_GO(false, false, false);
+#undef ADY_FE2_GO
+}
+
+int launch_features_foa_fe2(const int16_t* audio, int B, long long N, const float* mean, const float* istd, float dc_offset,
+                            const int8_t* rot, const long long* clip_off, float* out, void* ws, cudaStream_t stream) {
+    return launch_fe2(audio, B, N, mean, istd, dc_offset, rot, clip_off, out, nullptr, ws, stream);
+}
+
+// MIC format, first half: 4 log-mel channels of out (B, 10, T, 64) + unit phasors (B, T, 608) x 16 bytes
+int launch_features_mic_fe2(const int16_t* audio, int B, long long N, const float* mean, const float* istd, float dc_offset,
+                            float* out, void* phasor, void* ws, cudaStream_t stream) {
+    if (!phasor) return set_error(ADY_ERR_INVALID, "features_mic: phasor scratch is NULL");
+    return launch_fe2(audio, B, N, mean, istd, dc_offset, nullptr, nullptr, out, reinterpret_cast<uint4*>(phasor), ws, stream);
 }
 
 }  // namespace ady

@@ -26,6 +26,10 @@
 
 #include "fft_codelets.cuh"
 
+#if !defined(__CUDACC__)
+struct uint4 { unsigned x, y, z, w; };      // plain C++ build (tests/emu)
+#endif
+
 namespace ady {
 namespace fe2 {
 
@@ -402,6 +406,89 @@ ADY_HD void stage_c_foa(unsigned char* __restrict__ xb, const unsigned char* __r
         st_f4(xb + pbase + 16 * d, va[0], va[1], va[2], va[3]);
         st_f4(xb + vbbase + 16 * d, vb[0], vb[1], vb[2], vb[3]);
     }
+}
+
+// ---------------------------------------------------------------- MIC format: |X|^2 for the log-mel + unit phasors for GCC-PHAT
+// The GCC-PHAT cross spectrum of a microphone pair is R / |R| = conj(u_m) u_n with u_c = X_c / |X_c|, so the front end
+// hands the lag-transform kernel one unit phasor per channel and bin as half2 (16 bytes per bin instead of the 32 bytes of
+// four complex64 spectra; a vanishing channel is sent as (0, 0): every pair it takes part in has R = 0, phase 0).
+// Phasor position of (pair-task, d): regular task tau -> 5 tau + d, c = 0 task i -> 560 + 5 i + d  (605 positions, K = 608).
+constexpr int PH_K = 608;
+ADY_HD int phasor_pos(bool c0, int task, int d) { return (c0 ? 5 * NREG + 5 * task : 5 * task) + d; }
+ADY_HD int raw_bin_of(int k16, int c, int d) { return (225 * k16 + 976 * (c + 15 * d)) % 1200; }
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ uint32_t pack_half2(float re, float im) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(im), "f"(re));   // upper half <- first source
+    return r;
+}
+__device__ __forceinline__ float rsqrt_or_zero(float p) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
+    return p > 0.f ? r : 0.f;
+}
+#endif
+
+template <bool C0>
+ADY_HD void stage_c_mic(unsigned char* __restrict__ xb, const unsigned char* __restrict__ tw, int task, float dc0, float dc1,
+                        uint4* __restrict__ ph_frame /* this frame's PH_K phasor records, or host emulation buffer */) {
+    int pbase, qbase, vbbase, c, cq;
+    stage_c_offsets<C0>(task, pbase, qbase, vbbase, c, cq);
+    c2 P[5], Q[5];
+    stage_c_load<C0>(xb, tw, pbase, qbase, c, cq, P, Q);
+    if (C0 && task == 7) { add_dc(P[0], dc0, 0u); add_dc(Q[0], dc0, 0u); }
+    if (!C0 && task == 1) { add_dc(P[0], dc1, 0u); add_dc(Q[4], dc1, 0u); }
+    const int k16 = C0 ? (task < 7 ? task + 1 : (task == 7 ? 0 : 8)) : (task & 15);
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+        float va[4], vb[4];
+        c2 s0, s1;
+        split_power_iv(P[d], Q[mirror_d<C0>(d)], va, vb, s0, s1);     // (the intensity part is dead code here)
+        st_f4(xb + pbase + 16 * d, va[0], va[1], va[2], va[3]);
+        // channel spectra at raw bin k_d; k_d > 600 holds the conjugate of bin 1200 - k_d
+        const float sg = raw_bin_of(k16, c, d) > 600 ? -1.f : 1.f;
+#if defined(__CUDA_ARCH__)
+        const float r0 = rsqrt_or_zero(va[0]), r2 = rsqrt_or_zero(va[1]), r1 = rsqrt_or_zero(va[2]), r3 = rsqrt_or_zero(va[3]);
+        uint4 rec;
+        rec.x = pack_half2(lo2(s0.re) * r0, sg * lo2(s0.im) * r0);      // channel 0 (W)
+        rec.y = pack_half2(lo2(s1.re) * r1, sg * lo2(s1.im) * r1);      // channel 1 (Y)
+        rec.z = pack_half2(hi2(s0.re) * r2, sg * hi2(s0.im) * r2);      // channel 2 (Z)
+        rec.w = pack_half2(hi2(s1.re) * r3, sg * hi2(s1.im) * r3);      // channel 3 (X)
+        ph_frame[phasor_pos(C0, task, d)] = rec;
+#else
+        float* o = reinterpret_cast<float*>(ph_frame) + phasor_pos(C0, task, d) * 8;   // emulation: 8 floats per position
+        const float pw[4] = {va[0], va[2], va[1], va[3]};
+        const float re[4] = {lo2(s0.re), lo2(s1.re), hi2(s0.re), hi2(s1.re)}, im[4] = {lo2(s0.im), lo2(s1.im), hi2(s0.im), hi2(s1.im)};
+        for (int ch = 0; ch < 4; ++ch) {
+            const float r = pw[ch] > 0.f ? 1.0f / __builtin_sqrtf(pw[ch]) : 0.f;
+            o[2 * ch] = re[ch] * r;
+            o[2 * ch + 1] = sg * im[ch] * r;
+        }
+#endif
+    }
+    if (C0 && task == 8) {                                            // K padding 605..607: finite zeros
+#if defined(__CUDA_ARCH__)
+        for (int i = 605; i < PH_K; ++i) ph_frame[i] = make_uint4(0u, 0u, 0u, 0u);
+#endif
+    }
+}
+
+// host-side: folded FFT bin of phasor position p, or -1 (duplicate of a self-mirror row / padding)
+inline void bins_of_phasor_pos(int (&bin_of_pos)[PH_K]) {
+    bool seen[NBIN];
+    for (int k = 0; k < NBIN; ++k) seen[k] = false;
+    for (int p = 0; p < PH_K; ++p) bin_of_pos[p] = -1;
+    for (int task = 0; task < NREG; ++task)
+        for (int d = 0; d < 5; ++d) {
+            const int k = bin_of(task & 15, (task >> 4) + 1, d);
+            if (!seen[k]) { seen[k] = true; bin_of_pos[phasor_pos(false, task, d)] = k; }
+        }
+    for (int task = 0; task < NC0; ++task)
+        for (int d = 0; d < 5; ++d) {
+            const int k = bin_of(task < 7 ? task + 1 : (task == 7 ? 0 : 8), 0, d);
+            if (!seen[k]) { seen[k] = true; bin_of_pos[phasor_pos(true, task, d)] = k; }
+        }
 }
 
 // host-side: V record offsets of bin k (first occurrence), for the mel schedule

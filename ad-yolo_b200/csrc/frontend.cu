@@ -286,6 +286,15 @@ size_t frontend_workspace_bytes(int B, long long N) {
     return 64;   // [flags int x4]
 }
 
+int launch_features_clamp_nch(float* out, int B, long long N, const float* mean, const float* istd, float top_db, int nch,
+                               cudaStream_t stream) {
+    const long long T = N / HOP;
+    if (B <= 0 || T <= 0) return set_error(ADY_ERR_INVALID, "features_clamp: empty input");
+    clamp_topdb_kernel<<<B * 4, 256, 0, stream>>>(out, mean, istd, (int)T, top_db, nch);
+    ADY_LAUNCH_CHECK("clamp_topdb_kernel");
+    return ADY_OK;
+}
+
 int launch_features_foa_clamp(float* out, int B, long long N, const float* mean, const float* istd, float top_db,
                               void* ws, cudaStream_t stream) {
     (void)ws;

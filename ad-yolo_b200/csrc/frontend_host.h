@@ -32,8 +32,15 @@ int launch_features_foa(const int16_t* audio, int B, long long N, const float* m
 int launch_features_foa_fe2(const int16_t* audio, int B, long long N, const float* mean, const float* istd, float dc_offset,
                             const int8_t* rot, const long long* clip_off, float* out, void* ws, cudaStream_t stream);
 
+// MIC format on the fe2 kernel: log-mel channels 0..3 of out (B, 10, T, 64), un-clamped, + half2 unit phasors
+// (B, T, 608, 4) for launch_gcc_from_phasors (gcc_tc.cu)
+int launch_features_mic_fe2(const int16_t* audio, int B, long long N, const float* mean, const float* istd, float dc_offset,
+                            float* out, void* phasor, void* ws, cudaStream_t stream);
+
 int launch_features_mic_logmel(const int16_t* audio, int B, long long N, const float* mean, const float* istd,
                                float dc_offset, float top_db, int apply_topdb, float* out, float2* spec, void* ws,
+                               cudaStream_t stream);
+int launch_features_clamp_nch(float* out, int B, long long N, const float* mean, const float* istd, float top_db, int nch,
                                cudaStream_t stream);
 int launch_features_foa_clamp(float* out, int B, long long N, const float* mean, const float* istd, float top_db,
                               void* ws, cudaStream_t stream);

@@ -34,11 +34,15 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <vector>
 
 #include "common.cuh"
 #include "frontend_core.cuh"
+#include <cuda_fp16.h>
+
+#include "fe2_core.cuh"
 #include "frontend_host.h"
 
 namespace ady {
@@ -54,19 +58,27 @@ constexpr int GT_CHUNKS = 76;                 // 608 bins >= 601
 constexpr int GT_THREADS = 256;
 constexpr int GT_STAGES = 2;                  // A-operand stages (generation of chunk c+1 overlaps the MMAs of chunk c)
 constexpr int GT_KCH = GT_BINS * 2 / 4;       // 16-byte k-chunks per stage (4)
-// A operand: k-chunk pitch (= LBO) padded by 32 B so that the 4 k-chunks a warp stores at once fall
-// into different bank groups (the stores of a warp then need the minimum of two wavefronts)
-constexpr int GT_A_LBO = (GT_ITEMS / 8) * 128 + 32;                    // 6176
-constexpr int GT_A_BYTES = GT_KCH * GT_A_LBO;                          // 24704
+// Two input formats (template parameter PH):
+//   PH = false: raw channel spectra, complex64 (B, T, 601, 4) -- the compatibility entry adyolo_gcc_from_stft;
+//               a 16-byte piece is one channel PAIR of a (frame, bin); partner lanes swap the other pair
+//   PH = true : per-channel unit phasors as half2, (B, T, 608) x 16 bytes in the fe2 kernel's position order
+//               (fe2_core.cuh::phasor_pos) -- half the bytes, no rsqrt and no lane exchange here: a 16-byte
+//               piece is ALL four channels of a (frame, position) and its lane forms all six cross spectra
+// A operand: the k-chunk pitch (= LBO) is skewed (32 B / 16 B) so that the 8-byte stores of a half-warp hit 16 distinct
+// 8-byte slots (see the store sites)
+template <bool PH> struct GtCfg {
+    static constexpr int A_LBO = (GT_ITEMS / 8) * 128 + (PH ? 16 : 32);       // 6160 | 6176
+    static constexpr int A_BYTES = GT_KCH * A_LBO;
+    static constexpr int RAW_BYTES = GT_FRAMES * GT_BINS * (PH ? 16 : 32);    // 8192 | 16384
+    static constexpr int PIECES = RAW_BYTES / 16 / GT_THREADS;                // 16-byte pieces per thread and chunk (2 | 4)
+    static constexpr int OFF_B = GT_STAGES * A_BYTES;
+    static constexpr int OFF_RAW = OFF_B + 4 * 4096;
+    static constexpr int SMEM = OFF_RAW + 3 * RAW_BYTES;                       // <= 114944 B: two CTAs per SM
+};
 constexpr int GT_B_LBO = (64 / 8) * 128;                               // 1024
 constexpr int GT_B_BYTES = GT_KCH * GT_B_LBO;                          // 4096
 constexpr int GT_B_SLOTS = 4;                 // B chunk c+2 is copied while the MMAs of chunk c-1 may still read theirs
-constexpr int GT_RAW_STAGES = 3;              // raw spectra: chunks c+1 and c+2 in flight while chunk c is consumed
-constexpr int GT_RAW_BYTES = GT_FRAMES * GT_BINS * 32;                 // 16384
-constexpr int GT_PIECES = GT_RAW_BYTES / 16 / GT_THREADS;              // 16-byte pieces per thread and chunk (4)
-constexpr int GT_OFF_B = GT_STAGES * GT_A_BYTES;
-constexpr int GT_OFF_RAW = GT_OFF_B + GT_B_SLOTS * GT_B_BYTES;
-constexpr int GT_SMEM = GT_OFF_RAW + GT_RAW_STAGES * GT_RAW_BYTES;     // 114944 B: two CTAs per SM
+constexpr int GT_RAW_STAGES = 3;              // raw input: chunks c+1 and c+2 in flight while chunk c is consumed
 constexpr uint32_t GT_TMEM_COLS = 256;        // 3 x 64 fp32 columns, power of two
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -118,38 +130,60 @@ __device__ __forceinline__ float2 unit(float2 a, bool& zero) {
     return make_float2(re * r, im * r);
 }
 
-// Piece ownership: piece q = tid + 256 j of a chunk is (frame q / 16, bin (q % 16) / 2, channel half
+// Piece ownership (PH = false): piece q = tid + 256 j of a chunk is (frame q / 16, bin (q % 16) / 2, channel half
 // q % 2), i.e. consecutive lanes copy consecutive 16-byte pieces (one frame's 8 bins x 4 channels are
 // 256 contiguous bytes) and consume exactly what they copied; the partner holding the other two
 // channels of the same (frame, bin) is lane ^ 1.
 __device__ __forceinline__ int gt_half(int tid) { return tid & 1; }
 __device__ __forceinline__ int gt_kb(int tid) { return (tid & 15) >> 1; }
 __device__ __forceinline__ int gt_frame(int tid, int j) { return (tid + GT_THREADS * j) >> 4; }
+// PH = true: piece q = tid + 256 j is (position q % 8 of the chunk, frame slot q / 8); the four frame slots of a warp are
+// frames 4 w + {0, 2, 1, 3}: the two frames of a half-warp are 2 apart = 4 rows = 64 bytes in the A operand, which
+// together with the 16-byte k-chunk skew makes the 16 float2 stores of a half-warp conflict-free.
+__device__ __forceinline__ int ph_kb(int tid) { return tid & 7; }
+__device__ __forceinline__ int ph_frame(int tid, int j) {
+    const int g = (tid + GT_THREADS * j) >> 3, i = g & 3;
+    return (g & ~3) + ((i & 1) << 1) + (i >> 1);
+}
 
-// Asynchronous staging of one chunk: every thread copies the GT_PIECES 16-byte pieces (one channel
-// pair of one bin of one frame) that it will itself consume, so the raw data need no barrier at
-// all (cp.async.wait_group only), plus one piece of the B operand chunk.  Pieces past the last frame / bin 600 are zero-filled (src-size 0).
-__device__ __forceinline__ void issue_chunk_copy(unsigned char* smem, const float2* __restrict__ spec, const float* __restrict__ btab,
+// Asynchronous staging of one chunk: every thread copies the 16-byte pieces that it will itself consume, so the raw
+// data need no barrier at all (cp.async.wait_group only), plus one piece of the B operand chunk.  Pieces past the
+// last frame / bin 600 are zero-filled (src-size 0).
+template <bool PH>
+__device__ __forceinline__ void issue_chunk_copy(unsigned char* smem, const void* __restrict__ in, const float* __restrict__ btab,
                                                  long long f0, long long n_frames, int ch, int tid) {
+    using Cfg = GtCfg<PH>;
     if (ch < GT_CHUNKS) {
-        const uint32_t raw = smem_u32(smem + GT_OFF_RAW + (ch % GT_RAW_STAGES) * GT_RAW_BYTES) + tid * 16;
+        const uint32_t raw = smem_u32(smem + Cfg::OFF_RAW + (ch % GT_RAW_STAGES) * Cfg::RAW_BYTES) + tid * 16;
 #pragma unroll
-        for (int j = 0; j < GT_PIECES; ++j) {
-            const int f = gt_frame(tid, j), bin = ch * GT_BINS + gt_kb(tid);
-            const long long fr = f0 + f;
-            const bool live = fr < n_frames && bin < NBIN;
-            const float2* src = live ? spec + (fr * NBIN + bin) * 4 + gt_half(tid) * 2 : spec;
+        for (int j = 0; j < Cfg::PIECES; ++j) {
+            const void* src;
+            bool live;
+            if (PH) {
+                const long long fr = f0 + ph_frame(tid, j);
+                live = fr < n_frames;
+                src = live ? (const void*)(reinterpret_cast<const uint4*>(in) + fr * 608 + ch * GT_BINS + ph_kb(tid)) : in;
+            } else {
+                const int f = gt_frame(tid, j), bin = ch * GT_BINS + gt_kb(tid);
+                const long long fr = f0 + f;
+                live = fr < n_frames && bin < NBIN;
+                src = live ? (const void*)(reinterpret_cast<const float2*>(in) + (fr * NBIN + bin) * 4 + gt_half(tid) * 2) : in;
+            }
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(raw + j * (GT_THREADS * 16)), "l"(src), "r"(live ? 16 : 0) : "memory");
         }
-        const uint32_t d = smem_u32(smem + GT_OFF_B + (ch % GT_B_SLOTS) * GT_B_BYTES) + tid * 16;
+        const uint32_t d = smem_u32(smem + Cfg::OFF_B + (ch % GT_B_SLOTS) * GT_B_BYTES) + tid * 16;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(btab + (size_t)ch * (GT_B_BYTES / 4) + tid * 4) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+template <bool PH>
 __global__ void __launch_bounds__(GT_THREADS, 2)
-gcc_tc_kernel(const float2* __restrict__ spec, long long n_frames, int T, const float* __restrict__ btab,
+gcc_tc_kernel(const void* __restrict__ spec, long long n_frames, int T, const float* __restrict__ btab,
               const float* __restrict__ mean, const float* __restrict__ istd, float* __restrict__ out, OutStrides os) {
+    using Cfg = GtCfg<PH>;
+    constexpr int GT_A_LBO = Cfg::A_LBO, GT_A_BYTES = Cfg::A_BYTES, GT_OFF_B = Cfg::OFF_B, GT_OFF_RAW = Cfg::OFF_RAW,
+                  GT_RAW_BYTES = Cfg::RAW_BYTES, GT_PIECES = Cfg::PIECES;
     extern __shared__ __align__(128) unsigned char smem[];      // A x2 | B x4 | raw x3
     __shared__ __align__(8) unsigned long long mbar[GT_STAGES];
     __shared__ uint32_t tmem_base_s;
@@ -158,8 +192,8 @@ gcc_tc_kernel(const float2* __restrict__ spec, long long n_frames, int T, const 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long f0 = (long long)blockIdx.x * GT_FRAMES;
 
-    issue_chunk_copy(smem, spec, btab, f0, n_frames, 0, tid);
-    issue_chunk_copy(smem, spec, btab, f0, n_frames, 1, tid);
+    issue_chunk_copy<PH>(smem, spec, btab, f0, n_frames, 0, tid);
+    issue_chunk_copy<PH>(smem, spec, btab, f0, n_frames, 1, tid);
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(GT_TMEM_COLS));
@@ -182,10 +216,39 @@ gcc_tc_kernel(const float2* __restrict__ spec, long long n_frames, int T, const 
         unsigned char* sA = smem + stg * GT_A_BYTES;
         // A stage (and the B slot chunk ch+2 is about to overwrite) free once the MMAs of chunk ch-2 are done
         if (ch >= GT_STAGES) mbar_wait(smem_u32(&mbar[stg]), (uint32_t)(((ch - GT_STAGES) / GT_STAGES) & 1));
-        issue_chunk_copy(smem, spec, btab, f0, n_frames, ch + 2, tid);
+        issue_chunk_copy<PH>(smem, spec, btab, f0, n_frames, ch + 2, tid);
         asm volatile("cp.async.wait_group 2;" ::: "memory");            // this thread's pieces of chunk ch have landed
 
         const float4* raw = reinterpret_cast<const float4*>(smem + GT_OFF_RAW + (ch % GT_RAW_STAGES) * GT_RAW_BYTES) + tid;
+        if (PH) {
+            // phasor input: this lane holds all four unit phasors of (frame f, position kb) and forms the six cross
+            // spectra conj(u_m) u_n; a zero phasor marks a vanishing channel -> (1, 0).  Pair p = 0..5 = (0,1) (0,2) (0,3)
+            // (1,2) (1,3) (2,3) goes to M-tile p / 2, row 2 f + (p & 1).
+#pragma unroll
+            for (int j = 0; j < GT_PIECES; ++j) {
+                const int f = ph_frame(tid, j), pkb = ph_kb(tid);
+                const uint4 v = *reinterpret_cast<const uint4*>(&raw[j * GT_THREADS]);
+                float2 u[4];
+                {
+                    const __half2 h0 = *reinterpret_cast<const __half2*>(&v.x), h1 = *reinterpret_cast<const __half2*>(&v.y);
+                    const __half2 h2 = *reinterpret_cast<const __half2*>(&v.z), h3 = *reinterpret_cast<const __half2*>(&v.w);
+                    u[0] = __half22float2(h0); u[1] = __half22float2(h1); u[2] = __half22float2(h2); u[3] = __half22float2(h3);
+                }
+                const bool z0 = v.x == 0u, z1 = v.y == 0u, z2 = v.z == 0u, z3 = v.w == 0u;     // (+0, +0): written by the front end
+                const bool zz[4] = {z0, z1, z2, z3};
+                unsigned char* base = sA + (pkb >> 1) * GT_A_LBO + (pkb & 1) * 8;
+#pragma unroll
+                for (int p = 0; p < 6; ++p) {
+                    constexpr int PM[6] = {0, 0, 0, 1, 1, 2}, PN[6] = {1, 2, 3, 2, 3, 3};
+                    const float2 a = u[PM[p]], b2 = u[PN[p]];
+                    float2 P = make_float2(a.x * b2.x + a.y * b2.y, a.x * b2.y - a.y * b2.x);
+                    if (zz[PM[p]] || zz[PN[p]]) P = make_float2(1.f, 0.f);
+                    const int r = 2 * f + (p & 1);
+                    *reinterpret_cast<float2*>(base + (p >> 1) * 2048 + (r >> 3) * 128 + (r & 7) * 16) =
+                        make_float2(tf32_rn_bits(P.x), tf32_rn_bits(P.y));
+                }
+            }
+        } else {
 #pragma unroll
         for (int j = 0; j < GT_PIECES; ++j) {
             const int f = gt_frame(tid, j);
@@ -230,6 +293,7 @@ gcc_tc_kernel(const float2* __restrict__ spec, long long n_frames, int T, const 
             *reinterpret_cast<float2*>(d0 + (half ? 2 : 0) * 2048) = make_float2(tf32_rn_bits(P0.x), tf32_rn_bits(P0.y));
             *reinterpret_cast<float2*>(d1 + (half ? 2 : 0) * 2048) = make_float2(tf32_rn_bits(P1.x), tf32_rn_bits(P1.y));
             *reinterpret_cast<float2*>(d0 + 2048) = make_float2(tf32_rn_bits(P2.x), tf32_rn_bits(P2.y));
+        }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy / cp.async writes -> async proxy (UMMA)
         __syncthreads();
@@ -319,20 +383,25 @@ gcc_tc_kernel(const float2* __restrict__ spec, long long n_frames, int T, const 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(GT_TMEM_COLS));
 }
 
-// B operand table: [GT_CHUNKS][GT_KCH k-chunks][8 lag-groups][8 lags][4 k'] floats (canonical K-major layout)
-static int get_gcc_btab(const float** dev_tab) {
+// B operand table: [GT_CHUNKS][GT_KCH k-chunks][8 lag-groups][8 lags][4 k'] floats (canonical K-major layout).
+// K index = FFT bin (PH = false) or the fe2 kernel's phasor position (PH = true; duplicate / padding positions
+// get all-zero rows).
+static int get_gcc_btab(const float** dev_tab, bool ph) {
     static std::mutex mu;
-    static float* cache[64] = {nullptr};
+    static float* cache[2][64] = {{nullptr}, {nullptr}};
     int dev = 0;
     ADY_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return set_error(ADY_ERR_INVALID, "device index %d out of range", dev);
     std::lock_guard<std::mutex> lk(mu);
-    if (!cache[dev]) {
+    if (!cache[ph][dev]) {
+        int bin_of_pos[fe2::PH_K];
+        fe2::bins_of_phasor_pos(bin_of_pos);
         std::vector<float> h((size_t)GT_CHUNKS * GT_B_BYTES / 4, 0.f);
         for (int ch = 0; ch < GT_CHUNKS; ++ch)
             for (int kp = 0; kp < 2 * GT_BINS; ++kp) {            // k' within the chunk
-                const int bin = ch * GT_BINS + (kp >> 1);
-                if (bin >= NBIN) continue;
+                const int kidx = ch * GT_BINS + (kp >> 1);
+                const int bin = ph ? bin_of_pos[kidx] : (kidx < NBIN ? kidx : -1);
+                if (bin < 0) continue;
                 const double ck = (bin == 0 || bin == 600) ? 0.5 : 1.0;    // x 2/N in the epilogue
                 for (int n = 0; n < 64; ++n) {
                     const int lag = n - 32;                       // output order cc[-32:], cc[:32]
@@ -351,31 +420,43 @@ static int get_gcc_btab(const float** dev_tab) {
         float* d = nullptr;
         ADY_CUDA_CHECK(cudaMalloc(&d, h.size() * sizeof(float)));
         ADY_CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
-        cache[dev] = d;
+        cache[ph][dev] = d;
     }
-    *dev_tab = cache[dev];
+    *dev_tab = cache[ph][dev];
+    return ADY_OK;
+}
+
+template <bool PH>
+static int launch_gcc(const void* in, int B, long long T, const float* mean, const float* istd, float* out, OutStrides os,
+                      cudaStream_t stream) {
+    const float* btab = nullptr;
+    int rc = get_gcc_btab(&btab, PH);
+    if (rc) return rc;
+    const long long n_frames = (long long)B * T;
+    const long long blocks = (n_frames + GT_FRAMES - 1) / GT_FRAMES;
+    if (blocks > 0x7fffffffLL) return set_error(ADY_ERR_INVALID, "gcc: too many frames");
+    static std::atomic<unsigned long long> configured{0};      // per (instantiation, device); the call is idempotent
+    int dev = 0;
+    ADY_CUDA_CHECK(cudaGetDevice(&dev));
+    const int shmem = GtCfg<PH>::SMEM;
+    if (!((configured.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
+        ADY_CUDA_CHECK(cudaFuncSetAttribute(gcc_tc_kernel<PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, shmem));
+        configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
+    gcc_tc_kernel<PH><<<(unsigned)blocks, GT_THREADS, shmem, stream>>>(in, n_frames, (int)T, btab, mean, istd, out, os);
+    ADY_LAUNCH_CHECK("gcc_tc_kernel");
     return ADY_OK;
 }
 
 int launch_gcc_from_stft(const float2* spec, int B, long long T, const float* mean, const float* istd, float* out,
                          OutStrides os, cudaStream_t stream) {
-    const float* btab = nullptr;
-    int rc = get_gcc_btab(&btab);
-    if (rc) return rc;
-    const long long n_frames = (long long)B * T;
-    const long long blocks = (n_frames + GT_FRAMES - 1) / GT_FRAMES;
-    if (blocks > 0x7fffffffLL) return set_error(ADY_ERR_INVALID, "gcc: too many frames");
-    static int configured_dev = -1;
-    int dev = 0;
-    ADY_CUDA_CHECK(cudaGetDevice(&dev));
-    const int shmem = GT_SMEM;
-    if (configured_dev != dev) {
-        ADY_CUDA_CHECK(cudaFuncSetAttribute(gcc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, shmem));
-        configured_dev = dev;
-    }
-    gcc_tc_kernel<<<(unsigned)blocks, GT_THREADS, shmem, stream>>>(spec, n_frames, (int)T, btab, mean, istd, out, os);
-    ADY_LAUNCH_CHECK("gcc_tc_kernel");
-    return ADY_OK;
+    return launch_gcc<false>(spec, B, T, mean, istd, out, os, stream);
+}
+
+// phasors: half2 x 4 channels per (frame, fe2 position), (B, T, 608) x 16 bytes, written by launch_features_mic_fe2
+int launch_gcc_from_phasors(const void* phasors, int B, long long T, const float* mean, const float* istd, float* out,
+                            OutStrides os, cudaStream_t stream) {
+    return launch_gcc<true>(phasors, B, T, mean, istd, out, os, stream);
 }
 
 }  // namespace ady

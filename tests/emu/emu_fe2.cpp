@@ -118,3 +118,37 @@ extern "C" int emu_fe2_features_foa(const int16_t* audio, int B, long long N, co
         }
     return 0;
 }
+
+// MIC format, CPU emulation of stages A / B / C (stage_c_mic): one clip -> unit phasors (T, 608, 4 channels, re/im) as
+// float32 (the device packs them as half2) and the position -> FFT-bin map the GCC-PHAT B table is built from.
+extern "C" int emu_fe2_mic_phasors(const int16_t* audio, long long N, const float* mel_dense, float dc_offset,
+                                   float* phasors /* T x 608 x 8 */, int* bin_of_pos /* 608 */) {
+    const int T = (int)(N / HOP);
+    const int tpc = (T + TFR - 1) / TFR;
+    static Tables tab;
+    static MelPlan plan;
+    bool ok;
+    fill_tables(mel_dense, tab, plan, ok);
+    if (!ok) return -1;
+    int bop[PH_K];
+    bins_of_phasor_pos(bop);
+    for (int p = 0; p < PH_K; ++p) bin_of_pos[p] = bop[p];
+    std::vector<unsigned char> smem(SmemLayout::total, 0);
+    unsigned char* s_samp = smem.data() + SmemLayout::off_samples;
+    unsigned char* s_x = smem.data() + SmemLayout::off_x;
+    const unsigned char* s_tw = reinterpret_cast<const unsigned char*>(tab.tw75);
+    const float dc0 = dc_offset * 300.0f, dc1 = -dc_offset * 150.0f;
+    memset(phasors, 0, sizeof(float) * (size_t)T * PH_K * 8);
+    for (int tile = 0; tile < tpc; ++tile) {
+        const int t0 = tile * TFR, nf = std::min(TFR, T - t0);
+        stage_copy(s_samp, audio, t0, nf);
+        for (int tid = 0; tid < NT_AB; ++tid) { const int f = tid / 80, l = tid % 80; if (l < 75 && f < nf) stage_a(s_samp, tab.win, s_x, f, l, stage_a_const(l)); }
+        for (int tid = 0; tid < NT_AB; ++tid) { const int f = tid / 80, u = tid % 80; if (f < nf) stage_b(s_x, f, u); }
+        for (int f = 0; f < nf; ++f) {
+            uint4* ph = reinterpret_cast<uint4*>(phasors + ((size_t)(t0 + f) * PH_K) * 8);   // 8 floats per position
+            for (int task = 0; task < NREG; ++task) stage_c_mic<false>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, ph);
+            for (int task = 0; task < NC0; ++task) stage_c_mic<true>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, ph);
+        }
+    }
+    return 0;
+}

@@ -184,3 +184,35 @@ def test_emulated_fe2_ragged_batch_and_rotation(built):
         assert ref.shape == (7, T, 64)
         assert (np.abs(out[b, :4] - ref[:4]) / np.maximum(np.abs(ref[:4]), 1.0)).max() < 1e-4, b
         assert np.abs(out[b, 4:] - ref[4:]).max() < 1e-6, b
+
+
+def test_emulated_fe2_mic_phasors_give_the_oracle_gcc(built):
+    """MIC format: the unit phasors stage C hands to the GCC-PHAT kernel (position order, conjugate for folded bins,
+    channel order) reproduce the float64 GCC-PHAT oracle when the lag transform is done in numpy."""
+    L = ctypes.CDLL(os.path.join(ROOT, "build", "emu_fe2.so"))
+    rng = np.random.default_rng(9)
+    N = 600 * 9
+    clip = np.clip(rng.standard_normal((N, 4)) * 1500, -32767, 32767).astype(np.int16)
+    clip[:, 1] = np.roll(clip[:, 0], 3)                              # a delayed copy: a clear GCC peak at lag 3
+    T = N // 600
+    mel = built.mel_filterbank(24000, 1200, 64).copy()
+    ph = np.zeros((T, 608, 4, 2), np.float32)
+    bop = np.zeros(608, np.int32)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    assert L.emu_fe2_mic_phasors(vp(clip), ctypes.c_longlong(N), vp(mel), ctypes.c_float(1e-8), vp(ph), vp(bop)) == 0
+    assert sorted(bop[bop >= 0].tolist()) == list(range(601))        # every bin exactly once
+    u = np.zeros((T, 601, 4), np.complex128)
+    for p in range(608):
+        if bop[p] >= 0:
+            u[:, bop[p]] = ph[:, p, :, 0] + 1j * ph[:, p, :, 1]
+    assert np.abs(np.abs(u) - 1).max() < 1e-5
+    got = []
+    for m in range(4):
+        for n in range(m + 1, 4):
+            cc = np.fft.irfft(np.conj(u[:, :, m]) * u[:, :, n], n=1200, axis=1)
+            got.append(np.concatenate((cc[:, -32:], cc[:, :32]), axis=-1))
+    got = np.stack(got, -1)
+    audio = F.normalise_int16(clip)
+    ref = F.gcc_phat(F.audio2stft(audio, T, 1200, 600, 1200, "han"), 1200, 64)
+    assert np.abs(got - ref).max() < 1e-4
+    assert np.argmax(ref[2, :, 0]) == 32 + 3
