@@ -150,7 +150,7 @@ int adyolo_features_mic_gcc(const int16_t* audio, int B, int64_t N, const adyolo
     rc = launch_features_mic_fe2(audio, B, (long long)N, mean, inv_std, cfg->dc_offset, out, spec_c64, workspace, (cudaStream_t)stream);
     if (rc) return rc;
     if (apply_topdb) {
-        rc = launch_features_clamp_nch(out, B, (long long)N, mean, inv_std, cfg->top_db, 10, (cudaStream_t)stream);
+        rc = launch_features_clamp_nch(out, B, (long long)N, mean, inv_std, cfg->top_db, 10, workspace, (cudaStream_t)stream);
         if (rc) return rc;
     }
     const long long T = (long long)N / HOP;

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM)
 fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_per_clip, int ntiles,
                const Tables* __restrict__ tab, const float* __restrict__ mean, const float* __restrict__ istd,
                float dc0, float dc1, const int8_t* __restrict__ rot, const long long* __restrict__ clip_off,
-               float* __restrict__ out, uint4* __restrict__ phasor, int* __restrict__ flags) {
+               float* __restrict__ out, uint4* __restrict__ phasor, int* __restrict__ flags, uint32_t* __restrict__ kext, int B) {
     constexpr int NCH = MIC ? 10 : 7;
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned char* s_samp = smem + SmemLayout::off_samples;
@@ -100,9 +100,9 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
             const float mu = mean ? mean[i] : 0.f, is = istd ? istd[i] : 1.f;
             s_scale[i] = make_float2(is, -mu * is);
         }
-        if (tid < NMEL) s_meljobs[tid] = tab->mel_njobs[tid];
+        if (tid < NMEL) { s_meljobs[tid] = tab->mel_job0[tid]; s_meljobs[NMEL + tid] = tab->mel_njobs[tid]; }
     }
-    const int rec_off = tab->job_rec[tid < NJOBS ? tid : 0] * 16;                   // this lane-job's record slot
+    const int rec_off = tid * 16;                                                   // this lane-job's record slot
 
     for (; tile < ntiles; tile += gridDim.x) {
         const int b = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * TFR, nf = min(TFR, T - t0);
@@ -165,14 +165,14 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
         // ---- epilogue: thread = (frame, mel)
         if (tid < TFR * NMEL && (tid >> 6) < nf) {
             const int f = tid >> 6, j = tid & 63;
-            const int nq = s_meljobs[j];
-            const unsigned char* ra = s_x + (2 * f) * REC_PLANE + j * 16;
+            const int nq = s_meljobs[NMEL + j];
+            const unsigned char* ra = s_x + (2 * f) * REC_PLANE + s_meljobs[j] * 16;
             float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
             for (int i = 0; i < nq; ++i) {                  // fixed order: the result does not depend on scheduling
-                const float4 a = *reinterpret_cast<const float4*>(ra + i * (REC_PITCH * 16));
+                const float4 a = *reinterpret_cast<const float4*>(ra + i * 16);
                 pa.x += a.x; pa.y += a.y; pa.z += a.z; pa.w += a.w;
                 if (!MIC) {
-                    const float4 c = *reinterpret_cast<const float4*>(ra + REC_PLANE + i * (REC_PITCH * 16));
+                    const float4 c = *reinterpret_cast<const float4*>(ra + REC_PLANE + i * 16);
                     pb.x += c.x; pb.y += c.y; pb.z += c.z;
                 }
             }
@@ -184,6 +184,17 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
                 if (rb & 2u) v[5] = -v[5];
                 if (rb & 4u) v[6] = -v[6];
                 if (rb & 8u) { float t = v[1]; v[1] = v[3]; v[3] = t; t = v[4]; v[4] = v[6]; v[6] = t; }   // X <-> Y
+            }
+            // per-(clip, log-mel channel) extrema of the un-clamped dB values for the top_db pass (power_to_db's global
+            // max, datasets.py:265): one warp-wide integer reduction per channel on order-preserving keys
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t key = f2key(v[c]);
+                const uint32_t hi = __reduce_max_sync(0xffffffffu, key), lo = __reduce_min_sync(0xffffffffu, key);
+                if ((tid & 31) == 0) {
+                    atomicMax(kext + b * 4 + c, hi);
+                    atomicMin(kext + (B + b) * 4 + c, lo);
+                }
             }
             float* o = out + (((long long)b * NCH) * T + t0 + f) * NMEL + j;
             const long long T64 = (long long)T * NMEL;
@@ -226,7 +237,7 @@ static int get_fe2_tables(const Tables** dev_tables) {
 template <bool ROT, bool VIEW, bool MIC>
 static int launch_inst(int grid, cudaStream_t stream, const int16_t* audio, long long N, int T, int tpc, int ntiles, const Tables* tab,
                        const float* mean, const float* istd, float dc0, float dc1, const int8_t* rot, const long long* clip_off,
-                       float* out, uint4* phasor, int* flags) {
+                       float* out, uint4* phasor, int* flags, int B) {
     // once per (instantiation, device); a racing second thread at worst repeats the idempotent call
     static std::atomic<unsigned long long> configured{0};
     int dev = 0;
@@ -237,7 +248,8 @@ static int launch_inst(int grid, cudaStream_t stream, const int16_t* audio, long
         configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     fe2_foa_kernel<ROT, VIEW, MIC><<<grid, NT, SmemLayout::total, stream>>>(audio, N, T, tpc, ntiles, tab, mean, istd, dc0, dc1, rot,
-                                                                          clip_off, out, phasor, flags);
+                                                                          clip_off, out, phasor, flags,
+                                                                          reinterpret_cast<uint32_t*>(flags) + 16, B);
     ADY_LAUNCH_CHECK("fe2_foa_kernel");
     return ADY_OK;
 }
@@ -256,15 +268,17 @@ static int launch_fe2(const int16_t* audio, int B, long long N, const float* mea
     const long long tpc = (T + TFR - 1) / TFR;
     const long long ntiles = (long long)B * tpc;
     if (ntiles > 0x7fffffffLL) return set_error(ADY_ERR_INVALID, "features: too many tiles");
+    // workspace: [flags | pad to 64 B] [max keys (B,4)] [min keys (B,4)]  (frontend_workspace_bytes)
     int* flags = reinterpret_cast<int*>(ws);
-    ADY_CUDA_CHECK(cudaMemsetAsync(ws, 0, 16, stream));
+    ADY_CUDA_CHECK(cudaMemsetAsync(ws, 0, 64 + (size_t)B * 16, stream));
+    ADY_CUDA_CHECK(cudaMemsetAsync(reinterpret_cast<char*>(ws) + 64 + (size_t)B * 16, 0xff, (size_t)B * 16, stream));
     int dev = 0, sms = 0;
     ADY_CUDA_CHECK(cudaGetDevice(&dev));
     ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = (int)(ntiles < (long long)CTAS_PER_SM * sms ? ntiles : (long long)CTAS_PER_SM * sms);
     // window scale: 2^-15 (int16 -> [-1,1)) * 1/2 (channel split), DC terms scaled by the same 1/2
     const float dc0 = dc_offset * 300.0f, dc1 = -dc_offset * 150.0f;
-#define ADY_FE2_GO(R, V, M) return launch_inst<R, V, M>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, phasor, flags)
+#define ADY_FE2_GO(R, V, M) return launch_inst<R, V, M>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, phasor, flags, B)
     if (phasor) ADY_FE2_GO(false, false, true);
     if (rot && clip_off) ADY_FE2_GO(true, true, false);
     if (rot) ADY_FE2_GO(true, false, false);

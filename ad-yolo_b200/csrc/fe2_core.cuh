@@ -144,6 +144,12 @@ ADY_HD void p_dft15(c2 (&x)[15]) {
     }
 }
 
+// order-preserving float <-> uint key (atomicMax / atomicMin on floats of any sign)
+ADY_HD uint32_t f2key(float f) {
+    union { float f; uint32_t u; } c; c.f = f;
+    return (c.u & 0x80000000u) ? ~c.u : (c.u | 0x80000000u);
+}
+
 // RotationAug combination number (utils/augmentations.py:46-70) -> bit0 = Y negated, bit1 = Z negated, bit2 = X negated,
 // bit3 = X <-> Y swap (the table of frontend_core.cuh::rot_bits as a 64-bit immediate)
 ADY_HD unsigned rot_bits_rt(int comb) { return (unsigned)((0xFDECA8B964753120ull >> (4 * (comb & 15))) & 15ull); }
@@ -165,10 +171,8 @@ constexpr int MEL_L = NT >= 192 ? 7 : 9;     // schedule rows: non-zeros per lan
 constexpr int NJOBS = NT >= 192 ? 192 : 160; // lane-jobs of the mel projection (191 / 156 used), one per thread
 constexpr int NREG = 112;                    // regular pair-tasks per frame in stage C (c = 1..7, k16 = 0..15)
 constexpr int NC0 = 9;                       // c = 0 pair-tasks per frame (k16 = 1..7 and the two self-mirror rows)
-constexpr int REC_PITCH = 65;                // partial record of job i of mel j lives at record slot i * 65 + j (16-byte planes)
 constexpr int REC_MAXJOBS = 9;               // <= 9 jobs per mel filter (61 non-zeros / 7)
-constexpr int REC_SLOTS = REC_MAXJOBS * REC_PITCH;
-constexpr int REC_PLANE = REC_SLOTS * 16;    // 4 planes: (frame 0 | frame 1) x (powers | intensities)
+constexpr int REC_PLANE = NJOBS * 16;        // partial record of job q: slot q of 4 planes (frame 0 | frame 1) x (powers | intensities)
 
 struct MelEnt {            // one non-zero: byte offsets of the bin's two V records inside a frame's buffer + weight
     uint16_t offa, offb;
@@ -179,8 +183,7 @@ struct Tables {            // device-resident constants of the fe2 kernel (built
     float win[16 * 80];            // stage A: 2^-16 x periodic Hann at the sample lane l (task r = 16 l mod 75) loads as n16, [n16][l]
     float tw75[15 * 4 * 2];        // stage C: W75^{b c} as (wr, wi) for c = 0..14, b = 1..4
     MelEnt ent[MEL_L * NJOBS];     // [row][job]
-    uint8_t mel_njobs[NMEL];       // number of lane-jobs of mel j (<= 7)
-    uint16_t job_rec[NJOBS];       // record slot of job q: i * REC_PITCH + j for the i-th job of mel j
+    uint8_t mel_job0[NMEL], mel_njobs[NMEL];   // lane-jobs of mel j: mel_job0[j] .. + mel_njobs[j]  (record slot = job index)
     uint8_t job_mel[NJOBS];        // (diagnostics / emulation)
 };
 
@@ -191,8 +194,8 @@ struct SmemLayout {
     static constexpr int off_tw = off_ent + MEL_L * NJOBS * 8;            // float2 [15][4]
     static constexpr int off_win = off_tw + 15 * 4 * 8;                   // float [16][80]
     static constexpr int off_scale = off_win + 16 * 80 * 4;               // float2 [7][64]: (istd, -mean*istd)
-    static constexpr int off_meljobs = off_scale + 7 * NMEL * 8;          // uint8 [64]
-    static constexpr int total = ((off_meljobs + NMEL + 15) / 16) * 16;
+    static constexpr int off_meljobs = off_scale + 7 * NMEL * 8;          // uint8 [2][64]
+    static constexpr int total = ((off_meljobs + 2 * NMEL + 15) / 16) * 16;
 };
 static_assert(4 * REC_PLANE <= TFR * X_BYTES, "partial records alias the frame buffers");
 static_assert(SmemLayout::off_x % 16 == 0 && SmemLayout::off_ent % 16 == 0 && SmemLayout::off_tw % 16 == 0, "alignment");

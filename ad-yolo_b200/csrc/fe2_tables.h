@@ -131,13 +131,8 @@ inline void fill_tables(const float* mel, Tables& t, MelPlan& plan, bool& ok) {
     ok = build_mel_plan(mel, plan);
     if (!ok) return;
     for (size_t i = 0; i < plan.ent.size(); ++i) t.ent[i] = plan.ent[i];
-    for (int j = 0; j < NMEL; ++j) t.mel_njobs[j] = (uint8_t)plan.njobs[j];
-    for (int q = 0; q < NJOBS; ++q) {
-        const int j = plan.job_mel[q];
-        t.job_mel[q] = (uint8_t)(j < 0 ? 0 : j);
-        // idle jobs (no filter) park their all-zero record in an unused slot: mel 0 has a single job
-        t.job_rec[q] = (uint16_t)(j < 0 ? (REC_MAXJOBS - 1) * REC_PITCH : (q - plan.job0[j]) * REC_PITCH + j);
-    }
+    for (int j = 0; j < NMEL; ++j) { t.mel_job0[j] = (uint8_t)plan.job0[j]; t.mel_njobs[j] = (uint8_t)plan.njobs[j]; }
+    for (int q = 0; q < NJOBS; ++q) t.job_mel[q] = (uint8_t)(plan.job_mel[q] < 0 ? 0 : plan.job_mel[q]);
 }
 
 }  // namespace fe2

@@ -282,14 +282,56 @@ clamp_topdb_kernel(float* __restrict__ out, const float* __restrict__ mean, cons
 
 // ------------------------------------------------------------------------------------------------
 size_t frontend_workspace_bytes(int B, long long N) {
-    (void)B; (void)N;
-    return 64;   // [flags int x4]
+    (void)N;
+    // [flags int x4 | pad to 64] [max key uint32 (B,4)] [min key uint32 (B,4)]: per-(clip, log-mel channel) extrema of
+    // the un-clamped dB values, left by the fe2 kernel for the top_db pass (order-preserving float keys, f2key)
+    return 64 + (size_t)(B > 0 ? B : 0) * 32;
 }
 
+// top_db pass of the fe2 path: the fused kernel already knows every (clip, channel) maximum and minimum (its epilogue
+// reduces them per warp and keeps them in the workspace), so a plane whose minimum is within top_db of its maximum --
+// the usual case -- costs one block that returns at once, and the others are rewritten in one pass (no max pass).
+__global__ void __launch_bounds__(256)
+clamp_topdb_known_kernel(float* __restrict__ out, const float* __restrict__ mean, const float* __restrict__ istd,
+                         int T, float top_db, int nch, const uint32_t* __restrict__ kmax, const uint32_t* __restrict__ kmin) {
+    const int b = blockIdx.x >> 2, c = blockIdx.x & 3;
+    const float mx = key2f(kmax[blockIdx.x]), mn = key2f(kmin[blockIdx.x]);
+    const float thr = mx - top_db;
+    if (!(mn < thr)) return;
+    float4* base = reinterpret_cast<float4*>(out + ((long long)b * nch + c) * T * NMEL);
+    const int n4 = T * (NMEL / 4);
+    const int j4 = threadIdx.x & 15;
+    float th[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float mu = mean ? mean[c * NMEL + 4 * j4 + q] : 0.f, is = istd ? istd[c * NMEL + 4 * j4 + q] : 1.f;
+        th[q] = fmaf(thr, is, -mu * is);                                   // same form as the front-end epilogue
+    }
+    for (int i = threadIdx.x; i < n4; i += 256) {                          // 256 % 16 == 0 -> j4 is loop-invariant
+        float4 v = base[i];
+        if (v.x < th[0] || v.y < th[1] || v.z < th[2] || v.w < th[3]) {
+            v.x = fmaxf(v.x, th[0]); v.y = fmaxf(v.y, th[1]); v.z = fmaxf(v.z, th[2]); v.w = fmaxf(v.w, th[3]);
+            base[i] = v;
+        }
+    }
+}
+
+static bool frontend_is_v1() {
+    static const bool v1 = [] { const char* e = getenv("ADYOLO_FRONTEND"); return e && e[0] == 'v' && e[1] == '1'; }();
+    return v1;
+}
+
+// ws: the workspace the preceding fe2 launch left the extrema in (NULL: recompute the maxima from `out`)
 int launch_features_clamp_nch(float* out, int B, long long N, const float* mean, const float* istd, float top_db, int nch,
-                               cudaStream_t stream) {
+                               const void* ws, cudaStream_t stream) {
     const long long T = N / HOP;
     if (B <= 0 || T <= 0) return set_error(ADY_ERR_INVALID, "features_clamp: empty input");
+    if (ws && !frontend_is_v1()) {
+        const uint32_t* kmax = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(ws) + 64);
+        clamp_topdb_known_kernel<<<B * 4, 256, 0, stream>>>(out, mean, istd, (int)T, top_db, nch, kmax, kmax + (size_t)B * 4);
+        ADY_LAUNCH_CHECK("clamp_topdb_known_kernel");
+        return ADY_OK;
+    }
     clamp_topdb_kernel<<<B * 4, 256, 0, stream>>>(out, mean, istd, (int)T, top_db, nch);
     ADY_LAUNCH_CHECK("clamp_topdb_kernel");
     return ADY_OK;
@@ -297,12 +339,7 @@ int launch_features_clamp_nch(float* out, int B, long long N, const float* mean,
 
 int launch_features_foa_clamp(float* out, int B, long long N, const float* mean, const float* istd, float top_db,
                               void* ws, cudaStream_t stream) {
-    (void)ws;
-    const long long T = N / HOP;
-    if (B <= 0 || T <= 0) return set_error(ADY_ERR_INVALID, "features_foa_clamp: empty input");
-    clamp_topdb_kernel<<<B * 4, 256, 0, stream>>>(out, mean, istd, (int)T, top_db, NCH_FOA);
-    ADY_LAUNCH_CHECK("clamp_topdb_kernel");
-    return ADY_OK;
+    return launch_features_clamp_nch(out, B, N, mean, istd, top_db, NCH_FOA, ws, stream);
 }
 
 template <bool ROT, bool VIEW, bool MIC>
@@ -332,8 +369,7 @@ int launch_features_foa(const int16_t* audio, int B, long long N, const float* m
     if (N <= HOP) return set_error(ADY_ERR_INVALID, "features_foa: reflect padding needs N > %d samples", HOP);
     // The product path is the second-generation kernel (fe2.cu).  ADYOLO_FRONTEND=v1 selects the round-1 kernel of
     // this file for A/B measurements (both are hand-written sm_100a kernels; neither is a fallback).
-    static const bool use_v1 = [] { const char* e = getenv("ADYOLO_FRONTEND"); return e && e[0] == 'v' && e[1] == '1'; }();
-    if (!use_v1) {
+    if (!frontend_is_v1()) {
         int rc2 = launch_features_foa_fe2(audio, B, N, mean, istd, dc_offset, rot, clip_off, out, ws, stream);
         if (rc2) return rc2;
         if (apply_topdb) return launch_features_foa_clamp(out, B, N, mean, istd, top_db, ws, stream);

@@ -41,7 +41,7 @@ int launch_features_mic_logmel(const int16_t* audio, int B, long long N, const f
                                float dc_offset, float top_db, int apply_topdb, float* out, float2* spec, void* ws,
                                cudaStream_t stream);
 int launch_features_clamp_nch(float* out, int B, long long N, const float* mean, const float* istd, float top_db, int nch,
-                               cudaStream_t stream);
+                               const void* ws, cudaStream_t stream);
 int launch_features_foa_clamp(float* out, int B, long long N, const float* mean, const float* istd, float top_db,
                               void* ws, cudaStream_t stream);
 

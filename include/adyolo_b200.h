@@ -87,9 +87,11 @@ int adyolo_features_foa_views(const int16_t* audio, const int64_t* clip_offsets,
                               const int8_t* rot_comb, float* out, void* workspace, int apply_topdb, void* stream);
 
 /* Second half of adyolo_features_foa when it was called with apply_topdb = 0: applies the
- * power_to_db top_db clamp (datasets.py:265).  The per-(clip,channel) maximum is recomputed from
- * `out` itself (one block per plane, pass 1 max, pass 2 rewrite of the values below max - top_db);
- * `workspace` is unused.  Exposed separately so the two kernels can be timed individually.   */
+ * power_to_db top_db clamp (datasets.py:265) from the per-(clip,channel) maxima and minima of the
+ * un-clamped dB values that call left in `workspace` (the fused kernel's epilogue reduces them): a
+ * plane whose minimum is within top_db of its maximum is left alone, the others are rewritten in one
+ * pass.  Pass the SAME workspace, untouched in between.  Exposed separately so the two kernels can
+ * be timed individually.                                                                        */
 int adyolo_features_foa_clamp(float* out, int B, int64_t N, const adyolo_frontend_cfg* cfg, const float* mean,
                               const float* inv_std, void* workspace, void* stream);
 

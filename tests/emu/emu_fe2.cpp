@@ -79,8 +79,8 @@ extern "C" int emu_fe2_features_foa(const int16_t* audio, int B, long long N, co
         for (int q = 0; q < NJOBS; ++q)                           // partial records over the frame buffers, 4 planes
             for (int f = 0; f < TFR; ++f) {
                 const f2* a = &accs[(q * TFR + f) * 4];
-                st_f4(s_x + (2 * f) * REC_PLANE + tab.job_rec[q] * 16, lo2(a[0]), hi2(a[0]), lo2(a[1]), hi2(a[1]));
-                st_f4(s_x + (2 * f + 1) * REC_PLANE + tab.job_rec[q] * 16, lo2(a[2]), hi2(a[2]), lo2(a[3]), hi2(a[3]));
+                st_f4(s_x + (2 * f) * REC_PLANE + q * 16, lo2(a[0]), hi2(a[0]), lo2(a[1]), hi2(a[1]));
+                st_f4(s_x + (2 * f + 1) * REC_PLANE + q * 16, lo2(a[2]), hi2(a[2]), lo2(a[3]), hi2(a[3]));
             }
         for (int e = 0; e < 128; ++e) {                           // epilogue: thread = (frame, mel)
             const int f = e >> 6, j = e & 63;
@@ -88,8 +88,8 @@ extern "C" int emu_fe2_features_foa(const int16_t* audio, int B, long long N, co
             float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             for (int i = 0; i < tab.mel_njobs[j]; ++i) {
                 float r[8];
-                memcpy(r, s_x + (2 * f) * REC_PLANE + (i * REC_PITCH + j) * 16, 16);
-                memcpy(r + 4, s_x + (2 * f + 1) * REC_PLANE + (i * REC_PITCH + j) * 16, 16);
+                memcpy(r, s_x + (2 * f) * REC_PLANE + (tab.mel_job0[j] + i) * 16, 16);
+                memcpy(r + 4, s_x + (2 * f + 1) * REC_PLANE + (tab.mel_job0[j] + i) * 16, 16);
                 for (int c = 0; c < 8; ++c) v[c] += r[c];
             }
             // record order (|W|^2,|Z|^2,|Y|^2,|X|^2, I_Y, I_Z, I_X, -) -> channels mel W,Y,Z,X, iv Y,Z,X
