@@ -26,7 +26,10 @@ namespace ady {
 int build_fe2_tables_host(fe2::Tables* t);   // tables.cu
 namespace fe2 {
 
-constexpr int CTAS_PER_SM = 3;
+#ifndef ADY_FE2_CTAS
+#define ADY_FE2_CTAS 3
+#endif
+constexpr int CTAS_PER_SM = ADY_FE2_CTAS;   // 3 in the product; 2 / 4 only for occupancy experiments (4 needs the ADY_FE2_ALIAS_X timing hack)
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -136,14 +139,14 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
             if (slot < 2 * NREG) {
                 const int f = slot >= NREG, task = slot - f * NREG;
                 if (f < nf) {
-                    if (MIC) stage_c_mic<false>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, phasor + ((long long)b * T + t0 + f) * PH_K);
-                    else stage_c_foa<false>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, rb);
+                    if (MIC) stage_c_mic<false>(s_x + f * X_STRIDE, s_tw, task, dc0, dc1, phasor + ((long long)b * T + t0 + f) * PH_K);
+                    else stage_c_foa<false>(s_x + f * X_STRIDE, s_tw, task, dc0, dc1, rb);
                 }
             } else if (rd == 1 && tid >= NT - 32 && tid < NT - 32 + 2 * NC0) {
                 const int i = tid - (NT - 32), f = i >= NC0, task = i - f * NC0;
                 if (f < nf) {
-                    if (MIC) stage_c_mic<true>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, phasor + ((long long)b * T + t0 + f) * PH_K);
-                    else stage_c_foa<true>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, rb);
+                    if (MIC) stage_c_mic<true>(s_x + f * X_STRIDE, s_tw, task, dc0, dc1, phasor + ((long long)b * T + t0 + f) * PH_K);
+                    else stage_c_foa<true>(s_x + f * X_STRIDE, s_tw, task, dc0, dc1, rb);
                 }
             }
         }

@@ -166,7 +166,12 @@ constexpr int ROWP = 80;                     // pitch of a 75-sample row of the 
 constexpr int NROWS = 8 * (TFR + 1);         // 3 hops = 24 rows
 constexpr int SAMP_BYTES = NROWS * ROWP * 8; // 15 360
 constexpr int XSLOTS = 1210;                 // 16-byte slots per frame: 1200 points + 2 x 5 (Vb of the self-mirror tasks)
-constexpr int X_BYTES = XSLOTS * 16;         // 19 456
+constexpr int X_BYTES = XSLOTS * 16;
+#ifdef ADY_FE2_ALIAS_X
+constexpr int X_STRIDE = 0;
+#else
+constexpr int X_STRIDE = X_BYTES;            // byte distance between the two frame buffers of a tile
+#endif
 constexpr int MEL_L = NT >= 192 ? 7 : 9;     // schedule rows: non-zeros per lane-job
 constexpr int NJOBS = NT >= 192 ? 192 : 160; // lane-jobs of the mel projection (191 / 156 used), one per thread
 constexpr int NREG = 112;                    // regular pair-tasks per frame in stage C (c = 1..7, k16 = 0..15)
@@ -190,7 +195,11 @@ struct Tables {            // device-resident constants of the fe2 kernel (built
 struct SmemLayout {
     static constexpr int off_samples = 0;
     static constexpr int off_x = SAMP_BYTES;                              // TFR frame buffers
+#ifdef ADY_FE2_ALIAS_X   // timing experiment only (wrong results): both frames share one buffer so that 4 CTAs fit
+    static constexpr int off_ent = off_x + X_BYTES;
+#else
     static constexpr int off_ent = off_x + TFR * X_BYTES;                 // MelEnt [MEL_L][NJOBS]
+#endif
     static constexpr int off_tw = off_ent + MEL_L * NJOBS * 8;            // float2 [15][4]
     static constexpr int off_win = off_tw + 15 * 4 * 8;                   // float [16][80]
     static constexpr int off_scale = off_win + 16 * 80 * 4;               // float2 [7][64]: (istd, -mean*istd)
@@ -271,13 +280,25 @@ ADY_HD void stage_a(const unsigned char* __restrict__ samp, const float* __restr
         memcpy(&wy, sp + off, 4); memcpy(&zx, sp + off + 4, 4);
 #endif
         const float w = win[n16 * 80 + l];
+#if defined(__CUDA_ARCH__)
+        // int16 -> float without the XU pipe (64 I2F.S16 per task kept it busy for 8 cycles each and made it the
+        // bottleneck of this stage): flip the sign bit (offset binary u = x + 32768), plant u in the mantissa of
+        // 2^23 with one byte permute, and subtract 2^23 + 32768 -- exact -- with one packed add per channel pair.
+        const uint32_t a = wy ^ 0x80008000u, c = zx ^ 0x80008000u;
+        const f2 magic = ADY_K2(-8421376.0);                                          // -(2^23 + 2^15)
+        const f2 re = mk2(__uint_as_float(__byte_perm(a, 0x4B000000u, 0x7410)), __uint_as_float(__byte_perm(c, 0x4B000000u, 0x7410))) + magic;
+        const f2 im = mk2(__uint_as_float(__byte_perm(a, 0x4B000000u, 0x7432)), __uint_as_float(__byte_perm(c, 0x4B000000u, 0x7432))) + magic;
+        x[n16].re = re * dup2(w);                                                     // (W, Z)
+        x[n16].im = im * dup2(w);                                                     // (Y, X)
+#else
         const float sW = (float)(int16_t)(wy & 0xffffu), sY = (float)(int16_t)(wy >> 16);
         const float sZ = (float)(int16_t)(zx & 0xffffu), sX = (float)(int16_t)(zx >> 16);
         x[n16].re = mk2(sW * w, sZ * w);
         x[n16].im = mk2(sY * w, sX * w);
+#endif
     }
     p_dft16(x);
-    unsigned char* xo = xf + f * X_BYTES + l * 16;
+    unsigned char* xo = xf + f * X_STRIDE + l * 16;
 #pragma unroll
     for (int s = 0; s < 16; ++s) st_c2(xo + dft16_slot_k(s) * (75 * 16), x[s]);   // X1 slot (k16, n75) = 75 k16 + n75
 }
@@ -289,7 +310,7 @@ ADY_HD void stage_a(const unsigned char* __restrict__ samp, const float* __restr
 // 16-byte bank group, and the mel gather (lanes = neighbouring bins) would serialise; with pi they are 85 slots apart.
 ADY_HD constexpr int pi15(int c) { return (2 * c) % 15; }
 ADY_HD void stage_b(unsigned char* __restrict__ xf, int f, int u) {
-    unsigned char* p = xf + f * X_BYTES + (75 * (u & 15) + (u >> 4)) * 16;
+    unsigned char* p = xf + f * X_STRIDE + (75 * (u & 15) + (u >> 4)) * 16;
     c2 x[15];
 #pragma unroll
     for (int a = 0; a < 15; ++a) ld_c2(p + a * 80, x[a]);
@@ -536,11 +557,11 @@ ADY_HD void mel_job(const unsigned char* __restrict__ x0, const MelEnt* __restri
 #pragma unroll
         for (int f = 0; f < TFR; ++f) {
             c2 a, b;
-            ld_c2(x0 + f * X_BYTES + e[it].offa, a);
+            ld_c2(x0 + f * X_STRIDE + e[it].offa, a);
             acc[f][0] = fma2(a.re, w, acc[f][0]);
             acc[f][1] = fma2(a.im, w, acc[f][1]);
             if (WITH_IV) {
-                ld_c2(x0 + f * X_BYTES + e[it].offb, b);
+                ld_c2(x0 + f * X_STRIDE + e[it].offb, b);
                 acc[f][2] = fma2(b.re, w, acc[f][2]);
                 acc[f][3] = fma2(b.im, w, acc[f][3]);
             }

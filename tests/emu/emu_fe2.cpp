@@ -63,11 +63,11 @@ extern "C" int emu_fe2_features_foa(const int16_t* audio, int B, long long N, co
         }
         for (int tid = 0; tid < 2 * NREG; ++tid) {                // stage C: the 224 regular pair-tasks, one per thread
             const int f = tid >= NREG, task = tid - f * NREG;
-            if (f < nf) stage_c_foa<false>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, rb);
+            if (f < nf) stage_c_foa<false>(s_x + f * X_STRIDE, s_tw, task, dc0, dc1, rb);
         }
         for (int tid = 0; tid < 2 * NC0; ++tid) {                 // ... and the 18 c = 0 pair-tasks
             const int f = tid >= NC0, task = tid - f * NC0;
-            if (f < nf) stage_c_foa<true>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, rb);
+            if (f < nf) stage_c_foa<true>(s_x + f * X_STRIDE, s_tw, task, dc0, dc1, rb);
         }
         std::vector<f2> accs((size_t)NJOBS * TFR * 4);             // mel jobs (all V reads happen before any record is written)
         for (int q = 0; q < NJOBS; ++q) {
@@ -146,8 +146,8 @@ extern "C" int emu_fe2_mic_phasors(const int16_t* audio, long long N, const floa
         for (int tid = 0; tid < NT_AB; ++tid) { const int f = tid / 80, u = tid % 80; if (f < nf) stage_b(s_x, f, u); }
         for (int f = 0; f < nf; ++f) {
             uint4* ph = reinterpret_cast<uint4*>(phasors + ((size_t)(t0 + f) * PH_K) * 8);   // 8 floats per position
-            for (int task = 0; task < NREG; ++task) stage_c_mic<false>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, ph);
-            for (int task = 0; task < NC0; ++task) stage_c_mic<true>(s_x + f * X_BYTES, s_tw, task, dc0, dc1, ph);
+            for (int task = 0; task < NREG; ++task) stage_c_mic<false>(s_x + f * X_STRIDE, s_tw, task, dc0, dc1, ph);
+            for (int task = 0; task < NC0; ++task) stage_c_mic<true>(s_x + f * X_STRIDE, s_tw, task, dc0, dc1, ph);
         }
     }
     return 0;
