@@ -26,10 +26,7 @@ namespace ady {
 int build_fe2_tables_host(fe2::Tables* t);   // tables.cu
 namespace fe2 {
 
-#ifndef ADY_FE2_CTAS
-#define ADY_FE2_CTAS 3
-#endif
-constexpr int CTAS_PER_SM = ADY_FE2_CTAS;   // 3 in the product; 2 / 4 only for occupancy experiments (4 needs the ADY_FE2_ALIAS_X timing hack)
+constexpr int CTAS_PER_SM = ADY_FE2_CTAS;   // 3: tables in shared memory; 4: tables read through L1 (fe2_core.cuh::TABLES_IN_SMEM)
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -73,7 +70,7 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned char* s_samp = smem + SmemLayout::off_samples;
     unsigned char* s_x = smem + SmemLayout::off_x;
-    MelEnt* s_ent = reinterpret_cast<MelEnt*>(smem + SmemLayout::off_ent);
+    MelEnt* s_ent = reinterpret_cast<MelEnt*>(smem + SmemLayout::off_ent);           // (only with TABLES_IN_SMEM)
     unsigned char* s_tw = smem + SmemLayout::off_tw;
     float* s_win = reinterpret_cast<float*>(smem + SmemLayout::off_win);
     float2* s_scale = reinterpret_cast<float2*>(smem + SmemLayout::off_scale);
@@ -94,14 +91,16 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
     cp_async_commit();
     // constant tables -> smem (once per persistent CTA)
     {
-        const uint2* src = reinterpret_cast<const uint2*>(tab->ent);
-        uint2* dst = reinterpret_cast<uint2*>(s_ent);
-        for (int i = tid; i < MEL_L * NJOBS; i += NT) dst[i] = src[i];
         for (int i = tid; i < 15 * 4 * 2; i += NT) reinterpret_cast<float*>(s_tw)[i] = tab->tw75[i];
-        for (int i = tid; i < 16 * 80; i += NT) s_win[i] = tab->win[i];
-        for (int i = tid; i < 7 * NMEL; i += NT) {   // standardisation as one FMA: x * is + (-mu * is)
-            const float mu = mean ? mean[i] : 0.f, is = istd ? istd[i] : 1.f;
-            s_scale[i] = make_float2(is, -mu * is);
+        if (TABLES_IN_SMEM) {
+            const uint2* src = reinterpret_cast<const uint2*>(tab->ent);
+            uint2* dst = reinterpret_cast<uint2*>(s_ent);
+            for (int i = tid; i < MEL_L * NJOBS; i += NT) dst[i] = src[i];
+            for (int i = tid; i < 16 * 80; i += NT) s_win[i] = tab->win[i];
+            for (int i = tid; i < 7 * NMEL; i += NT) {   // standardisation as one FMA: x * is + (-mu * is)
+                const float mu = mean ? mean[i] : 0.f, is = istd ? istd[i] : 1.f;
+                s_scale[i] = make_float2(is, -mu * is);
+            }
         }
         if (tid < NMEL) { s_meljobs[tid] = tab->mel_job0[tid]; s_meljobs[NMEL + tid] = tab->mel_njobs[tid]; }
     }
@@ -114,7 +113,7 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
         __syncthreads();                                   // samples landed; previous tile's epilogue is done with X
 
         // ---- stage A
-        if (ab && lA < 75 && fA < nf) stage_a(s_samp, s_win, s_x, fA, lA, ka);
+        if (ab && lA < 75 && fA < nf) stage_a(s_samp, TABLES_IN_SMEM ? s_win : tab->win, s_x, fA, lA, ka);
         __syncthreads();
 
         // samples are consumed: prefetch the next tile while the rest of this one runs
@@ -154,7 +153,7 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
 
         // ---- mel projection: lane-job tid, both frames
         f2 acc[TFR][4];
-        if (tid < NJOBS) mel_job<!MIC>(s_x, s_ent + tid, acc);
+        if (tid < NJOBS) mel_job<!MIC>(s_x, (TABLES_IN_SMEM ? s_ent : tab->ent) + tid, acc);
         __syncthreads();                                   // every V read is done -> records may overwrite the frame buffers
         if (tid < NJOBS) {
 #pragma unroll
@@ -203,7 +202,12 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
             const long long T64 = (long long)T * NMEL;
 #pragma unroll
             for (int c = 0; c < (MIC ? 4 : 7); ++c) {
-                const float2 k = s_scale[c * NMEL + j];
+                float2 k;
+                if (TABLES_IN_SMEM) k = s_scale[c * NMEL + j];
+                else {
+                    const float mu = mean ? mean[c * NMEL + j] : 0.f, is = istd ? istd[c * NMEL + j] : 1.f;
+                    k = make_float2(is, -mu * is);
+                }
                 o[c * T64] = fmaf(v[c], k.x, k.y);
             }
         }

@@ -192,22 +192,25 @@ struct Tables {            // device-resident constants of the fe2 kernel (built
     uint8_t job_mel[NJOBS];        // (diagnostics / emulation)
 };
 
+#ifndef ADY_FE2_CTAS
+#define ADY_FE2_CTAS 3
+#endif
+// With 4 CTAs per SM only 56 KB of shared memory are left per CTA: the mel schedule, the window and the
+// standardisation constants (20 KB, read-only) then stay in global memory and are read through L1.
+constexpr bool TABLES_IN_SMEM = ADY_FE2_CTAS < 4;
+
 struct SmemLayout {
     static constexpr int off_samples = 0;
     static constexpr int off_x = SAMP_BYTES;                              // TFR frame buffers
-#ifdef ADY_FE2_ALIAS_X   // timing experiment only (wrong results): both frames share one buffer so that 4 CTAs fit
-    static constexpr int off_ent = off_x + X_BYTES;
-#else
-    static constexpr int off_ent = off_x + TFR * X_BYTES;                 // MelEnt [MEL_L][NJOBS]
-#endif
-    static constexpr int off_tw = off_ent + MEL_L * NJOBS * 8;            // float2 [15][4]
-    static constexpr int off_win = off_tw + 15 * 4 * 8;                   // float [16][80]
+    static constexpr int off_tw = off_x + TFR * X_BYTES;                  // float2 [15][4]
+    static constexpr int off_meljobs = off_tw + 15 * 4 * 8;               // uint8 [2][64]
+    static constexpr int off_ent = off_meljobs + 2 * NMEL;                // MelEnt [MEL_L][NJOBS]            (TABLES_IN_SMEM)
+    static constexpr int off_win = off_ent + MEL_L * NJOBS * 8;           // float [16][80]
     static constexpr int off_scale = off_win + 16 * 80 * 4;               // float2 [7][64]: (istd, -mean*istd)
-    static constexpr int off_meljobs = off_scale + 7 * NMEL * 8;          // uint8 [2][64]
-    static constexpr int total = ((off_meljobs + 2 * NMEL + 15) / 16) * 16;
+    static constexpr int total = TABLES_IN_SMEM ? ((off_scale + 7 * NMEL * 8 + 15) / 16) * 16 : ((off_ent + 15) / 16) * 16;
 };
 static_assert(4 * REC_PLANE <= TFR * X_BYTES, "partial records alias the frame buffers");
-static_assert(SmemLayout::off_x % 16 == 0 && SmemLayout::off_ent % 16 == 0 && SmemLayout::off_tw % 16 == 0, "alignment");
+static_assert(SmemLayout::off_x % 16 == 0 && SmemLayout::off_ent % 16 == 0 && SmemLayout::off_tw % 16 == 0 && SmemLayout::off_win % 16 == 0, "alignment");
 
 // ---------------------------------------------------------------- small memory helpers (same code on host and device)
 ADY_HD void ld_c2(const unsigned char* p, c2& v) {
