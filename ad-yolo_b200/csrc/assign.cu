@@ -15,9 +15,8 @@
 // Launches per call, no host synchronisation:
 //   assign_rows_kernel  : 1 thread / target row  -> D, masks, argmin; atomicOr label bits into a
 //                         per-anchor 64-bit state word; unnormalised angular gradients
-//   loss_weights_kernel : normalisers of the means from the final positive counts
-//   loss_anchor_kernel  : warp-autonomous pass over the anchors -> BCE sums and (when asked) d loss/d logit
-//   loss_finalize_kernel: scalar loss
+//   loss_anchor_kernel  : warp-autonomous pass over the anchors -> BCE sums, (when asked) d loss / d logit, and the
+//                         scalar loss by the last block to finish
 //   grad_scale_kernel   : backward of the autograd wrapper: grad *= grad_output unless it is exactly 1
 #include "assign_host.h"
 #include "common.cuh"
@@ -213,72 +212,100 @@ __device__ __forceinline__ float bce_bwd_logit(float p, float t) {
     return q >= 1e-12f ? (p - t) : (p - t) * q * 1e12f;
 }
 
-constexpr int LA_THREADS = 256;
+__device__ __forceinline__ float bce_fwd_pos(float p) { return -fmaxf(log_bce(p), -100.f); }          // bce_fwd(p, 1)
+__device__ __forceinline__ float bce_fwd_neg(float p) { return -fmaxf(__logf(1.0f - p), -100.f); }   // bce_fwd(p, 0)
 
-// Normalisers of the means of loss.py:236-249, computed once from the final counts (FP64 division
-// by every thread of the big kernel was 20 % of its stall samples).
-__global__ void loss_weights_kernel(long long n_anchor, AssignCfg cfg, LossAccum* __restrict__ acc) {
+constexpr int LA_THREADS = 256;
+#ifndef ADY_LA_MINB
+#define ADY_LA_MINB 4
+#endif
+
+struct LossW {
+    float w_pos[ADY_MAX_THR], w_neg[ADY_MAX_THR], w_cls[ADY_MAX_THR], w_ang, w_neg_sum;
+};
+
+// Normalisers of the means of loss.py:236-249 from the final counts, once per block (FP64 divisions by every thread
+// were 20 % of the kernel's stall samples; a separate one-block launch cost 3 us of the step), times the upstream
+// gradient (device scalar).
+__device__ __forceinline__ void loss_weights_block(long long n_anchor, const AssignCfg& cfg, const LossAccum* acc, float gs,
+                                                   LossW* sw) {
     const int i = threadIdx.x;
     if (i < ADY_MAX_THR) {
         const double np_ = i < cfg.n_thr ? (double)acc->n_pos[i] : 0.0;
         const double nn_ = (double)n_anchor - np_;
-        acc->w_pos[i] = i < cfg.n_thr ? (float)(cfg.gain_obj / (cfg.n_thr * np_)) : 0.f;
-        acc->w_neg[i] = i < cfg.n_thr ? (float)(cfg.gain_nonobj / (cfg.n_thr * nn_)) : 0.f;
-        acc->w_cls[i] = i < cfg.n_thr ? (float)(cfg.gain_cls / (cfg.n_thr * np_ * cfg.nb_classes)) : 0.f;
+        sw->w_pos[i] = i < cfg.n_thr ? gs * (float)(cfg.gain_obj / (cfg.n_thr * np_)) : 0.f;
+        sw->w_neg[i] = i < cfg.n_thr ? gs * (float)(cfg.gain_nonobj / (cfg.n_thr * nn_)) : 0.f;
+        sw->w_cls[i] = i < cfg.n_thr ? gs * (float)(cfg.gain_cls / (cfg.n_thr * np_ * cfg.nb_classes)) : 0.f;
     }
-    if (i == 0) acc->w_ang = (float)(cfg.gain_ang / (180.0 * (double)acc->ang_cnt));
+    if (i == 32) {
+        sw->w_ang = gs * (float)(cfg.gain_ang / (180.0 * (double)acc->ang_cnt));
+        float t = 0.f;                                  // gradient weight of an anchor that is negative at every threshold
+        for (int k = 0; k < cfg.n_thr; ++k) {
+            const double nn_ = (double)n_anchor - (double)acc->n_pos[k];
+            t += gs * (float)(cfg.gain_nonobj / (cfg.n_thr * nn_));
+        }
+        sw->w_neg_sum = t;
+    }
 }
 
-// Warp-autonomous pass over the anchors (no block barriers, no shared memory); a warp owns groups
-// of 32 consecutive anchors (group base is 16-byte aligned for any channel count):
-//   1. lane = anchor: objectness logit -> sigmoid, BCE sums, objectness gradient (kept in the lane)
-//   2. (positive anchor, class) items of the group (ballot-compacted) spread over the lanes:
-//      class BCE sums / gradients
-//   3. (grad only) the group's gradient rows are assembled in a per-warp shared-memory tile that
-//      is zero except for objectness, (u,v) and the positives' class entries, and copied out with
-//      coalesced float4 stores
-// do_sums: accumulate the BCE sums (forward); grad != NULL: write gscale * d loss / d logit.
-__global__ void __launch_bounds__(LA_THREADS)
+__device__ __forceinline__ double ld_fresh_f64(const double* p) {     // a value other blocks of this launch accumulated
+    return __longlong_as_double((long long)atomicAdd(reinterpret_cast<unsigned long long*>(const_cast<double*>(p)), 0ull));
+}
+
+// loss.py:219, 244-249 (means of empty sets are NaN exactly like torch)
+__device__ __forceinline__ float loss_total(long long n_anchor, const AssignCfg& cfg, const LossAccum* acc) {
+    double total = cfg.gain_ang * (acc->ang_sum / 180.0) / (double)acc->ang_cnt;
+    for (int i = 0; i < cfg.n_thr; ++i) {
+        const double np_ = (double)acc->n_pos[i], nn_ = (double)n_anchor - np_;
+        const double pos = ld_fresh_f64(&acc->s_pos[i]) / np_, neg = ld_fresh_f64(&acc->s_neg[i]) / nn_;
+        const double cls = ld_fresh_f64(&acc->s_cls[i]) / (np_ * cfg.nb_classes);
+        total += (pos * cfg.gain_obj + neg * cfg.gain_nonobj + cls * cfg.gain_cls) / cfg.n_thr;
+    }
+    return (float)total;
+}
+
+// Warp-autonomous pass over the anchors (no block barriers in the loop); a warp owns groups of 32 consecutive anchors
+// (the group base is 16-byte aligned for any channel count):
+//   1. lane = anchor: objectness logit -> sigmoid -> BCE sums and the objectness gradient.  The label word and the
+//      logit of the next group are in flight while the current one is processed.  An anchor without any positive bit
+//      (94 % of them) needs one log and no per-threshold loop: its BCE(p, 0) goes to one accumulator that is added to
+//      every threshold's negative sum at the end.
+//   2. positive anchors of the group, two per iteration (peeled off the ballot mask with ffs), 16 lanes each, lane =
+//      class: class BCE sums / gradients.  No rank -> lane search, no division.
+//   3. (GRAD) the group's gradient rows are assembled in a per-warp shared-memory tile that is zero except for the
+//      objectness / (u, v) / positive-class entries; it is copied out with coalesced streaming float4 stores and every
+//      float4 is zeroed again right after it was read.
+// The last block to finish (ticket) turns the sums into the scalar loss: no finalisation launch.
+// do_sums: accumulate the BCE sums (forward); GRAD: write gscale * d loss / d logit.
+template <bool GRAD>
+__global__ void __launch_bounds__(LA_THREADS, ADY_LA_MINB)
 loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCfg cfg,
                    const unsigned long long* __restrict__ state, const float2* __restrict__ ang_grad,
                    LossAccum* __restrict__ acc, float* __restrict__ grad, const float* __restrict__ gscale,
-                   int do_sums) {
+                   int do_sums, float* __restrict__ loss_out) {
     const unsigned CH = cfg.nb_classes + 3, C = cfg.nb_classes;
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-
-    // per-threshold normalisers (loss_weights_kernel) times the upstream gradient (device scalar)
-    const float gs = gscale ? gscale[0] : 1.0f;
-    float w_pos[ADY_MAX_THR], w_neg[ADY_MAX_THR], w_cls[ADY_MAX_THR];
-#pragma unroll
-    for (int i = 0; i < ADY_MAX_THR; ++i) {
-        w_pos[i] = gs * acc->w_pos[i];
-        w_neg[i] = gs * acc->w_neg[i];
-        w_cls[i] = gs * acc->w_cls[i];
-    }
-    const float w_ang = gs * acc->w_ang;
     const unsigned long long OBJ_ANY = 0x0001000100010001ull;
+
+    __shared__ LossW sw;
+    extern __shared__ __align__(16) float s_tile_all[];
+    float* tile = s_tile_all + (threadIdx.x >> 5) * (32 * CH);
+    if (GRAD) {
+        loss_weights_block(n_anchor, cfg, acc, gscale ? gscale[0] : 1.0f, &sw);
+        for (unsigned i = lane; i < 32 * CH; i += 32) tile[i] = 0.f;
+        __syncthreads();
+    }
+    const float w_neg_sum = GRAD ? sw.w_neg_sum : 0.f, w_ang = GRAD ? sw.w_ang : 0.f;
 
     // per-thread partial sums stay in FP32 (a thread sees only tens of anchors); they are widened
     // to FP64 for the warp reduction and the global accumulation
     float s_pos[ADY_MAX_THR] = {0, 0, 0, 0}, s_neg[ADY_MAX_THR] = {0, 0, 0, 0}, s_cls[ADY_MAX_THR] = {0, 0, 0, 0};
+    float s_neg_all = 0.f;
 
     const long long n_groups = (n_anchor + 31) / 32;
     const long long warp0 = ((long long)blockIdx.x * LA_THREADS + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * LA_THREADS) >> 5;
-    // gradient staging tile of this warp: exactly the global layout of its 32 anchors (32*CH
-    // floats).  It is kept all-zero between groups; per group only the objectness / (u,v) values
-    // and the class gradients of positive anchors are written, then it is copied out with float4
-    // stores and the touched class entries are zeroed again.
-    extern __shared__ __align__(16) float s_tile_all[];
-    float* tile = s_tile_all + (threadIdx.x >> 5) * (32 * CH);
-    if (grad) {
-        for (unsigned i = lane; i < 32 * CH; i += 32) tile[i] = 0.f;
-        __syncwarp();
-    }
-
-    // software pipeline: label word and objectness logit of the next group are in flight while the
-    // current group is processed
     unsigned long long st_n = 0ull;
     float x_n = 0.f;
     if (warp0 < n_groups && warp0 * 32 + lane < n_anchor) {
@@ -290,7 +317,6 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
         const unsigned na = (unsigned)min(32LL, n_anchor - a0);
         const unsigned nel = na * CH;
         const float* src = logit + a0 * CH;
-        float* dst = grad ? grad + a0 * CH : nullptr;
 
         // ---- pass 1: objectness, lane = anchor
         const bool valid = (unsigned)lane < na;
@@ -301,41 +327,51 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
             if (grp + n_warps < n_groups && an < n_anchor) { st_n = state[an]; x_n = logit[an * CH]; }
             else { st_n = 0ull; x_n = 0.f; }
         }
-        float go = 0.f;
+        const bool positive = valid && (st & OBJ_ANY);
         if (valid) {
             const float p = sigmoid_fast(x_obj);
-            const float g_pos = bce_bwd_logit(p, 1.f), g_neg = bce_bwd_logit(p, 0.f);
-            float l_pos = 0.f, l_neg = 0.f;
-            if (do_sums) { l_pos = bce_fwd(p, 1.f); l_neg = bce_fwd(p, 0.f); }
+            const float g_neg = bce_bwd_logit(p, 0.f);
+            float l_neg = 0.f;
+            if (do_sums) l_neg = bce_fwd_neg(p);
+            float go;
+            if (!positive) {
+                s_neg_all += l_neg;
+                go = w_neg_sum * g_neg;
+            } else {
+                const float g_pos = bce_bwd_logit(p, 1.f);
+                float l_pos = 0.f;
+                if (do_sums) l_pos = bce_fwd_pos(p);
+                go = 0.f;
 #pragma unroll
-            for (int i = 0; i < ADY_MAX_THR; ++i) {
-                if (i >= cfg.n_thr) break;
-                if ((st >> (16 * i)) & 1ull) { s_pos[i] += l_pos; go += w_pos[i] * g_pos; }
-                else                         { s_neg[i] += l_neg; go += w_neg[i] * g_neg; }
+                for (int i = 0; i < ADY_MAX_THR; ++i) {
+                    if (i >= cfg.n_thr) break;
+                    if ((st >> (16 * i)) & 1ull) { s_pos[i] += l_pos; if (GRAD) go += sw.w_pos[i] * g_pos; }
+                    else                         { s_neg[i] += l_neg; if (GRAD) go += sw.w_neg[i] * g_neg; }
+                }
+                if (GRAD && (st & 1ull)) {              // the angular term lives on the first threshold's positives
+                    const float2 ag = ang_grad[a0 + lane];
+                    tile[(unsigned)lane * CH + C + 1] = ag.x * w_ang;
+                    tile[(unsigned)lane * CH + C + 2] = ag.y * w_ang;
+                }
             }
-        }
-        const unsigned posmask = __ballot_sync(FULL, valid && (st & OBJ_ANY));
-        if (dst && valid) {
-            const float2 ag = ang_grad[a0 + lane];
-            tile[(unsigned)lane * CH] = go;
-            tile[(unsigned)lane * CH + C + 1] = ag.x * w_ang;
-            tile[(unsigned)lane * CH + C + 2] = ag.y * w_ang;
+            if (GRAD) tile[(unsigned)lane * CH] = go;
         }
 
-        // ---- pass 2: (positive anchor, class) items spread over the lanes; the loop count is
-        // warp-uniform so the shuffles that fetch the anchor's label word are convergent
-        const unsigned n_items = (unsigned)__popc(posmask) * C;
-        for (unsigned base = 0; base < n_items; base += 32) {
-            const unsigned it = base + lane;
-            const bool on = it < n_items;
-            const unsigned pi = on ? it / C : 0u, c = on ? it - pi * C : 0u;
-            const int al = (int)__fns(posmask, 0, (int)pi + 1);       // index of the pi-th positive anchor
+        // ---- pass 2: the positive anchors, two per iteration, lane = (which of the two, class)
+        unsigned m = __ballot_sync(FULL, positive);
+        while (m) {
+            const int al0 = __ffs(m) - 1;
+            m &= m - 1;
+            const int al1 = m ? __ffs(m) - 1 : -1;
+            m &= m - 1;                                  // (0 & anything = 0)
+            const int al = (lane & 16) ? al1 : al0;
+            const unsigned c = lane & 15;
             const unsigned long long sta = __shfl_sync(FULL, st, al & 31);
-            if (on) {
+            if (al >= 0 && c < C) {
                 const float pc = sigmoid_fast(src[(unsigned)al * CH + 1 + c]);
-                const float g1 = bce_bwd_logit(pc, 1.f), g0 = bce_bwd_logit(pc, 0.f);
                 float l1 = 0.f, l0 = 0.f;
-                if (do_sums) { l1 = bce_fwd(pc, 1.f); l0 = bce_fwd(pc, 0.f); }
+                if (do_sums) { l1 = bce_fwd_pos(pc); l0 = bce_fwd_neg(pc); }
+                const float g1 = bce_bwd_logit(pc, 1.f), g0 = bce_bwd_logit(pc, 0.f);
                 float gc = 0.f;
 #pragma unroll
                 for (int i = 0; i < ADY_MAX_THR; ++i) {
@@ -343,26 +379,24 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
                     if ((sta >> (16 * i)) & 1ull) {
                         const bool t = (sta >> (16 * i + 1 + c)) & 1ull;
                         s_cls[i] += t ? l1 : l0;
-                        gc += w_cls[i] * (t ? g1 : g0);
+                        if (GRAD) gc += sw.w_cls[i] * (t ? g1 : g0);
                     }
                 }
-                if (dst) tile[(unsigned)al * CH + 1 + c] = gc;
+                if (GRAD) tile[(unsigned)al * CH + 1 + c] = gc;
             }
         }
 
-        // ---- pass 3 (grad only): coalesced float4 copy-out of the tile, then restore the zeros
-        if (dst) {
+        // ---- pass 3 (GRAD): coalesced float4 copy-out of the tile; each float4 is zeroed again once it is in registers
+        if (GRAD) {
+            float* dst = grad + a0 * CH;
             __syncwarp();
             for (unsigned el = (unsigned)lane * 4; el < nel; el += 128) {
-                if (el + 4 <= nel) *reinterpret_cast<float4*>(dst + el) = *reinterpret_cast<const float4*>(tile + el);
-                else for (unsigned q = 0; el + q < nel; ++q) dst[el + q] = tile[el + q];
-            }
-            __syncwarp();
-            for (unsigned base = 0; base < n_items; base += 32) {
-                const unsigned it = base + lane;
-                if (it < n_items) {
-                    const unsigned pi = it / C, c = it - pi * C;
-                    tile[(unsigned)__fns(posmask, 0, (int)pi + 1) * CH + 1 + c] = 0.f;
+                if (el + 4 <= nel) {
+                    const float4 v = *reinterpret_cast<const float4*>(tile + el);
+                    *reinterpret_cast<float4*>(tile + el) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    __stcs(reinterpret_cast<float4*>(dst + el), v);
+                } else {
+                    for (unsigned q = 0; el + q < nel; ++q) { dst[el + q] = tile[el + q]; tile[el + q] = 0.f; }
                 }
             }
             __syncwarp();
@@ -372,9 +406,14 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
     // warp reduce (FP64) -> block reduce through shared memory -> one atomic per block and sum:
     // per-warp atomics on a handful of addresses serialise in L2 (10^5 of them cost ~10^2 us)
     __shared__ double s_red[LA_THREADS / 32][3 * ADY_MAX_THR];
+    __shared__ bool s_last;
     double d[3 * ADY_MAX_THR];
 #pragma unroll
-    for (int i = 0; i < ADY_MAX_THR; ++i) { d[i] = s_pos[i]; d[ADY_MAX_THR + i] = s_neg[i]; d[2 * ADY_MAX_THR + i] = s_cls[i]; }
+    for (int i = 0; i < ADY_MAX_THR; ++i) {
+        d[i] = s_pos[i];
+        d[ADY_MAX_THR + i] = i < cfg.n_thr ? (double)s_neg[i] + (double)s_neg_all : 0.0;
+        d[2 * ADY_MAX_THR + i] = s_cls[i];
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1)
 #pragma unroll
@@ -392,31 +431,32 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
             double* dstp = kind == 0 ? acc->s_pos : (kind == 1 ? acc->s_neg : acc->s_cls);
             atomicAdd(&dstp[i], t);
         }
+        __threadfence();
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&acc->done_blocks, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0 && loss_out) loss_out[0] = loss_total(n_anchor, cfg, acc);
 }
 
-__global__ void loss_finalize_kernel(long long n_anchor, AssignCfg cfg, const LossAccum* __restrict__ acc,
-                                     float* __restrict__ loss_out) {
-    if (threadIdx.x || blockIdx.x) return;
-    // loss.py:219, 244-249 (means of empty sets are NaN exactly like torch)
-    double total = cfg.gain_ang * (acc->ang_sum / 180.0) / (double)acc->ang_cnt;
-    for (int i = 0; i < cfg.n_thr; ++i) {
-        const double np_ = (double)acc->n_pos[i], nn_ = (double)n_anchor - np_;
-        const double pos = acc->s_pos[i] / np_, neg = acc->s_neg[i] / nn_;
-        const double cls = acc->s_cls[i] / (np_ * cfg.nb_classes);
-        total += (pos * cfg.gain_obj + neg * cfg.gain_nonobj + cls * cfg.gain_cls) / cfg.n_thr;
-    }
-    loss_out[0] = (float)total;
-}
-
-static int loss_anchor_blocks_per_sm() {
-    static int cached = 0;
-    if (!cached) {
+template <bool GRAD>
+static int loss_anchor_blocks(long long n_anchor, size_t shmem, int* blocks_out) {
+    static int per_sm = 0;
+    int dev = 0, sms = 0;
+    ADY_CUDA_CHECK(cudaGetDevice(&dev));
+    ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (!per_sm) {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, loss_anchor_kernel, LA_THREADS, 8 * 32 * 18 * 4) != cudaSuccess || n < 1) n = 2;
-        cached = n;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, loss_anchor_kernel<GRAD>, LA_THREADS, shmem) != cudaSuccess || n < 1) n = 2;
+        per_sm = n;
     }
-    return cached;
+    long long blocks = (n_anchor + LA_THREADS - 1) / LA_THREADS;
+    if (blocks > (long long)sms * per_sm) blocks = (long long)sms * per_sm;   // one resident wave
+    *blocks_out = (int)blocks;
+    return ADY_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -461,20 +501,19 @@ int launch_loss(const float* logit, const float* target, long long M, const long
         assign_rows_kernel<<<blocks, 128, 0, stream>>>(logit, target, M, M_dev, B, T, cfg, D, mask, argmin, state, ang, acc);
         ADY_LAUNCH_CHECK("assign_rows_kernel");
     }
-    int dev = 0, sms = 0;
-    ADY_CUDA_CHECK(cudaGetDevice(&dev));
-    ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    loss_weights_kernel<<<1, 32, 0, stream>>>(n_anchor, cfg, acc);
-    ADY_LAUNCH_CHECK("loss_weights_kernel");
-    long long blocks = (n_anchor + LA_THREADS - 1) / LA_THREADS;
-    const long long cap = (long long)sms * loss_anchor_blocks_per_sm();   // one resident wave
-    if (blocks > cap) blocks = cap;
-    const size_t shmem = grad_out ? (size_t)(LA_THREADS / 32) * 32 * (cfg.nb_classes + 3) * sizeof(float) : 0;
-    loss_anchor_kernel<<<(int)blocks, LA_THREADS, shmem, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out,
-                                                                   nullptr, 1);
+    int blocks = 0;
+    if (grad_out) {      // training: gradient, sums and the scalar loss in one launch
+        if (reinterpret_cast<uintptr_t>(grad_out) & 15) return set_error(ADY_ERR_INVALID, "adyolo_loss: grad must be 16-byte aligned");
+        const size_t shmem = (size_t)(LA_THREADS / 32) * 32 * (cfg.nb_classes + 3) * sizeof(float);
+        rc = loss_anchor_blocks<true>(n_anchor, shmem, &blocks);
+        if (rc) return rc;
+        loss_anchor_kernel<true><<<blocks, LA_THREADS, shmem, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out, nullptr, 1, loss_out);
+    } else {
+        rc = loss_anchor_blocks<false>(n_anchor, 0, &blocks);
+        if (rc) return rc;
+        loss_anchor_kernel<false><<<blocks, LA_THREADS, 0, stream>>>(logit, n_anchor, cfg, state, ang, acc, nullptr, nullptr, 1, loss_out);
+    }
     ADY_LAUNCH_CHECK("loss_anchor_kernel");
-    loss_finalize_kernel<<<1, 32, 0, stream>>>(n_anchor, cfg, acc, loss_out);
-    ADY_LAUNCH_CHECK("loss_finalize_kernel");
     return ADY_OK;
 }
 
@@ -489,15 +528,12 @@ int launch_loss_backward(const float* logit, int B, int T, const AssignCfg& cfg,
     LossAccum* acc = const_cast<LossAccum*>(reinterpret_cast<const LossAccum*>(ws));
     const unsigned long long* state = reinterpret_cast<const unsigned long long*>(acc + 1);
     const float2* ang = reinterpret_cast<const float2*>(state + n_anchor);
-    int dev = 0, sms = 0;
-    ADY_CUDA_CHECK(cudaGetDevice(&dev));
-    ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    long long blocks = (n_anchor + LA_THREADS - 1) / LA_THREADS;
-    const long long cap = (long long)sms * loss_anchor_blocks_per_sm();
-    if (blocks > cap) blocks = cap;
+    if (reinterpret_cast<uintptr_t>(grad_out) & 15) return set_error(ADY_ERR_INVALID, "adyolo_loss_backward: grad must be 16-byte aligned");
     const size_t shmem = (size_t)(LA_THREADS / 32) * 32 * (cfg.nb_classes + 3) * sizeof(float);
-    loss_anchor_kernel<<<(int)blocks, LA_THREADS, shmem, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out,
-                                                                   grad_output, 0);
+    int blocks = 0;
+    rc = loss_anchor_blocks<true>(n_anchor, shmem, &blocks);
+    if (rc) return rc;
+    loss_anchor_kernel<true><<<blocks, LA_THREADS, shmem, stream>>>(logit, n_anchor, cfg, state, ang, acc, grad_out, grad_output, 0, nullptr);
     ADY_LAUNCH_CHECK("loss_anchor_kernel(backward)");
     return ADY_OK;
 }

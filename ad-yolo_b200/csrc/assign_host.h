@@ -32,7 +32,7 @@ struct LossAccum {
     float w_pos[ADY_MAX_THR], w_neg[ADY_MAX_THR], w_cls[ADY_MAX_THR];   // gain / (n_thr * count), by loss_weights_kernel
     float w_ang, pad_f[3];
     int bad_rows;
-    int pad;
+    unsigned int done_blocks;    // ticket of loss_stream_kernel's last-block finalisation
 };
 
 size_t loss_workspace_bytes(int B, int T, const AssignCfg& cfg);

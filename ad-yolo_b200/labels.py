@@ -87,7 +87,7 @@ def label_rows_batched(events: torch.Tensor, nb_label_frames: int, grid: GridSpe
     with torch.cuda.device(events.device):
         ws = torch.empty(max(L.adyolo_label_workspace_bytes(E), 64), dtype=torch.uint8, device=events.device)
         cellmask = torch.empty(max(E, 1), dtype=torch.int32, device=events.device)
-        total = torch.zeros(1, dtype=torch.int64, device=events.device)
+        total = torch.empty(1, dtype=torch.int64, device=events.device)   # always written by adyolo_label_cells
         if rot_comb is not None:
             if rot_comb.dtype != torch.int8 or not rot_comb.is_cuda:
                 raise ValueError("rot_comb must be an int8 CUDA tensor")

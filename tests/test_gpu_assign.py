@@ -213,8 +213,35 @@ def test_fused_forward_gradient_reuse_and_repeat_backward(A):
     logit.grad = None
     (crit(logit, rows) * 0.25).sum().backward()                # expanded, non-unit upstream gradient
     assert torch.allclose(logit.grad, 0.25 * g1, rtol=1e-6, atol=0)
+    with torch.no_grad():                                       # validation kernel: other summation order
+        assert abs(crit(logit, rows).item() - loss.item()) <= 1e-6 * abs(loss.item())
+
+
+@pytest.mark.parametrize("C,grid_deg,anchors,BT", [(12, 60, 3, (1, 1)), (12, 60, 3, (3, 7)), (13, 60, 3, (3, 7)), (1, 45, 5, (2, 3)), (15, 90, 1, (5, 5))])
+def test_loss_streaming_pass_odd_shapes_vs_torch_oracle(A, C, grid_deg, anchors, BT):
+    """Gradient tensors whose element count is not a multiple of 4, channel counts 4..18, float4s straddling two
+    anchors, fewer float4s than one block: loss and d loss / d logit vs the torch oracle on the same GPU."""
+    B, T = BT
+    p = default_params(C, "cuda:0")
+    p["train_config"]["grid_size"] = [grid_deg, grid_deg]
+    p["train_config"]["nb_anchors"] = anchors
+    grid = A.labels.GridSpec(C, anchors, [grid_deg, grid_deg], 0.5)
+    rng = np.random.default_rng(C * 100 + grid_deg)
+    ev = _events(rng, B, T, C, max_ev=2)
+    if len(ev) == 0:
+        ev = np.array([[0, 0, 0, 10.0, 5.0]])
+    rows = A.label_rows_batched(torch.from_numpy(ev).cuda(), T, grid)
+    gen = torch.Generator(device="cuda").manual_seed(C)
+    logit = (2 * torch.randn((B, T, grid.nb_predicts * grid.nb_channels), device="cuda", generator=gen)).requires_grad_(True)
+    loss = A.ADYOLOloss(p)(logit, rows)
+    loss.backward()
+    l2 = logit.detach().clone().requires_grad_(True)
+    ref = ADYOLOlossOracle(p)(l2, rows)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert (logit.grad - l2.grad).abs().max().item() <= 2e-5 * l2.grad.abs().max().item()
     with torch.no_grad():
-        assert crit(logit, rows).item() == loss.item()
+        assert abs(A.ADYOLOloss(p)(logit, rows).item() - ref.item()) <= 1e-5 * abs(ref.item())
 
 
 def test_loss_nan_without_targets_and_bad_shapes(A):
