@@ -303,31 +303,69 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
     float s_pos[ADY_MAX_THR] = {0, 0, 0, 0}, s_neg[ADY_MAX_THR] = {0, 0, 0, 0}, s_cls[ADY_MAX_THR] = {0, 0, 0, 0};
     float s_neg_all = 0.f;
 
+    // Work distribution: a warp takes its first rounds of groups statically (group = warp + k * n_warps) and claims the
+    // last quarter from a counter, one group at a time: the time of a group depends on how many positives it holds, and
+    // with a purely static split a quarter of all warp time was spent waiting for the slowest warp at the final barrier.
+    // The group after the current one is always known (and its label words / objectness logits in flight) while the
+    // current one is processed; the claim for the one after that is issued a whole group ahead of its use.
     const long long n_groups = (n_anchor + 31) / 32;
     const long long warp0 = ((long long)blockIdx.x * LA_THREADS + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * LA_THREADS) >> 5;
+    const long long k_static = (n_groups / n_warps) * 3 / 4;
+    const long long dyn_base = k_static * n_warps;
+    long long k_round = -1;
+    auto issue_claim = [&]() -> long long {              // the value is meaningful in lane 0 (static rounds: in every lane)
+        ++k_round;
+        if (k_round < k_static) return warp0 + k_round * n_warps;
+        long long v = 0;
+        if (lane == 0) v = dyn_base + (long long)atomicAdd(&acc->next_group, 1u);
+        return v;
+    };
     unsigned long long st_n = 0ull;
     float x_n = 0.f;
-    if (warp0 < n_groups && warp0 * 32 + lane < n_anchor) {
-        st_n = state[warp0 * 32 + lane];
-        x_n = logit[(warp0 * 32 + lane) * CH];
-    }
-    for (long long grp = warp0; grp < n_groups; grp += n_warps) {
+    auto prefetch = [&](long long g) {
+        const long long an = g * 32 + lane;
+        if (g < n_groups && an < n_anchor) { st_n = state[an]; x_n = logit[an * CH]; }
+        else { st_n = 0ull; x_n = 0.f; }
+    };
+    long long grp = __shfl_sync(FULL, issue_claim(), 0);
+    long long raw_next = issue_claim();
+    prefetch(grp);
+    while (grp < n_groups) {
         const long long a0 = grp * 32;
         const unsigned na = (unsigned)min(32LL, n_anchor - a0);
         const unsigned nel = na * CH;
         const float* src = logit + a0 * CH;
-
-        // ---- pass 1: objectness, lane = anchor
         const bool valid = (unsigned)lane < na;
         const unsigned long long st = st_n;
         const float x_obj = x_n;
-        {
-            const long long an = (grp + n_warps) * 32 + lane;
-            if (grp + n_warps < n_groups && an < n_anchor) { st_n = state[an]; x_n = logit[an * CH]; }
-            else { st_n = 0ull; x_n = 0.f; }
-        }
+        const long long nxt = __shfl_sync(FULL, raw_next, 0);
+        prefetch(nxt);
+        raw_next = issue_claim();
+
+        // everything this group will wait for is requested before the arithmetic starts: the angular partials of
+        // the first threshold's positives and the class logits of the first two positive anchors
         const bool positive = valid && (st & OBJ_ANY);
+        unsigned m = __ballot_sync(FULL, positive);
+        const unsigned c = lane & 15;
+        auto peel = [&]() -> int {                       // next two positive anchors off the mask -> this half-warp's anchor
+            const int al0 = __ffs(m) - 1;
+            m &= m - 1;
+            const int al1 = m ? __ffs(m) - 1 : -1;
+            m &= m - 1;                                  // (0 & anything = 0)
+            return (lane & 16) ? al1 : al0;
+        };
+        int al = -1;
+        float xc = 0.f;
+        bool have = m != 0;                              // warp-uniform: a pair (or a single anchor) is pending in (al, xc)
+        if (have) {
+            al = peel();
+            if (al >= 0 && c < C) xc = src[(unsigned)al * CH + 1 + c];
+        }
+        float2 ag = make_float2(0.f, 0.f);
+        if (GRAD && positive && (st & 1ull)) ag = ang_grad[a0 + lane];   // the angular term lives on the first threshold's positives
+
+        // ---- pass 1: objectness, lane = anchor
         if (valid) {
             const float p = sigmoid_fast(x_obj);
             const float g_neg = bce_bwd_logit(p, 0.f);
@@ -348,8 +386,7 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
                     if ((st >> (16 * i)) & 1ull) { s_pos[i] += l_pos; if (GRAD) go += sw.w_pos[i] * g_pos; }
                     else                         { s_neg[i] += l_neg; if (GRAD) go += sw.w_neg[i] * g_neg; }
                 }
-                if (GRAD && (st & 1ull)) {              // the angular term lives on the first threshold's positives
-                    const float2 ag = ang_grad[a0 + lane];
+                if (GRAD && (st & 1ull)) {
                     tile[(unsigned)lane * CH + C + 1] = ag.x * w_ang;
                     tile[(unsigned)lane * CH + C + 2] = ag.y * w_ang;
                 }
@@ -357,18 +394,20 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
             if (GRAD) tile[(unsigned)lane * CH] = go;
         }
 
-        // ---- pass 2: the positive anchors, two per iteration, lane = (which of the two, class)
-        unsigned m = __ballot_sync(FULL, positive);
-        while (m) {
-            const int al0 = __ffs(m) - 1;
-            m &= m - 1;
-            const int al1 = m ? __ffs(m) - 1 : -1;
-            m &= m - 1;                                  // (0 & anything = 0)
-            const int al = (lane & 16) ? al1 : al0;
-            const unsigned c = lane & 15;
-            const unsigned long long sta = __shfl_sync(FULL, st, al & 31);
-            if (al >= 0 && c < C) {
-                const float pc = sigmoid_fast(src[(unsigned)al * CH + 1 + c]);
+        // ---- pass 2: the positive anchors, two per iteration, lane = (which of the two, class); the logits of the
+        // next pair are requested before the current pair is evaluated
+        while (have) {
+            const int al_c = al;
+            const float x_c = xc;
+            al = -1;
+            have = m != 0;
+            if (have) {
+                al = peel();
+                if (al >= 0 && c < C) xc = src[(unsigned)al * CH + 1 + c];
+            }
+            const unsigned long long sta = __shfl_sync(FULL, st, al_c & 31);
+            if (al_c >= 0 && c < C) {
+                const float pc = sigmoid_fast(x_c);
                 float l1 = 0.f, l0 = 0.f;
                 if (do_sums) { l1 = bce_fwd_pos(pc); l0 = bce_fwd_neg(pc); }
                 const float g1 = bce_bwd_logit(pc, 1.f), g0 = bce_bwd_logit(pc, 0.f);
@@ -376,13 +415,14 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
 #pragma unroll
                 for (int i = 0; i < ADY_MAX_THR; ++i) {
                     if (i >= cfg.n_thr) break;
-                    if ((sta >> (16 * i)) & 1ull) {
-                        const bool t = (sta >> (16 * i + 1 + c)) & 1ull;
+                    const unsigned f = (unsigned)(sta >> (16 * i)) & 0xffffu;   // this threshold's (class bits | obj bit)
+                    if (f & 1u) {
+                        const bool t = (f >> (1 + c)) & 1u;
                         s_cls[i] += t ? l1 : l0;
                         if (GRAD) gc += sw.w_cls[i] * (t ? g1 : g0);
                     }
                 }
-                if (GRAD) tile[(unsigned)al * CH + 1 + c] = gc;
+                if (GRAD) tile[(unsigned)al_c * CH + 1 + c] = gc;
             }
         }
 
@@ -401,45 +441,53 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
             }
             __syncwarp();
         }
+        grp = nxt;
     }
-    if (!do_sums) return;
     // warp reduce (FP64) -> block reduce through shared memory -> one atomic per block and sum:
     // per-warp atomics on a handful of addresses serialise in L2 (10^5 of them cost ~10^2 us)
     __shared__ double s_red[LA_THREADS / 32][3 * ADY_MAX_THR];
     __shared__ bool s_last;
-    double d[3 * ADY_MAX_THR];
+    if (do_sums) {
+        double d[3 * ADY_MAX_THR];
 #pragma unroll
-    for (int i = 0; i < ADY_MAX_THR; ++i) {
-        d[i] = s_pos[i];
-        d[ADY_MAX_THR + i] = i < cfg.n_thr ? (double)s_neg[i] + (double)s_neg_all : 0.0;
-        d[2 * ADY_MAX_THR + i] = s_cls[i];
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1)
-#pragma unroll
-        for (int i = 0; i < 3 * ADY_MAX_THR; ++i) d[i] += __shfl_xor_sync(FULL, d[i], o);
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 3 * ADY_MAX_THR; ++i) s_red[threadIdx.x >> 5][i] = d[i];
-    }
-    __syncthreads();
-    if (threadIdx.x < 3 * ADY_MAX_THR) {
-        double t = 0.0;
-        for (int w = 0; w < LA_THREADS / 32; ++w) t += s_red[w][threadIdx.x];
-        const int kind = threadIdx.x / ADY_MAX_THR, i = threadIdx.x % ADY_MAX_THR;
-        if (i < cfg.n_thr && t != 0.0) {
-            double* dstp = kind == 0 ? acc->s_pos : (kind == 1 ? acc->s_neg : acc->s_cls);
-            atomicAdd(&dstp[i], t);
+        for (int i = 0; i < ADY_MAX_THR; ++i) {
+            d[i] = s_pos[i];
+            d[ADY_MAX_THR + i] = i < cfg.n_thr ? (double)s_neg[i] + (double)s_neg_all : 0.0;
+            d[2 * ADY_MAX_THR + i] = s_cls[i];
         }
-        __threadfence();
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < 3 * ADY_MAX_THR; ++i) d[i] += __shfl_xor_sync(FULL, d[i], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 3 * ADY_MAX_THR; ++i) s_red[threadIdx.x >> 5][i] = d[i];
+        }
+        __syncthreads();
+        if (threadIdx.x < 3 * ADY_MAX_THR) {
+            double t = 0.0;
+            for (int w = 0; w < LA_THREADS / 32; ++w) t += s_red[w][threadIdx.x];
+            const int kind = threadIdx.x / ADY_MAX_THR, i = threadIdx.x % ADY_MAX_THR;
+            if (i < cfg.n_thr && t != 0.0) {
+                double* dstp = kind == 0 ? acc->s_pos : (kind == 1 ? acc->s_neg : acc->s_cls);
+                atomicAdd(&dstp[i], t);
+            }
+            __threadfence();
+        }
     }
+    // the last block to finish (ticket) writes the scalar loss and leaves the two scheduling counters at zero for a
+    // later backward launch over the same workspace
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         s_last = atomicAdd(&acc->done_blocks, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0 && loss_out) loss_out[0] = loss_total(n_anchor, cfg, acc);
+    if (s_last && threadIdx.x == 0) {
+        if (do_sums && loss_out) loss_out[0] = loss_total(n_anchor, cfg, acc);
+        acc->next_group = 0u;
+        acc->done_blocks = 0u;
+    }
 }
 
 template <bool GRAD>

@@ -30,7 +30,8 @@ struct LossAccum {
     unsigned long long n_pos[ADY_MAX_THR];
     double s_pos[ADY_MAX_THR], s_neg[ADY_MAX_THR], s_cls[ADY_MAX_THR];
     float w_pos[ADY_MAX_THR], w_neg[ADY_MAX_THR], w_cls[ADY_MAX_THR];   // gain / (n_thr * count), by loss_weights_kernel
-    float w_ang, pad_f[3];
+    float w_ang, pad_f;
+    unsigned int next_group, pad_u;   // loss_anchor_kernel's group counter (dynamic tail of the work split)
     int bad_rows;
     unsigned int done_blocks;    // ticket of loss_stream_kernel's last-block finalisation
 };
