@@ -313,12 +313,22 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
     const long long n_warps = ((long long)gridDim.x * LA_THREADS) >> 5;
     const long long k_static = (n_groups / n_warps) * 3 / 4;
     const long long dyn_base = k_static * n_warps;
+    // the dynamic range is cut into ADY_LOSS_NCTR contiguous parts, each with its own counter (in its own 128-byte line)
+    // and served by the blocks with blockIdx % ADY_LOSS_NCTR == part: one counter for all 4.7 k warps queued the claims
+    // behind each other in one L2 slice (20 % of the kernel's stall samples)
+    const int n_parts = min((int)gridDim.x, ADY_LOSS_NCTR);
+    const long long dyn_part = (n_groups - dyn_base + n_parts - 1) / n_parts;
+    const int my_part = blockIdx.x % n_parts;
+    const long long part_base = dyn_base + my_part * dyn_part;
     long long k_round = -1;
     auto issue_claim = [&]() -> long long {              // the value is meaningful in lane 0 (static rounds: in every lane)
         ++k_round;
         if (k_round < k_static) return warp0 + k_round * n_warps;
         long long v = 0;
-        if (lane == 0) v = dyn_base + (long long)atomicAdd(&acc->next_group, 1u);
+        if (lane == 0) {
+            const long long t = (long long)atomicAdd(&acc->group_ctr[my_part][0], 1u);
+            v = (t < dyn_part && part_base + t < n_groups) ? part_base + t : n_groups;
+        }
         return v;
     };
     unsigned long long st_n = 0ull;
@@ -485,7 +495,7 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
     __syncthreads();
     if (s_last && threadIdx.x == 0) {
         if (do_sums && loss_out) loss_out[0] = loss_total(n_anchor, cfg, acc);
-        acc->next_group = 0u;
+        for (int j = 0; j < ADY_LOSS_NCTR; ++j) acc->group_ctr[j][0] = 0u;
         acc->done_blocks = 0u;
     }
 }

@@ -7,6 +7,7 @@
 #define ADY_MAX_THR 4
 #define ADY_MAX_ANCHORS 8
 #define ADY_MAX_GRID 16
+#define ADY_LOSS_NCTR 16
 
 namespace ady {
 
@@ -31,9 +32,12 @@ struct LossAccum {
     double s_pos[ADY_MAX_THR], s_neg[ADY_MAX_THR], s_cls[ADY_MAX_THR];
     float w_pos[ADY_MAX_THR], w_neg[ADY_MAX_THR], w_cls[ADY_MAX_THR];   // gain / (n_thr * count), by loss_weights_kernel
     float w_ang, pad_f;
-    unsigned int next_group, pad_u;   // loss_anchor_kernel's group counter (dynamic tail of the work split)
+    unsigned int pad_u[2];
     int bad_rows;
-    unsigned int done_blocks;    // ticket of loss_stream_kernel's last-block finalisation
+    unsigned int done_blocks;    // ticket of loss_anchor_kernel's last-block finalisation
+    // loss_anchor_kernel's group counters (dynamic tail of the work split), one per 128-byte line: same-address atomics
+    // serialise in one L2 slice
+    unsigned int group_ctr[ADY_LOSS_NCTR][32];
 };
 
 size_t loss_workspace_bytes(int B, int T, const AssignCfg& cfg);
