@@ -102,6 +102,7 @@ _SIGS = {
     "adyolo_label_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "adyolo_label_cells": (C.c_int, [_P, C.c_int64, C.c_int, C.POINTER(GridCfg), _P, C.c_int64, _P, _P, _P, _P]),
     "adyolo_label_rows": (C.c_int, [_P, C.c_int64, C.POINTER(GridCfg), _P, C.c_int64, _P, _P, _P, C.c_int64, _P]),
+    "adyolo_label_cells_rows": (C.c_int, [_P, C.c_int64, C.c_int, C.POINTER(GridCfg), _P, C.c_int64, _P, _P, _P, _P, C.c_int64, _P]),
     "adyolo_launch_count": (C.c_longlong, []),
     "adyolo_loss_bad_rows_offset": (C.c_size_t, []),
     "adyolo_assign": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.POINTER(GridCfg), _P, _P, _P, _P]),

@@ -234,6 +234,18 @@ int adyolo_label_rows(const double* events, int64_t E, const adyolo_grid_cfg* cf
                              (cudaStream_t)stream);
 }
 
+int adyolo_label_cells_rows(const double* events, int64_t E, int nb_label_frames, const adyolo_grid_cfg* cfg,
+                            const int8_t* rot_comb, int64_t n_rot, uint32_t* cellmask, int64_t* total_rows,
+                            void* workspace, float* rows, int64_t max_rows, void* stream) {
+    CellCfg cc;
+    int rc = make_cfgs(cfg, nullptr, &cc);
+    if (rc) return rc;
+    if (!total_rows) return set_error(ADY_ERR_INVALID, "label_cells_rows: NULL total_rows");
+    if (E > 0 && (!events || !cellmask || !workspace || (max_rows > 0 && !rows))) return set_error(ADY_ERR_INVALID, "label_cells_rows: NULL pointer");
+    return launch_label_cells_rows(events, (long long)E, nb_label_frames, cc, rot_comb, (long long)n_rot, cellmask,
+                                   reinterpret_cast<long long*>(total_rows), workspace, rows, (long long)max_rows, (cudaStream_t)stream);
+}
+
 int adyolo_assign(const float* logit, const float* target, int64_t M, int B, int T,
                   const adyolo_grid_cfg* cfg, float* D, uint8_t* mask, int32_t* argmin, void* stream) {
     AssignCfg a;

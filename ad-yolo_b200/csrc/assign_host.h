@@ -64,6 +64,8 @@ struct CellCfg {
 size_t label_workspace_bytes(long long E);
 int launch_label_cells(const double* events, long long E, int nb_label_frames, const CellCfg& cfg, const int8_t* rot, long long n_rot,
                        uint32_t* cellmask, long long* total_rows_dev, void* ws, cudaStream_t stream);
+int launch_label_cells_rows(const double* events, long long E, int nb_label_frames, const CellCfg& cfg, const int8_t* rot, long long n_rot,
+                            uint32_t* cellmask, long long* total_rows_dev, void* ws, float* rows, long long max_rows, cudaStream_t stream);
 int launch_label_rows(const double* events, long long E, const CellCfg& cfg, const int8_t* rot, long long n_rot, const uint32_t* cellmask,
                       const void* ws, float* rows, long long max_rows, cudaStream_t stream);
 

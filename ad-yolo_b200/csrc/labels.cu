@@ -105,15 +105,41 @@ __global__ void label_scan_kernel(long long* __restrict__ block_tot, long long n
     if (threadIdx.x == 0) *total = carry;
 }
 
+// INLINE_SCAN: block_off holds the per-block totals as label_cells_kernel left them; every block adds up the totals of
+// the blocks before it (nblocks = E / 256 is small: ~75 values at config[1]) and the last block publishes the row count,
+// which saves the one-block scan launch between the two kernels.
+template <bool INLINE_SCAN>
 __global__ void __launch_bounds__(LB)
 label_rows_kernel(const double* __restrict__ ev, long long E, CellCfg cfg, const int8_t* __restrict__ rot, long long n_rot,
                   const uint32_t* __restrict__ cellmask, const uint32_t* __restrict__ local_off,
-                  const long long* __restrict__ block_off, float* __restrict__ rows, long long max_rows) {
+                  const long long* __restrict__ block_off, float* __restrict__ rows, long long max_rows,
+                  long long* __restrict__ total) {
+    long long base;
+    if (INLINE_SCAN) {
+        __shared__ long long s_part[LB / 32];
+        __shared__ long long s_base;
+        long long t = 0;
+        for (long long i = threadIdx.x; i < (long long)blockIdx.x; i += LB) t += block_off[i];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = t;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long b = 0;
+            for (int w = 0; w < LB / 32; ++w) b += s_part[w];
+            s_base = b;
+            if (blockIdx.x == gridDim.x - 1) *total = b + block_off[blockIdx.x];
+        }
+        __syncthreads();
+        base = s_base;
+    } else {
+        base = block_off[blockIdx.x];
+    }
     const long long e = (long long)blockIdx.x * LB + threadIdx.x;
     if (e >= E) return;
     uint32_t mask = cellmask[e];
     if (!mask) return;
-    long long o = block_off[blockIdx.x] + local_off[e];
+    long long o = base + local_off[e];
     double azi = ev[e * 5 + 3], ele = ev[e * 5 + 4];
     if (rot) {
         const long long bi = (long long)ev[e * 5];
@@ -163,7 +189,27 @@ int launch_label_rows(const double* events, long long E, const CellCfg& cfg, con
     const long long nb = (E + LB - 1) / LB;
     const uint32_t* local_off = reinterpret_cast<const uint32_t*>(ws);
     const long long* block_off = reinterpret_cast<const long long*>(reinterpret_cast<const char*>(ws) + ((E * 4 + 7) / 8) * 8);
-    label_rows_kernel<<<(int)nb, LB, 0, stream>>>(events, E, cfg, rot, n_rot, cellmask, local_off, block_off, rows, max_rows);
+    label_rows_kernel<false><<<(int)nb, LB, 0, stream>>>(events, E, cfg, rot, n_rot, cellmask, local_off, block_off, rows, max_rows, nullptr);
+    ADY_LAUNCH_CHECK("label_rows_kernel");
+    return ADY_OK;
+}
+
+// cells + rows back to back for a caller that has the row capacity up front (no host read of the count in between)
+int launch_label_cells_rows(const double* events, long long E, int nb_label_frames, const CellCfg& cfg, const int8_t* rot, long long n_rot,
+                            uint32_t* cellmask, long long* total_rows_dev, void* ws, float* rows, long long max_rows, cudaStream_t stream) {
+    const long long nb = (E + LB - 1) / LB;
+    if (E <= 0 || nb > 4096) {       // empty input, or so many blocks that the quadratic inline scan stops being free
+        int rc = launch_label_cells(events, E, nb_label_frames, cfg, rot, n_rot, cellmask, total_rows_dev, ws, stream);
+        if (rc) return rc;
+        return launch_label_rows(events, E, cfg, rot, n_rot, cellmask, ws, rows, max_rows, stream);
+    }
+    if (cfg.ga * cfg.ge > 32 || cfg.ga > ADY_MAX_GRID || cfg.ge > ADY_MAX_GRID)
+        return set_error(ADY_ERR_UNSUPPORTED, "label cells: grid %dx%d exceeds the 32-cell mask", cfg.ga, cfg.ge);
+    uint32_t* local_off = reinterpret_cast<uint32_t*>(ws);
+    long long* block_tot = reinterpret_cast<long long*>(reinterpret_cast<char*>(ws) + ((E * 4 + 7) / 8) * 8);
+    label_cells_kernel<<<(int)nb, LB, 0, stream>>>(events, E, nb_label_frames, cfg, rot, n_rot, cellmask, local_off, block_tot);
+    ADY_LAUNCH_CHECK("label_cells_kernel");
+    label_rows_kernel<true><<<(int)nb, LB, 0, stream>>>(events, E, cfg, rot, n_rot, cellmask, local_off, block_tot, rows, max_rows, total_rows_dev);
     ADY_LAUNCH_CHECK("label_rows_kernel");
     return ADY_OK;
 }

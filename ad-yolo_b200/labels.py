@@ -93,13 +93,14 @@ def label_rows_batched(events: torch.Tensor, nb_label_frames: int, grid: GridSpe
                 raise ValueError("rot_comb must be an int8 CUDA tensor")
             rot_comb = rot_comb.contiguous()
         n_rot = 0 if rot_comb is None else rot_comb.numel()
-        check(L.adyolo_label_cells(ptr(events), E, int(nb_label_frames), C.byref(grid.c), ptr(rot_comb), n_rot,
-                                   ptr(cellmask), ptr(total), ptr(ws), stream_ptr()), "adyolo_label_cells")
         if max_rows is not None:
             rows = torch.empty((int(max_rows), 7), dtype=torch.float32, device=events.device)
-            check(L.adyolo_label_rows(ptr(events), E, C.byref(grid.c), ptr(rot_comb), n_rot, ptr(cellmask), ptr(ws),
-                                      ptr(rows), int(max_rows), stream_ptr()), "adyolo_label_rows")
+            check(L.adyolo_label_cells_rows(ptr(events), E, int(nb_label_frames), C.byref(grid.c), ptr(rot_comb), n_rot,
+                                            ptr(cellmask), ptr(total), ptr(ws), ptr(rows), int(max_rows), stream_ptr()),
+                  "adyolo_label_cells_rows")
             return DeviceRows(rows, total)
+        check(L.adyolo_label_cells(ptr(events), E, int(nb_label_frames), C.byref(grid.c), ptr(rot_comb), n_rot,
+                                   ptr(cellmask), ptr(total), ptr(ws), stream_ptr()), "adyolo_label_cells")
         M = int(total.item())   # the one host sync of the label path (sizes the output)
         rows = torch.empty((M, 7), dtype=torch.float32, device=events.device)
         check(L.adyolo_label_rows(ptr(events), E, C.byref(grid.c), ptr(rot_comb), n_rot, ptr(cellmask), ptr(ws),

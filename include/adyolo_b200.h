@@ -171,6 +171,11 @@ int adyolo_label_cells(const double* events, int64_t E, int nb_label_frames, con
 int adyolo_label_rows(const double* events, int64_t E, const adyolo_grid_cfg* cfg, const int8_t* rot_comb,
                       int64_t n_rot, const uint32_t* cellmask, const void* workspace, float* rows,
                       int64_t max_rows, void* stream);
+/* adyolo_label_cells + adyolo_label_rows in one call for a caller that sizes `rows` up front (max_rows): two launches,
+ * the block offsets are derived inside the row kernel and *total_rows is written by it (same overflow contract).    */
+int adyolo_label_cells_rows(const double* events, int64_t E, int nb_label_frames, const adyolo_grid_cfg* cfg,
+                            const int8_t* rot_comb, int64_t n_rot, uint32_t* cellmask, int64_t* total_rows,
+                            void* workspace, float* rows, int64_t max_rows, void* stream);
 
 /* ADYOLOloss decode + distance_between_polar_coordinates + responsibility (loss.py:193-226):
  *   logit  device float32 (B, T, Ga*Ge*A*(C+3));  target device float32 (M, 7)
