@@ -128,18 +128,24 @@ assign_rows_kernel(const float* __restrict__ logit, const float* __restrict__ ta
             // target side of loss.py:184-186 (deg2rad, sin, cos) — computed once per row
             const float tur = __fmul_rn(g.tu, cfg.deg2rad), tvr = __fmul_rn(g.tv, cfg.deg2rad);
             const float stv = sinf(tvr), ctv = cosf(tvr);
-            // Two rolled passes keep the code small (the 5x unrolled chain with its inlined libdevice calls was
-            // 8.2 k SASS instructions and the kernel spent its time on instruction fetch): pass 1 evaluates D for
-            // every anchor, pass 2 sets the responsibility bits and re-evaluates the chain, now with its gradient,
-            // only for the anchors that enter the angular term.
+            // Rolled loops around one non-inlined copy of the chain keep the code small (the 5x unrolled chain with its
+            // inlined libdevice calls was 8.2 k SASS instructions and the kernel spent its time on instruction fetch).
+            // The logits of all anchors are requested before the first chain starts (one DRAM latency instead of A),
+            // and the chain runs once per anchor: its gradient is taken right away (cheap next to the chain itself)
+            // and kept for the anchors that turn out to enter the angular term.
             const ChainK ck{cfg.ovl_scale, cfg.gs_u, cfg.gs_v, cfg.deg2rad, cfg.rad2deg, cfg.clip_lo, cfg.clip_hi};
-            float Dv[ADY_MAX_ANCHORS];
+            float xu[ADY_MAX_ANCHORS], xv[ADY_MAX_ANCHORS];
+#pragma unroll
+            for (int a = 0; a < ADY_MAX_ANCHORS; ++a)
+                if (a < A) { xu[a] = lp[a * CH]; xv[a] = lp[a * CH + 1]; }
+            float Dv[ADY_MAX_ANCHORS], gu[ADY_MAX_ANCHORS], gv[ADY_MAX_ANCHORS];
             float dmin = 0.f;
             int amin = 0;
 #pragma unroll 1
             for (int a = 0; a < A; ++a) {
-                const AnchorEval e = eval_anchor(lp[a * CH], lp[a * CH + 1], ck, off_u, off_v, tur, stv, ctv);
+                const AnchorEval e = eval_anchor(xu[a], xv[a], ck, off_u, off_v, tur, stv, ctv);
                 Dv[a] = e.D;
+                if (ang_grad) { gu[a] = anchor_grad_u(e, ck, ctv); gv[a] = anchor_grad_v(e, ck, stv, ctv); }
                 if (a == 0 || e.D < dmin) { dmin = e.D; amin = a; }   // first minimum (torch.min)
             }
             if (argmin_out) argmin_out[m] = amin;
@@ -156,9 +162,8 @@ assign_rows_kernel(const float* __restrict__ logit, const float* __restrict__ ta
                         ang_sum += (double)Da;
                         ang_cnt += 1;
                         if (ang_grad) {
-                            const AnchorEval e = eval_anchor(lp[a * CH], lp[a * CH + 1], ck, off_u, off_v, tur, stv, ctv);
-                            atomicAdd(&ang_grad[cell * A + a].x, anchor_grad_u(e, ck, ctv));
-                            atomicAdd(&ang_grad[cell * A + a].y, anchor_grad_v(e, ck, stv, ctv));
+                            atomicAdd(&ang_grad[cell * A + a].x, gu[a]);
+                            atomicAdd(&ang_grad[cell * A + a].y, gv[a]);
                         }
                     }
                 }
