@@ -149,6 +149,7 @@ assign_rows_kernel(const float* __restrict__ logit, const float* __restrict__ ta
                 if (a == 0 || e.D < dmin) { dmin = e.D; amin = a; }   // first minimum (torch.min)
             }
             if (argmin_out) argmin_out[m] = amin;
+            unsigned long long bits_a[ADY_MAX_ANCHORS];
 #pragma unroll 1
             for (int a = 0; a < A; ++a) {
                 const float Da = Dv[a];
@@ -167,11 +168,21 @@ assign_rows_kernel(const float* __restrict__ logit, const float* __restrict__ ta
                         }
                     }
                 }
-                if (bits && state) {
-                    const unsigned long long old = atomicOr(&state[cell * A + a], bits);
-                    const unsigned long long fresh = bits & ~old;
-                    for (int i = 0; i < cfg.n_thr; ++i) newpos[i] += (int)((fresh >> (16 * i)) & 1ull);
-                }
+                bits_a[a] = bits;
+            }
+            if (state) {
+                // the label words of all anchors are updated before the first returned value is looked at: A atomics
+                // in flight instead of A round trips in a row (27 % of the kernel's stall samples)
+                unsigned long long old_a[ADY_MAX_ANCHORS];
+#pragma unroll
+                for (int a = 0; a < ADY_MAX_ANCHORS; ++a)
+                    if (a < A) old_a[a] = bits_a[a] ? atomicOr(&state[cell * A + a], bits_a[a]) : 0ull;
+#pragma unroll
+                for (int a = 0; a < ADY_MAX_ANCHORS; ++a)
+                    if (a < A) {
+                        const unsigned long long fresh = bits_a[a] & ~old_a[a];
+                        for (int i = 0; i < cfg.n_thr; ++i) newpos[i] += (int)((fresh >> (16 * i)) & 1ull);
+                    }
             }
         }
     }
