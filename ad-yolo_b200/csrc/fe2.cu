@@ -38,7 +38,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Stage the 3 hops of frames t0, t0+1 of the clip starting at sample `clip0` of `audio` (see stage_col()).
 // thread (h = tid / 80, rem = tid % 80 < 75) copies column rem of rows 12 h .. 12 h + 11.
 __device__ __forceinline__ void issue_tile_copy(unsigned char* samp, const int16_t* __restrict__ audio, long long clip0, int t0, int nf,
-                                                int tid, int dst_off /* (12 h * ROWP + stage_col(rem)) * 8 or -1 */) {
+                                                int tid, int dst_off /* (12 h * ROWP + col_perm[stage_col(rem)]) * 8 or -1 */) {
     if (dst_off < 0) return;
     const int h = tid >= 80, rem = tid - 80 * h;        // (dst_off < 0 for tid >= NT_AB)
     const int16_t* clip = audio + clip0 * 4;
@@ -80,8 +80,8 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
     // fixed roles
     const bool ab = tid < NT_AB;                                                    // warps 0..4 run stages A / B and the copies
     const int fA = tid >= 80, lA = tid - 80 * fA;                                  // stages A / B: frame, lane
-    const StageAConst ka = stage_a_const(ab && lA < 75 ? lA : 0);
-    const int copy_dst = ab && lA < 75 ? (12 * fA * ROWP + stage_col(lA)) * 8 : -1;
+    const StageAConst ka = stage_a_const(ab && lA < 75 ? lA : 0, ab && lA < 75 ? tab->col_perm[lA] : 0);
+    const int copy_dst = ab && lA < 75 ? (12 * fA * ROWP + tab->col_perm[stage_col(lA)]) * 8 : -1;
 
     int tile = blockIdx.x;
     if (tile < ntiles) {
@@ -102,7 +102,8 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
                 s_scale[i] = make_float2(is, -mu * is);
             }
         }
-        if (tid < NMEL) { s_meljobs[tid] = tab->mel_job0[tid]; s_meljobs[NMEL + tid] = tab->mel_njobs[tid]; }
+        if (tid < NMEL) s_meljobs[tid] = tab->mel_njobs[tid];
+        if (tid <= REC_MAXJOBS) reinterpret_cast<int*>(s_meljobs + NMEL)[tid] = tab->rec_off[tid] * 16;
     }
     const int rec_off = tid * 16;                                                   // this lane-job's record slot
 
@@ -167,14 +168,16 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
         // ---- epilogue: thread = (frame, mel)
         if (tid < TFR * NMEL && (tid >> 6) < nf) {
             const int f = tid >> 6, j = tid & 63;
-            const int nq = s_meljobs[NMEL + j];
-            const unsigned char* ra = s_x + (2 * f) * REC_PLANE + s_meljobs[j] * 16;
+            const int nq = s_meljobs[j];
+            const int* rec_off = reinterpret_cast<const int*>(s_meljobs + NMEL);
+            const unsigned char* ra = s_x + (2 * f) * REC_PLANE + j * 16;
             float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
             for (int i = 0; i < nq; ++i) {                  // fixed order: the result does not depend on scheduling
-                const float4 a = *reinterpret_cast<const float4*>(ra + i * 16);
+                const unsigned char* rp = ra + rec_off[i];  // chunk-major slots: the quarter-warp reads 8 consecutive records
+                const float4 a = *reinterpret_cast<const float4*>(rp);
                 pa.x += a.x; pa.y += a.y; pa.z += a.z; pa.w += a.w;
                 if (!MIC) {
-                    const float4 c = *reinterpret_cast<const float4*>(ra + REC_PLANE + i * 16);
+                    const float4 c = *reinterpret_cast<const float4*>(rp + REC_PLANE);
                     pb.x += c.x; pb.y += c.y; pb.z += c.z;
                 }
             }

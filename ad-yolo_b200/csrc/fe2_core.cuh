@@ -188,8 +188,12 @@ struct Tables {            // device-resident constants of the fe2 kernel (built
     float win[16 * 80];            // stage A: 2^-16 x periodic Hann at the sample lane l (task r = 16 l mod 75) loads as n16, [n16][l]
     float tw75[15 * 4 * 2];        // stage C: W75^{b c} as (wr, wi) for c = 0..14, b = 1..4
     MelEnt ent[MEL_L * NJOBS];     // [row][job]
-    uint8_t mel_job0[NMEL], mel_njobs[NMEL];   // lane-jobs of mel j: mel_job0[j] .. + mel_njobs[j]  (record slot = job index)
+    // lane-jobs, chunk-major: the i-th job of mel j (i < mel_njobs[j]) is lane / record slot j + rec_off[i] -- filters with
+    // more than i jobs form a suffix of the mel axis, so the 8 epilogue threads of a quarter-warp read 8 consecutive records
+    int16_t rec_off[REC_MAXJOBS + 1];
+    uint8_t mel_njobs[NMEL];
     uint8_t job_mel[NJOBS];        // (diagnostics / emulation)
+    uint8_t col_perm[80];          // staged-audio column of the samples stage-A lane l consumes (see "staging map")
 };
 
 #ifndef ADY_FE2_CTAS
@@ -203,7 +207,7 @@ struct SmemLayout {
     static constexpr int off_samples = 0;
     static constexpr int off_x = SAMP_BYTES;                              // TFR frame buffers
     static constexpr int off_tw = off_x + TFR * X_BYTES;                  // float2 [15][4]
-    static constexpr int off_meljobs = off_tw + 15 * 4 * 8;               // uint8 [2][64]
+    static constexpr int off_meljobs = off_tw + 15 * 4 * 8;               // uint8 mel_njobs[64] | int32 record byte offset of chunk i [16]
     static constexpr int off_ent = off_meljobs + 2 * NMEL;                // MelEnt [MEL_L][NJOBS]            (TABLES_IN_SMEM)
     static constexpr int off_win = off_ent + MEL_L * NJOBS * 8;           // float [16][80]
     static constexpr int off_scale = off_win + 16 * 80 * 4;               // float2 [7][64]: (istd, -mean*istd)
@@ -242,11 +246,14 @@ ADY_HD void st_f4(unsigned char* p, float a, float b, float c, float d) {
 
 // ---------------------------------------------------------------- staging map
 // Tile sample N (0 .. 1799; clip sample 600 (t0 - 1) + N, mirrored about 0 for the reflect padding of
-// librosa.stft(center=True)) lives at row N / 75, column 61 (N mod 75) mod 75 of the staged buffer: the
-// stage-A lane l (task r = 16 l mod 75, i.e. samples n == r mod 75) finds all its samples in column l, and
-// because the row pitch is 80 samples = 640 bytes == 0 mod 128 the 16 lanes of a half-warp always read 16
-// different 8-byte bank pairs, whatever row each of them is in.
-ADY_HD constexpr int stage_col(int rem) { return (61 * rem) % 75; }
+// librosa.stft(center=True)) lives at row N / 75, column col_perm[61 (N mod 75) mod 75] of the staged buffer: the
+// stage-A lane l (task r = 16 l mod 75, i.e. samples n == r mod 75) finds all its samples in one column,
+// col_perm[l].  The row pitch is 80 samples = 640 bytes == 0 mod 128, so the 8-byte bank pair of an access is its
+// column mod 16 whatever row it is in.  col_perm (fe2_tables.h) is chosen so that BOTH sides are conflict-free:
+// the 16 lanes of every half-warp of stage A read 16 different bank pairs, and so do the 16 threads of every
+// half-warp of the copy (thread rem writes the column of lane 61 rem mod 75; with col_perm = identity those
+// columns step by -14 mod 75 and a half-warp's cp.async needed 1.8 wavefronts instead of 1).
+ADY_HD constexpr int stage_col(int rem) { return (61 * rem) % 75; }   // the stage-A lane that consumes residue rem
 
 // ---------------------------------------------------------------- stage A: window + DFT-16 over n16 (75 tasks / frame)
 // PFA input map n = (75 n16 + 16 n75) mod 1200.  Lane l handles n75 = l, i.e. the samples n == r (mod 75),
@@ -256,12 +263,12 @@ ADY_HD constexpr int stage_col(int rem) { return (61 * rem) % 75; }
 // (cos, sin) pair costs two FMAs instead of one LDS but leaves a fixed ~2^-41 error pattern in the window whose
 // leakage shows up in the 'harsh' fixture: 2.4e-3 instead of 1.5e-3 on the standardised intensity channels.)
 struct StageAConst {
-    int col_off;     // byte offset of (row c_r, column l) in the staged buffer
+    int col_off;     // byte offset of (row c_r, column col_perm[l]) in the staged buffer
     int thr;         // n16 >= thr wraps to the row 16 below
 };
-ADY_HD StageAConst stage_a_const(int l) {
+ADY_HD StageAConst stage_a_const(int l, int col /* col_perm[l] */) {
     const int r = (16 * l) % 75, cr = (16 - (3 * r) % 16) % 16;
-    return {(cr * ROWP + l) * 8, 16 - cr};
+    return {(cr * ROWP + col) * 8, 16 - cr};
 }
 ADY_HD int stage_a_sample(int l, int n16) {   // frame sample index lane l loads as DFT-16 input n16 (host-side table builder)
     const int r = (16 * l) % 75, cr = (16 - (3 * r) % 16) % 16;

@@ -12,11 +12,11 @@
 using namespace ady;
 using namespace ady::fe2;
 
-static void stage_copy(unsigned char* samp, const int16_t* clip /* first sample of the clip */, int t0, int nf) {
+static void stage_copy(unsigned char* samp, const int16_t* clip /* first sample of the clip */, int t0, int nf, const uint8_t* col_perm) {
     for (int tid = 0; tid < NT_AB; ++tid) {
         const int h = tid / 80, rem = tid % 80;
         if (rem >= 75) continue;
-        const int col = stage_col(rem);
+        const int col = col_perm[stage_col(rem)];
         for (int i = 0; i < 12; ++i) {
             const int J = 12 * h + i;
             if (J >= 8 * (nf + 1)) continue;
@@ -52,10 +52,10 @@ extern "C" int emu_fe2_features_foa(const int16_t* audio, int B, long long N, co
     for (int tile = 0; tile < B * tpc; ++tile) {
         const int b = tile / tpc, t0 = (tile % tpc) * TFR, nf = std::min(TFR, T - t0);
         const unsigned rb = rot_bits_per_clip ? rot_bits_per_clip[b] : 0u;
-        stage_copy(s_samp, audio + (long long)b * N * 4, t0, nf);
+        stage_copy(s_samp, audio + (long long)b * N * 4, t0, nf, tab.col_perm);
         for (int tid = 0; tid < NT_AB; ++tid) {                   // stage A
             const int f = tid / 80, l = tid % 80;
-            if (l < 75 && f < nf) stage_a(s_samp, tab.win, s_x, f, l, stage_a_const(l));
+            if (l < 75 && f < nf) stage_a(s_samp, tab.win, s_x, f, l, stage_a_const(l, tab.col_perm[l]));
         }
         for (int tid = 0; tid < NT_AB; ++tid) {                   // stage B
             const int f = tid / 80, u = tid % 80;
@@ -88,8 +88,8 @@ extern "C" int emu_fe2_features_foa(const int16_t* audio, int B, long long N, co
             float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             for (int i = 0; i < tab.mel_njobs[j]; ++i) {
                 float r[8];
-                memcpy(r, s_x + (2 * f) * REC_PLANE + (tab.mel_job0[j] + i) * 16, 16);
-                memcpy(r + 4, s_x + (2 * f + 1) * REC_PLANE + (tab.mel_job0[j] + i) * 16, 16);
+                memcpy(r, s_x + (2 * f) * REC_PLANE + (j + tab.rec_off[i]) * 16, 16);
+                memcpy(r + 4, s_x + (2 * f + 1) * REC_PLANE + (j + tab.rec_off[i]) * 16, 16);
                 for (int c = 0; c < 8; ++c) v[c] += r[c];
             }
             // record order (|W|^2,|Z|^2,|Y|^2,|X|^2, I_Y, I_Z, I_X, -) -> channels mel W,Y,Z,X, iv Y,Z,X
@@ -141,8 +141,8 @@ extern "C" int emu_fe2_mic_phasors(const int16_t* audio, long long N, const floa
     memset(phasors, 0, sizeof(float) * (size_t)T * PH_K * 8);
     for (int tile = 0; tile < tpc; ++tile) {
         const int t0 = tile * TFR, nf = std::min(TFR, T - t0);
-        stage_copy(s_samp, audio, t0, nf);
-        for (int tid = 0; tid < NT_AB; ++tid) { const int f = tid / 80, l = tid % 80; if (l < 75 && f < nf) stage_a(s_samp, tab.win, s_x, f, l, stage_a_const(l)); }
+        stage_copy(s_samp, audio, t0, nf, tab.col_perm);
+        for (int tid = 0; tid < NT_AB; ++tid) { const int f = tid / 80, l = tid % 80; if (l < 75 && f < nf) stage_a(s_samp, tab.win, s_x, f, l, stage_a_const(l, tab.col_perm[l])); }
         for (int tid = 0; tid < NT_AB; ++tid) { const int f = tid / 80, u = tid % 80; if (f < nf) stage_b(s_x, f, u); }
         for (int f = 0; f < nf; ++f) {
             uint4* ph = reinterpret_cast<uint4*>(phasors + ((size_t)(t0 + f) * PH_K) * 8);   // 8 floats per position
