@@ -197,7 +197,7 @@ struct Tables {            // device-resident constants of the fe2 kernel (built
 };
 
 #ifndef ADY_FE2_CTAS
-#define ADY_FE2_CTAS 3
+#define ADY_FE2_CTAS 4
 #endif
 // With 4 CTAs per SM only 56 KB of shared memory are left per CTA: the mel schedule, the window and the
 // standardisation constants (20 KB, read-only) then stay in global memory and are read through L1.
