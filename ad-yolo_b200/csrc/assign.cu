@@ -456,14 +456,18 @@ loss_anchor_kernel(const float* __restrict__ logit, long long n_anchor, AssignCf
         if (GRAD) {
             float* dst = grad + a0 * CH;
             __syncwarp();
-            for (unsigned el = (unsigned)lane * 4; el < nel; el += 128) {
-                if (el + 4 <= nel) {
-                    const float4 v = *reinterpret_cast<const float4*>(tile + el);
-                    *reinterpret_cast<float4*>(tile + el) = make_float4(0.f, 0.f, 0.f, 0.f);
-                    __stcs(reinterpret_cast<float4*>(dst + el), v);
-                } else {
-                    for (unsigned q = 0; el + q < nel; ++q) { dst[el + q] = tile[el + q]; tile[el + q] = 0.f; }
+            if (na == 32) {                              // nel = 32 CH: a whole number of float4s, at most 5 per lane (CH <= 18)
+#pragma unroll
+                for (int it = 0; it < 5; ++it) {
+                    const unsigned el = (unsigned)lane * 4 + it * 128;
+                    if (el < nel) {
+                        const float4 v = *reinterpret_cast<const float4*>(tile + el);
+                        *reinterpret_cast<float4*>(tile + el) = make_float4(0.f, 0.f, 0.f, 0.f);
+                        __stcs(reinterpret_cast<float4*>(dst + el), v);
+                    }
                 }
+            } else {                                     // last, partial group
+                for (unsigned el = lane; el < nel; el += 32) { dst[el] = tile[el]; tile[el] = 0.f; }
             }
             __syncwarp();
         }
