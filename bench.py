@@ -484,7 +484,7 @@ def main_ours(args):
                          "peak": 148 * 128 * 2 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12, "unit": "TFLOP/s"},
                 "note": "bound by the shared-memory (L1 data) pipe, not HBM: three register-resident FFT stages exchange "
                         "through shared memory and the sparse mel gather reads it again (ncu: l1tex data pipe ~69 % busy, "
-                        "FMA pipe ~38 %, DRAM ~8 %); see DESIGN.md section 4.1 / profiles/r02_*"}
+                        "FMA pipe ~41 %, DRAM ~8 %); see DESIGN.md section 4.1 / profiles/r02_*"}
         roof["fp32"]["frac"] = roof["fp32"]["achieved"] / roof["fp32"]["peak"]
     side = None
     if not args.no_side_configs:
