@@ -177,6 +177,68 @@ __device__ __forceinline__ void issue_chunk_copy(unsigned char* smem, const void
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// ---- epilogue (shared by the TF32 and the FP16 kernels).  A warp may read TMEM lanes 32 (w % 4) .. +31: warps w and
+// w + 4 share a lane quarter and split the 64 lag columns.  TMEM lane = row of the M-tile = 2 * frame + (pair & 1),
+// pair = 2 * tile + (row & 1): a quarter holds 16 frames x the tile's two pairs.  Natural output layout: the 32 x 32
+// block goes through shared memory so that global stores are 128-byte row segments; any other stride set is stored
+// directly.
+__device__ __forceinline__ void gcc_epilogue(uint32_t tmem, unsigned char* smem, int warp, int lane, long long f0, long long n_frames,
+                                             int T, const float* __restrict__ mean, const float* __restrict__ istd,
+                                             float* __restrict__ out, const OutStrides& os) {
+    {
+        constexpr float kScale = 2.0f / NFFT;               // B holds cos / -sin (x 1/2 at bins 0 and 600): exact at lag 0
+        const int q = warp & 3, h = warp >> 2;
+        const bool vec = os.sj == 1 && ((os.sb | os.sc | os.st) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+        float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);      // 32 rows, 144-byte pitch: conflict-free
+        // vec: this lane's 8 (row, 16-byte column) targets, row = 4 it + lane / 8; otherwise row = lane
+        const int pp = vec ? (lane >> 3) & 1 : lane & 1;                       // pair parity of the lane's row(s)
+        long long off[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int row = vec ? 4 * it + (lane >> 3) : lane;
+            const long long fr = f0 + 16 * q + (row >> 1);
+            const long long b = fr / T;
+            off[it] = fr < n_frames ? b * os.sb + (fr - b * T) * os.st + pp * os.sc + (vec ? h * 32 + (lane & 7) * 4 : 0) : -1;
+        }
+#pragma unroll 1
+        for (int mt = 0; mt < 3; ++mt) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + mt * 64 + h * 32;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int p = mt * 2 + pp;
+            const float* mu = mean ? mean + p * NMEL + h * 32 : nullptr;
+            const float* is = istd ? istd + p * NMEL + h * 32 : nullptr;
+            if (vec) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4)
+                    *reinterpret_cast<float4*>(stage + lane * 36 + j4 * 4) =
+                        make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]), __uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3]));
+                __syncwarp();
+                const int c4 = (lane & 7) * 4;
+                const float4 m4 = mu ? *reinterpret_cast<const float4*>(mu + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 i4 = is ? *reinterpret_cast<const float4*>(is + c4) : make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    float4 v = *reinterpret_cast<const float4*>(stage + (4 * it + (lane >> 3)) * 36 + c4);
+                    v.x = (v.x * kScale - m4.x) * i4.x; v.y = (v.y * kScale - m4.y) * i4.y;
+                    v.z = (v.z * kScale - m4.z) * i4.z; v.w = (v.w * kScale - m4.w) * i4.w;
+                    if (off[it] >= 0) *reinterpret_cast<float4*>(out + off[it] + (2 * mt) * os.sc) = v;
+                }
+                __syncwarp();
+            } else if (off[0] >= 0) {
+                float* o = out + off[0] + (2 * mt) * os.sc + (long long)(h * 32) * os.sj;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    o[j * os.sj] = (__uint_as_float(r[j]) * kScale - (mu ? mu[j] : 0.f)) * (is ? is[j] : 1.f);
+            }
+        }
+    }
+}
+
 template <bool PH>
 __global__ void __launch_bounds__(GT_THREADS, 2)
 gcc_tc_kernel(const void* __restrict__ spec, long long n_frames, int T, const float* __restrict__ btab,
@@ -321,63 +383,7 @@ gcc_tc_kernel(const void* __restrict__ spec, long long n_frames, int T, const fl
     mbar_wait(smem_u32(&mbar[(GT_CHUNKS - 1) & (GT_STAGES - 1)]), (uint32_t)(((GT_CHUNKS - 1) / GT_STAGES) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;");
 
-    // ---- epilogue.  A warp may read TMEM lanes 32 (w % 4) .. +31: warps w and w + 4 share a lane
-    // quarter and split the 64 lag columns.  TMEM lane = row of the M-tile = 2 * frame + (pair & 1),
-    // pair = 2 * tile + (row & 1): a quarter holds 16 frames x the tile's two pairs.  Natural output
-    // layout: the 32 x 32 block goes through shared memory so that global stores are 128-byte row
-    // segments; any other stride set is stored directly.
-    {
-        constexpr float kScale = 2.0f / NFFT;               // B holds cos / -sin (x 1/2 at bins 0 and 600): exact at lag 0
-        const int q = warp & 3, h = warp >> 2;
-        const bool vec = os.sj == 1 && ((os.sb | os.sc | os.st) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-        float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);      // 32 rows, 144-byte pitch: conflict-free
-        // vec: this lane's 8 (row, 16-byte column) targets, row = 4 it + lane / 8; otherwise row = lane
-        const int pp = vec ? (lane >> 3) & 1 : lane & 1;                       // pair parity of the lane's row(s)
-        long long off[8];
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int row = vec ? 4 * it + (lane >> 3) : lane;
-            const long long fr = f0 + 16 * q + (row >> 1);
-            const long long b = fr / T;
-            off[it] = fr < n_frames ? b * os.sb + (fr - b * T) * os.st + pp * os.sc + (vec ? h * 32 + (lane & 7) * 4 : 0) : -1;
-        }
-#pragma unroll 1
-        for (int mt = 0; mt < 3; ++mt) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + mt * 64 + h * 32;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int p = mt * 2 + pp;
-            const float* mu = mean ? mean + p * NMEL + h * 32 : nullptr;
-            const float* is = istd ? istd + p * NMEL + h * 32 : nullptr;
-            if (vec) {
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4)
-                    *reinterpret_cast<float4*>(stage + lane * 36 + j4 * 4) =
-                        make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]), __uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3]));
-                __syncwarp();
-                const int c4 = (lane & 7) * 4;
-                const float4 m4 = mu ? *reinterpret_cast<const float4*>(mu + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 i4 = is ? *reinterpret_cast<const float4*>(is + c4) : make_float4(1.f, 1.f, 1.f, 1.f);
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    float4 v = *reinterpret_cast<const float4*>(stage + (4 * it + (lane >> 3)) * 36 + c4);
-                    v.x = (v.x * kScale - m4.x) * i4.x; v.y = (v.y * kScale - m4.y) * i4.y;
-                    v.z = (v.z * kScale - m4.z) * i4.z; v.w = (v.w * kScale - m4.w) * i4.w;
-                    if (off[it] >= 0) *reinterpret_cast<float4*>(out + off[it] + (2 * mt) * os.sc) = v;
-                }
-                __syncwarp();
-            } else if (off[0] >= 0) {
-                float* o = out + off[0] + (2 * mt) * os.sc + (long long)(h * 32) * os.sj;
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    o[j * os.sj] = (__uint_as_float(r[j]) * kScale - (mu ? mu[j] : 0.f)) * (is ? is[j] : 1.f);
-            }
-        }
-    }
+    gcc_epilogue(tmem, smem, warp, lane, f0, n_frames, T, mean, istd, out, os);
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(GT_TMEM_COLS));
@@ -448,6 +454,228 @@ static int launch_gcc(const void* in, int B, long long T, const float* mean, con
     return ADY_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// FP16 variant for the phasor input (the product path of adyolo_features_mic_gcc).  The unit phasors arrive as half2,
+// so the six cross spectra conj(u_m) u_n are formed with packed half arithmetic on TWO positions at a time
+// (HMUL2 / HFMA2: 4 instructions per microphone pair and position pair instead of 8 FP32 ones plus 4 roundings to
+// TF32) and stored as the FP16 A operand of tcgen05.mma kind::f16: half the shared-memory bytes and half the MMAs of
+// the TF32 kernel above.  Rounding: two half roundings per component (<= 5e-4 each, zero-mean) average out over the
+// 1202-term sum with its 2 / N factor: ~1e-5 on an output of magnitude <= 1 (measured against the float64 oracle in
+// tests/test_gpu_features.py, gate 1e-3).
+//
+// One chunk = 16 positions = K 32 = four 16-byte k-chunks; a lane pairs position i with position i + 8 of the chunk, so
+// k-chunk q holds [re p, re p+8, im p, im p+8] for p = 2 q and again for p = 2 q + 1 (the B table is built in that
+// order); 38 chunks.  Thread roles inside a warp (the warp owns frames 8 w .. 8 w + 7 of the CTA):
+//   copy   : piece (j, lane) = frame 8 w + 2 j + lane / 16, position lane % 16 -- a half-warp copies the 256 contiguous
+//            bytes of one frame, destinations linear in the lane (a permuted LDGSTS destination serialises into 32
+//            shared-memory wavefronts: measured, profiles/r02_gcc_ph16_*)
+//   consume: item (jj, lane) = frame 8 w + 4 jj + {0, 2, 1, 3}[lane / 8], positions i and i + 8 with i = lane % 8: two
+//            conflict-free LDS.128, six 8-byte stores; the two frames of a half-warp are 2 apart = 64 bytes in the A
+//            operand, which with the 16-byte k-chunk skew makes the 16 stores of a half-warp hit 16 distinct slots
+// The pieces a warp consumes are the ones it copied: cp.async.wait_group + __syncwarp, no block barrier for the input.
+constexpr int H_POS = 16;                               // positions per chunk
+constexpr int H_CHUNKS = fe2::PH_K / H_POS;             // 38
+constexpr int H_A_LBO = (GT_ITEMS / 8) * 128 + 16;      // 6160
+constexpr int H_A_BYTES = GT_KCH * H_A_LBO;             // 24 640
+constexpr int H_RAW_BYTES = GT_FRAMES * H_POS * 16;     // 16 384
+constexpr int H_OFF_B = GT_STAGES * H_A_BYTES;
+constexpr int H_OFF_RAW = H_OFF_B + GT_B_SLOTS * GT_B_BYTES;
+constexpr int H_SMEM = H_OFF_RAW + GT_RAW_STAGES * H_RAW_BYTES;   // 114 816 B: two CTAs per SM
+static_assert(fe2::PH_K % H_POS == 0, "whole chunks");
+// instruction descriptor: D = F32, A = B = F16, both K-major, N = 64, M = 128
+constexpr uint32_t H_IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void h_issue_chunk_copy(unsigned char* smem, const uint4* __restrict__ ph, const uint4* __restrict__ btab,
+                                                   long long f0, long long n_frames, int ch, int tid) {
+    if (ch < H_CHUNKS) {
+        const int w = tid >> 5, lane = tid & 31, pos = lane & 15;
+        const uint32_t raw = smem_u32(smem + H_OFF_RAW + (ch % GT_RAW_STAGES) * H_RAW_BYTES) + pos * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int f = 8 * w + 2 * j + (lane >> 4);
+            const long long fr = f0 + f;
+            const bool live = fr < n_frames;
+            const uint4* src = live ? ph + fr * fe2::PH_K + ch * H_POS + pos : ph;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(raw + f * 256), "l"(src), "r"(live ? 16 : 0) : "memory");
+        }
+        const uint32_t d = smem_u32(smem + H_OFF_B + (ch % GT_B_SLOTS) * GT_B_BYTES) + tid * 16;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(btab + (size_t)ch * (GT_B_BYTES / 16) + tid) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t h2_mul(uint32_t a, uint32_t b) { uint32_t r; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t h2_neg(uint32_t a) { uint32_t r; asm("neg.f16x2 %0, %1;" : "=r"(r) : "r"(a)); return r; }
+
+__global__ void __launch_bounds__(GT_THREADS, 2)
+gcc_ph16_kernel(const uint4* __restrict__ ph, long long n_frames, int T, const uint4* __restrict__ btab,
+                const float* __restrict__ mean, const float* __restrict__ istd, float* __restrict__ out, OutStrides os) {
+    extern __shared__ __align__(128) unsigned char smem[];      // A x2 | B x4 | raw x3
+    __shared__ __align__(8) unsigned long long mbar[GT_STAGES];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long f0 = (long long)blockIdx.x * GT_FRAMES;
+
+    h_issue_chunk_copy(smem, ph, btab, f0, n_frames, 0, tid);
+    h_issue_chunk_copy(smem, ph, btab, f0, n_frames, 1, tid);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(GT_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < GT_STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[s])));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = tmem_base_s;
+
+    // consume role
+    const int i = lane & 7, a = lane >> 3, fsub = ((a & 1) << 1) + (a >> 1);
+    const int raw_off = (8 * warp + fsub) * 256 + i * 16;                                     // + jj * 4 * 256; position i + 8: + 128
+    const int a_off = (i >> 1) * H_A_LBO + (i & 1) * 8 + (2 * warp) * 128 + (2 * fsub) * 16;  // + jj * 128, + (p & 1) * 16 + (p >> 1) * 2048
+
+    for (int ch = 0; ch < H_CHUNKS; ++ch) {
+        const int stg = ch & (GT_STAGES - 1);
+        unsigned char* sA = smem + stg * H_A_BYTES + a_off;
+        if (ch >= GT_STAGES) mbar_wait(smem_u32(&mbar[stg]), (uint32_t)(((ch - GT_STAGES) / GT_STAGES) & 1));
+        h_issue_chunk_copy(smem, ph, btab, f0, n_frames, ch + 2, tid);
+        asm volatile("cp.async.wait_group 2;" ::: "memory");            // this thread's pieces of chunk ch have landed ...
+        __syncwarp();                                                   // ... and so have those of the other lanes of the warp
+
+        const unsigned char* raw = smem + H_OFF_RAW + (ch % GT_RAW_STAGES) * H_RAW_BYTES + raw_off;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            const uint4 v0 = *reinterpret_cast<const uint4*>(raw + jj * 1024);          // position i     : (re, im) x 4 channels
+            const uint4 v1 = *reinterpret_cast<const uint4*>(raw + jj * 1024 + 128);    // position i + 8
+            const uint32_t c0[4] = {v0.x, v0.y, v0.z, v0.w}, c1[4] = {v1.x, v1.y, v1.z, v1.w};
+            uint32_t re[4], im[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                re[c] = __byte_perm(c0[c], c1[c], 0x5410);      // (re p, re p+8)
+                im[c] = __byte_perm(c0[c], c1[c], 0x7632);      // (im p, im p+8)
+            }
+            // a zero phasor (+0, +0; the front end writes exactly that) marks a vanishing channel: every pair it takes
+            // part in has a vanishing cross spectrum, whose phase upstream is np.angle(0) = 0 -> (1, 0)
+            const uint32_t mn = min(min(min(v0.x, v0.y), min(v0.z, v0.w)), min(min(v1.x, v1.y), min(v1.z, v1.w)));
+            uint32_t pr[6], pi[6];
+#pragma unroll
+            for (int p = 0; p < 6; ++p) {
+                constexpr int PM[6] = {0, 0, 0, 1, 1, 2}, PN[6] = {1, 2, 3, 2, 3, 3};
+                const int m = PM[p], n = PN[p];
+                pr[p] = h2_fma(re[m], re[n], h2_mul(im[m], im[n]));                 // Re conj(u_m) u_n
+                pi[p] = h2_fma(re[m], im[n], h2_neg(h2_mul(im[m], re[n])));         // Im
+            }
+            if (__any_sync(0xffffffffu, mn == 0u)) {                                // rare (digital silence): warp-uniform branch
+                uint32_t zm[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) zm[c] = (c0[c] == 0u ? 0x0000ffffu : 0u) | (c1[c] == 0u ? 0xffff0000u : 0u);
+#pragma unroll
+                for (int p = 0; p < 6; ++p) {
+                    constexpr int PM[6] = {0, 0, 0, 1, 1, 2}, PN[6] = {1, 2, 3, 2, 3, 3};
+                    const uint32_t z = zm[PM[p]] | zm[PN[p]];
+                    pr[p] = (pr[p] & ~z) | (0x3c003c00u & z);
+                    pi[p] &= ~z;
+                }
+            }
+            unsigned char* dst = sA + jj * 128;
+#pragma unroll
+            for (int p = 0; p < 6; ++p) *reinterpret_cast<uint2*>(dst + (p & 1) * 16 + (p >> 1) * 2048) = make_uint2(pr[p], pi[p]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy / cp.async writes -> async proxy (UMMA)
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const uint32_t a0 = smem_u32(smem + stg * H_A_BYTES), b0 = smem_u32(smem + H_OFF_B + (ch % GT_B_SLOTS) * GT_B_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < GT_KCH / 2; ++ks) {                   // K = 16 halves per MMA = 2 k-chunks
+                const uint64_t bd = umma_desc(b0 + ks * 2 * GT_B_LBO, GT_B_LBO, 128);
+#pragma unroll
+                for (int mt = 0; mt < 3; ++mt) {
+                    const uint64_t ad = umma_desc(a0 + ks * 2 * H_A_LBO + mt * 16 * 128, H_A_LBO, 128);
+                    const uint32_t acc = (ch | ks) ? 1u : 0u;           // first MMA overwrites the accumulator
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                        ::"r"(tmem + mt * 64), "l"(ad), "l"(bd), "r"(H_IDESC), "r"(acc) : "memory");
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar[stg])) : "memory");
+        }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    mbar_wait(smem_u32(&mbar[(H_CHUNKS - 1) & (GT_STAGES - 1)]), (uint32_t)(((H_CHUNKS - 1) / GT_STAGES) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;");
+
+    gcc_epilogue(tmem, smem, warp, lane, f0, n_frames, T, mean, istd, out, os);
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(GT_TMEM_COLS));
+}
+
+// FP16 B table: [H_CHUNKS][4 k-chunks][8 lag-groups][8 lags][8 halves], K order inside k-chunk q
+// (re p, re p+8, im p, im p+8) for p = 2 q, then the same for p = 2 q + 1 (positions of the chunk)
+static int get_gcc_btab16(const uint4** dev_tab) {
+    static std::mutex mu;
+    static uint4* cache[64] = {nullptr};
+    int dev = 0;
+    ADY_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return set_error(ADY_ERR_INVALID, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (!cache[dev]) {
+        int bin_of_pos[fe2::PH_K];
+        fe2::bins_of_phasor_pos(bin_of_pos);
+        std::vector<__half> h((size_t)H_CHUNKS * GT_B_BYTES / 2, __float2half_rn(0.f));
+        for (int ch = 0; ch < H_CHUNKS; ++ch)
+            for (int kk = 0; kk < 2 * H_POS; ++kk) {              // K index within the chunk
+                const int q = kk >> 3, e = kk & 7;
+                const int pos = ch * H_POS + 2 * q + (e >> 2) + 8 * (e & 1), comp = (e >> 1) & 1;
+                const int bin = bin_of_pos[pos];
+                if (bin < 0) continue;
+                const double ck = (bin == 0 || bin == 600) ? 0.5 : 1.0;    // x 2/N in the epilogue
+                for (int n = 0; n < 64; ++n) {
+                    const int lag = n - 32;                       // output order cc[-32:], cc[:32]
+                    const double ang = 2.0 * M_PI * (double)((bin * (long long)((lag + NFFT) % NFFT)) % NFFT) / NFFT;
+                    const double v = comp ? -ck * sin(ang) : ck * cos(ang);
+                    const size_t off = (size_t)ch * (GT_B_BYTES / 2) + ((size_t)q * 8 + (n >> 3)) * 64 + (n & 7) * 8 + e;
+                    h[off] = __double2half(v);
+                }
+            }
+        uint4* d = nullptr;
+        ADY_CUDA_CHECK(cudaMalloc(&d, h.size() * sizeof(__half)));
+        ADY_CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        cache[dev] = d;
+    }
+    *dev_tab = cache[dev];
+    return ADY_OK;
+}
+
+static int launch_gcc_ph16(const void* in, int B, long long T, const float* mean, const float* istd, float* out, OutStrides os,
+                           cudaStream_t stream) {
+    const uint4* btab = nullptr;
+    int rc = get_gcc_btab16(&btab);
+    if (rc) return rc;
+    const long long n_frames = (long long)B * T;
+    const long long blocks = (n_frames + GT_FRAMES - 1) / GT_FRAMES;
+    if (blocks > 0x7fffffffLL) return set_error(ADY_ERR_INVALID, "gcc: too many frames");
+    static std::atomic<unsigned long long> configured{0};      // per device; the call is idempotent
+    int dev = 0;
+    ADY_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!((configured.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
+        ADY_CUDA_CHECK(cudaFuncSetAttribute(gcc_ph16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
+        configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
+    gcc_ph16_kernel<<<(unsigned)blocks, GT_THREADS, H_SMEM, stream>>>(reinterpret_cast<const uint4*>(in), n_frames, (int)T, btab, mean,
+                                                                       istd, out, os);
+    ADY_LAUNCH_CHECK("gcc_ph16_kernel");
+    return ADY_OK;
+}
+
 int launch_gcc_from_stft(const float2* spec, int B, long long T, const float* mean, const float* istd, float* out,
                          OutStrides os, cudaStream_t stream) {
     return launch_gcc<false>(spec, B, T, mean, istd, out, os, stream);
@@ -456,7 +684,10 @@ int launch_gcc_from_stft(const float2* spec, int B, long long T, const float* me
 // phasors: half2 x 4 channels per (frame, fe2 position), (B, T, 608) x 16 bytes, written by launch_features_mic_fe2
 int launch_gcc_from_phasors(const void* phasors, int B, long long T, const float* mean, const float* istd, float* out,
                             OutStrides os, cudaStream_t stream) {
-    return launch_gcc<true>(phasors, B, T, mean, istd, out, os, stream);
+    // ADYOLO_GCC=tf32 selects the round-2a TF32 kernel (A/B measurements); the default is the FP16 kernel
+    static const bool tf32 = [] { const char* e = getenv("ADYOLO_GCC"); return e && !strcmp(e, "tf32"); }();
+    if (tf32) return launch_gcc<true>(phasors, B, T, mean, istd, out, os, stream);
+    return launch_gcc_ph16(phasors, B, T, mean, istd, out, os, stream);
 }
 
 }  // namespace ady
