@@ -6,7 +6,9 @@
 // (C,T,F) stacking of :158-160; == src/utils/utility.py:142-215.  The maths and the per-thread building blocks
 // are in fe2_core.cuh; this file is the CTA-level choreography.
 //
-// Per tile of 2 frames of one clip (160 or 192 threads, 3 CTAs per SM):
+// One CTA per SM runs GROUPS = 4 independent tile pipelines ("groups" of 160 threads with their own staging + frame buffers
+// and their own named barrier) next to ONE shared-memory copy of the read-only tables.  Per group and tile of 2 frames
+// of one clip:
 //   global int16 (N,4) --cp.async(8 B / sample)--> 24 rows x 75 samples, columns permuted so that stage A is
 //                                                  bank-conflict free (3 hops, shared by the 2 frames)
 //   stage A  75 tasks / frame : window + DFT-16 of both packed FFTs (f32x2)          -> X1 (16 B / point)
@@ -26,7 +28,14 @@ namespace ady {
 int build_fe2_tables_host(fe2::Tables* t);   // tables.cu
 namespace fe2 {
 
-constexpr int CTAS_PER_SM = ADY_FE2_CTAS;   // 3: tables in shared memory; 4: tables read through L1 (fe2_core.cuh::TABLES_IN_SMEM)
+constexpr int CTAS_PER_SM = ADY_FE2_CTAS;   // x GROUPS tile pipelines each (fe2_core.cuh)
+constexpr int NTB = GROUPS * NT;            // threads per CTA
+
+// barrier of one group (bar 0 = __syncthreads is the whole CTA)
+__device__ __forceinline__ void group_sync(int g) {
+    if (GROUPS == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(NT) : "memory");
+}
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -61,65 +70,78 @@ __device__ __forceinline__ void issue_tile_copy(unsigned char* samp, const int16
 //       (B, 10, T, 64) tensor and stage C writes one half2 unit phasor per channel and bin to `phasor`
 //       (B, T, 608) x 16 bytes for the GCC-PHAT lag transform (gcc_tc.cu); no intensity vectors (ROT must be false).
 template <bool ROT, bool VIEW, bool MIC>
-__global__ void __launch_bounds__(NT, CTAS_PER_SM)
+__global__ void __launch_bounds__(NTB, CTAS_PER_SM)
 fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_per_clip, int ntiles,
                const Tables* __restrict__ tab, const float* __restrict__ mean, const float* __restrict__ istd,
                float dc0, float dc1, const int8_t* __restrict__ rot, const long long* __restrict__ clip_off,
                float* __restrict__ out, uint4* __restrict__ phasor, int* __restrict__ flags, uint32_t* __restrict__ kext, int B) {
     constexpr int NCH = MIC ? 10 : 7;
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned char* s_samp = smem + SmemLayout::off_samples;
-    unsigned char* s_x = smem + SmemLayout::off_x;
+    const int g = GROUPS == 1 ? 0 : (int)threadIdx.x / NT;                          // group (warp-uniform: NT is a multiple of 32)
+    const int tid = (int)threadIdx.x - g * NT;                                      // thread within the group
+    unsigned char* s_samp = smem + SmemLayout::off_group + g * SmemLayout::group_bytes;
+    unsigned char* s_x = s_samp + SAMP_BYTES;
     MelEnt* s_ent = reinterpret_cast<MelEnt*>(smem + SmemLayout::off_ent);           // (only with TABLES_IN_SMEM)
     unsigned char* s_tw = smem + SmemLayout::off_tw;
     float* s_win = reinterpret_cast<float*>(smem + SmemLayout::off_win);
-    float2* s_scale = reinterpret_cast<float2*>(smem + SmemLayout::off_scale);
+    float2* s_scale = reinterpret_cast<float2*>(smem + SmemLayout::off_scale);       // (only with scale_in_smem)
     uint8_t* s_meljobs = smem + SmemLayout::off_meljobs;
 
-    const int tid = threadIdx.x;
     // fixed roles
     const bool ab = tid < NT_AB;                                                    // warps 0..4 run stages A / B and the copies
     const int fA = tid >= 80, lA = tid - 80 * fA;                                  // stages A / B: frame, lane
     const StageAConst ka = stage_a_const(ab && lA < 75 ? lA : 0, ab && lA < 75 ? tab->col_perm[lA] : 0);
     const int copy_dst = ab && lA < 75 ? (12 * fA * ROWP + tab->col_perm[stage_col(lA)]) * 8 : -1;
 
-    int tile = blockIdx.x;
+    const int tile_step = (int)gridDim.x * GROUPS;
+    int tile = (int)blockIdx.x * GROUPS + g;
     if (tile < ntiles) {
         const int b = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * TFR;
         issue_tile_copy(s_samp, audio, VIEW ? clip_off[b] : (long long)b * N, t0, min(TFR, T - t0), tid, copy_dst);
     }
     cp_async_commit();
-    // constant tables -> smem (once per persistent CTA)
+    // constant tables -> smem (once per persistent CTA, by all its groups)
     {
-        for (int i = tid; i < 15 * 4 * 2; i += NT) reinterpret_cast<float*>(s_tw)[i] = tab->tw75[i];
+        const int t = (int)threadIdx.x;
+        for (int i = t; i < 15 * 4 * 2; i += NTB) reinterpret_cast<float*>(s_tw)[i] = tab->tw75[i];
         if (TABLES_IN_SMEM) {
             const uint2* src = reinterpret_cast<const uint2*>(tab->ent);
             uint2* dst = reinterpret_cast<uint2*>(s_ent);
-            for (int i = tid; i < MEL_L * NJOBS; i += NT) dst[i] = src[i];
-            for (int i = tid; i < 16 * 80; i += NT) s_win[i] = tab->win[i];
-            for (int i = tid; i < 7 * NMEL; i += NT) {   // standardisation as one FMA: x * is + (-mu * is)
+            for (int i = t; i < MEL_L * NJOBS; i += NTB) dst[i] = src[i];
+            for (int i = t; i < 16 * WIN_P; i += NTB) s_win[i] = tab->win[i];
+        }
+        if (SmemLayout::scale_in_smem) {
+            for (int i = t; i < 7 * NMEL; i += NTB) {   // standardisation as one FMA: x * is + (-mu * is)
                 const float mu = mean ? mean[i] : 0.f, is = istd ? istd[i] : 1.f;
                 s_scale[i] = make_float2(is, -mu * is);
             }
         }
-        if (tid < NMEL) s_meljobs[tid] = tab->mel_njobs[tid];
-        if (tid <= REC_MAXJOBS) reinterpret_cast<int*>(s_meljobs + NMEL)[tid] = tab->rec_off[tid] * 16;
+        if (t < NMEL) s_meljobs[t] = tab->mel_njobs[t];
+        if (t <= REC_MAXJOBS) reinterpret_cast<int*>(s_meljobs + NMEL)[t] = tab->rec_off[t] * 16;
     }
+    if (GROUPS > 1) __syncthreads();                                                // tables visible to every group
     const int rec_off = tid * 16;                                                   // this lane-job's record slot
 
-    for (; tile < ntiles; tile += gridDim.x) {
+    for (; tile < ntiles; tile += tile_step) {
         const int b = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * TFR, nf = min(TFR, T - t0);
         const unsigned rb = ROT ? rot_bits_rt(rot[b]) : 0u;
         cp_async_wait_all();
-        __syncthreads();                                   // samples landed; previous tile's epilogue is done with X
+        group_sync(g);                                   // samples landed; previous tile's epilogue is done with X
 
         // ---- stage A
-        if (ab && lA < 75 && fA < nf) stage_a(s_samp, TABLES_IN_SMEM ? s_win : tab->win, s_x, fA, lA, ka);
-        __syncthreads();
+        {
+            // the 32 per-sample offsets of stage A depend on loop-invariant lane constants only; left alone, ptxas computes
+            // them once and keeps them in local memory across the tile loop (33 spill loads per task).  An opaque copy of
+            // the wrap threshold per tile keeps the two selects per sample in the loop instead.
+            StageAConst kt = ka;
+            asm volatile("" : "+r"(kt.thr), "+r"(kt.win_step));
+            if (ab && lA < 75 && fA < nf) stage_a(s_samp, TABLES_IN_SMEM ? s_win : tab->win, s_x, fA, lA, kt);
+        }
+        group_sync(g);
 
         // samples are consumed: prefetch the next tile while the rest of this one runs
         {
-            const int nt = tile + gridDim.x;
+            const int nt = tile + tile_step;
             if (nt < ntiles) {
                 const int nb = nt / tiles_per_clip, nt0 = (nt % tiles_per_clip) * TFR;
                 issue_tile_copy(s_samp, audio, VIEW ? clip_off[nb] : (long long)nb * N, nt0, min(TFR, T - nt0), tid, copy_dst);
@@ -129,7 +151,7 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
 
         // ---- stage B (in place)
         if (ab && fA < nf) stage_b(s_x, fA, lA);
-        __syncthreads();
+        group_sync(g);
 
         // ---- stage C (in place): 224 regular pair-tasks + 18 c = 0 pair-tasks over two rounds of NT threads; the
         // c = 0 tasks run in round 1 on the last warp, next to the tail of the regular tasks on the first warps
@@ -150,12 +172,12 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
                 }
             }
         }
-        __syncthreads();
+        group_sync(g);
 
         // ---- mel projection: lane-job tid, both frames
         f2 acc[TFR][4];
         if (tid < NJOBS) mel_job<!MIC>(s_x, (TABLES_IN_SMEM ? s_ent : tab->ent) + tid, acc);
-        __syncthreads();                                   // every V read is done -> records may overwrite the frame buffers
+        group_sync(g);                                   // every V read is done -> records may overwrite the frame buffers
         if (tid < NJOBS) {
 #pragma unroll
             for (int f = 0; f < TFR; ++f) {
@@ -163,7 +185,7 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
                 if (!MIC) st_f4(s_x + (2 * f + 1) * REC_PLANE + rec_off, lo2(acc[f][2]), hi2(acc[f][2]), lo2(acc[f][3]), hi2(acc[f][3]));
             }
         }
-        __syncthreads();
+        group_sync(g);
 
         // ---- epilogue: thread = (frame, mel)
         if (tid < TFR * NMEL && (tid >> 6) < nf) {
@@ -206,7 +228,7 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
 #pragma unroll
             for (int c = 0; c < (MIC ? 4 : 7); ++c) {
                 float2 k;
-                if (TABLES_IN_SMEM) k = s_scale[c * NMEL + j];
+                if (SmemLayout::scale_in_smem) k = s_scale[c * NMEL + j];
                 else {
                     const float mu = mean ? mean[c * NMEL + j] : 0.f, is = istd ? istd[c * NMEL + j] : 1.f;
                     k = make_float2(is, -mu * is);
@@ -257,7 +279,7 @@ static int launch_inst(int grid, cudaStream_t stream, const int16_t* audio, long
         ADY_CUDA_CHECK(cudaFuncSetAttribute(fe2_foa_kernel<ROT, VIEW, MIC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
-    fe2_foa_kernel<ROT, VIEW, MIC><<<grid, NT, SmemLayout::total, stream>>>(audio, N, T, tpc, ntiles, tab, mean, istd, dc0, dc1, rot,
+    fe2_foa_kernel<ROT, VIEW, MIC><<<grid, NTB, SmemLayout::total, stream>>>(audio, N, T, tpc, ntiles, tab, mean, istd, dc0, dc1, rot,
                                                                           clip_off, out, phasor, flags,
                                                                           reinterpret_cast<uint32_t*>(flags) + 16, B);
     ADY_LAUNCH_CHECK("fe2_foa_kernel");
@@ -285,7 +307,8 @@ static int launch_fe2(const int16_t* audio, int B, long long N, const float* mea
     int dev = 0, sms = 0;
     ADY_CUDA_CHECK(cudaGetDevice(&dev));
     ADY_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int grid = (int)(ntiles < (long long)CTAS_PER_SM * sms ? ntiles : (long long)CTAS_PER_SM * sms);
+    const long long want = (ntiles + GROUPS - 1) / GROUPS;                          // one tile per group to start with
+    const int grid = (int)(want < (long long)CTAS_PER_SM * sms ? want : (long long)CTAS_PER_SM * sms);
     // window scale: 2^-15 (int16 -> [-1,1)) * 1/2 (channel split), DC terms scaled by the same 1/2
     const float dc0 = dc_offset * 300.0f, dc1 = -dc_offset * 150.0f;
 #define ADY_FE2_GO(R, V, M) return launch_inst<R, V, M>(grid, stream, audio, N, (int)T, (int)tpc, (int)ntiles, tab, mean, istd, dc0, dc1, rot, clip_off, out, phasor, flags, B)

@@ -163,6 +163,7 @@ constexpr int TFR = 2;                       // frames per tile
 constexpr int NT = ADY_FE2_NT;               // threads per CTA: 160 (5 warps) or 192 (6 warps: shorter mel jobs, 18 warps / SM)
 constexpr int NT_AB = 160;                   // stages A and B and the staging copy: 80 lanes per frame
 constexpr int ROWP = 80;                     // pitch of a 75-sample row of the staged audio, in samples (8 bytes each)
+constexpr int WIN_P = 40;                    // pitch of a window-table row (38 lanes used)
 constexpr int NROWS = 8 * (TFR + 1);         // 3 hops = 24 rows
 constexpr int SAMP_BYTES = NROWS * ROWP * 8; // 15 360
 constexpr int XSLOTS = 1210;                 // 16-byte slots per frame: 1200 points + 2 x 5 (Vb of the self-mirror tasks)
@@ -185,7 +186,8 @@ struct MelEnt {            // one non-zero: byte offsets of the bin's two V reco
 };
 
 struct Tables {            // device-resident constants of the fe2 kernel (built on the host, tables.cu)
-    float win[16 * 80];            // stage A: 2^-16 x periodic Hann at the sample lane l (task r = 16 l mod 75) loads as n16, [n16][l]
+    float win[16 * WIN_P];         // stage A: 2^-16 x periodic Hann at sample r + 75 m of lane l <= 37 (r = 16 l mod 75), [m][l]; lanes
+                                   // l >= 38 read the mirror image w[n] = w[1200 - n]: entry [15 - m][75 - l]  (stage_a_const)
     float tw75[15 * 4 * 2];        // stage C: W75^{b c} as (wr, wi) for c = 0..14, b = 1..4
     MelEnt ent[MEL_L * NJOBS];     // [row][job]
     // lane-jobs, chunk-major: the i-th job of mel j (i < mel_njobs[j]) is lane / record slot j + rec_off[i] -- filters with
@@ -196,25 +198,40 @@ struct Tables {            // device-resident constants of the fe2 kernel (built
     uint8_t col_perm[80];          // staged-audio column of the samples stage-A lane l consumes (see "staging map")
 };
 
-#ifndef ADY_FE2_CTAS
-#define ADY_FE2_CTAS 4
+// Occupancy.  GROUPS independent 5-warp tile pipelines ("groups", each with its own staging + frame buffers and its own
+// named barrier) share one CTA and with it ONE copy of the read-only tables in shared memory.  Default: 1 CTA per SM with
+// 4 groups = 20 warps per SM.  The alternative spelling of the same occupancy, 4 CTAs per SM with one group each
+// (-DADY_FE2_GROUPS=1 -DADY_FE2_CTAS=4), has no room for four table copies and reads them through an L1 that the 4 x 55 KB
+// of shared memory have shrunk to a few KB, i.e. from L2 (measured: 0.446 ms against 0.41 ms).
+#ifndef ADY_FE2_GROUPS
+#define ADY_FE2_GROUPS 4
 #endif
-// With 4 CTAs per SM only 56 KB of shared memory are left per CTA: the mel schedule, the window and the
-// standardisation constants (20 KB, read-only) then stay in global memory and are read through L1.
-constexpr bool TABLES_IN_SMEM = ADY_FE2_CTAS < 4;
+#ifndef ADY_FE2_CTAS
+#define ADY_FE2_CTAS 1
+#endif
+constexpr int GROUPS = ADY_FE2_GROUPS;
+constexpr bool TABLES_IN_SMEM = GROUPS > 1 || ADY_FE2_CTAS < 4;
 
 struct SmemLayout {
-    static constexpr int off_samples = 0;
-    static constexpr int off_x = SAMP_BYTES;                              // TFR frame buffers
-    static constexpr int off_tw = off_x + TFR * X_BYTES;                  // float2 [15][4]
+    static constexpr int smem_max = 232448;                                // 227 KB opt-in limit per CTA
+    // shared by the groups of a CTA
+    static constexpr int off_tw = 0;                                      // float2 [15][4]
     static constexpr int off_meljobs = off_tw + 15 * 4 * 8;               // uint8 mel_njobs[64] | int32 record byte offset of chunk i [16]
     static constexpr int off_ent = off_meljobs + 2 * NMEL;                // MelEnt [MEL_L][NJOBS]            (TABLES_IN_SMEM)
-    static constexpr int off_win = off_ent + MEL_L * NJOBS * 8;           // float [16][80]
-    static constexpr int off_scale = off_win + 16 * 80 * 4;               // float2 [7][64]: (istd, -mean*istd)
-    static constexpr int total = TABLES_IN_SMEM ? ((off_scale + 7 * NMEL * 8 + 15) / 16) * 16 : ((off_ent + 15) / 16) * 16;
+    static constexpr int off_win = off_ent + (TABLES_IN_SMEM ? MEL_L * NJOBS * 8 : 0);       // float [16][WIN_P]
+    static constexpr int off_scale = off_win + (TABLES_IN_SMEM ? 16 * WIN_P * 4 : 0);        // float2 [7][64]: (istd, -mean*istd)
+    static constexpr int group_bytes = SAMP_BYTES + TFR * X_BYTES;        // staged audio | TFR frame buffers
+    // the standardisation constants join the tables when they fit (they do not next to 4 groups: read through L1 / L2)
+    static constexpr bool scale_in_smem = TABLES_IN_SMEM && off_scale + 7 * NMEL * 8 + GROUPS * group_bytes <= smem_max / ADY_FE2_CTAS - 1024;
+    static constexpr int off_group = ((off_scale + (scale_in_smem ? 7 * NMEL * 8 : 0) + 15) / 16) * 16;
+    static constexpr int off_samples = off_group;                         // (group 0)
+    static constexpr int off_x = off_group + SAMP_BYTES;
+    static constexpr int total = off_group + GROUPS * group_bytes;
 };
 static_assert(4 * REC_PLANE <= TFR * X_BYTES, "partial records alias the frame buffers");
-static_assert(SmemLayout::off_x % 16 == 0 && SmemLayout::off_ent % 16 == 0 && SmemLayout::off_tw % 16 == 0 && SmemLayout::off_win % 16 == 0, "alignment");
+static_assert(SmemLayout::off_group % 16 == 0 && SmemLayout::off_ent % 16 == 0 && SmemLayout::off_tw % 16 == 0 && SmemLayout::off_win % 16 == 0 &&
+              SmemLayout::group_bytes % 16 == 0, "alignment");
+static_assert(SmemLayout::total <= SmemLayout::smem_max, "shared memory");
 
 // ---------------------------------------------------------------- small memory helpers (same code on host and device)
 ADY_HD void ld_c2(const unsigned char* p, c2& v) {
@@ -259,16 +276,20 @@ ADY_HD constexpr int stage_col(int rem) { return (61 * rem) % 75; }   // the sta
 // PFA input map n = (75 n16 + 16 n75) mod 1200.  Lane l handles n75 = l, i.e. the samples n == r (mod 75),
 // r = 16 l mod 75; sample n16 of the task is n = r + 75 ((n16 + c_r) & 15) with c_r = (16 - 3 r) & 15.
 // Window: periodic Hann scaled by 2^-16 (int16 -> [-1, 1) and the 1/2 of the channel split), read from a table of
-// correctly rounded values win[n16][l].  (Evaluating 0.5 - 0.5 cos(theta_l + 2 pi n16 / 16) from a per-lane
+// correctly rounded values (half a table: the window is symmetric, see stage_a_const).  (Evaluating 0.5 - 0.5 cos(theta_l + 2 pi n16 / 16) from a per-lane
 // (cos, sin) pair costs two FMAs instead of one LDS but leaves a fixed ~2^-41 error pattern in the window whose
 // leakage shows up in the 'harsh' fixture: 2.4e-3 instead of 1.5e-3 on the standardised intensity channels.)
 struct StageAConst {
     int col_off;     // byte offset of (row c_r, column col_perm[l]) in the staged buffer
     int thr;         // n16 >= thr wraps to the row 16 below
+    int win_off;     // window table index of n16 = 0; n16 adds win_step (and wraps by 16 rows like the samples)
+    int win_step;    // + WIN_P for the lanes l <= 37, - WIN_P for the mirrored lanes
 };
 ADY_HD StageAConst stage_a_const(int l, int col /* col_perm[l] */) {
     const int r = (16 * l) % 75, cr = (16 - (3 * r) % 16) % 16;
-    return {(cr * ROWP + col) * 8, 16 - cr};
+    // sample m = (n16 + c_r) & 15 of lane l is n = r + 75 m; w[n] = w[1200 - n] = sample 15 - m of lane 75 - l
+    const bool mir = l > 37;
+    return {(cr * ROWP + col) * 8, 16 - cr, mir ? (15 - cr) * WIN_P + (75 - l) : cr * WIN_P + l, mir ? -WIN_P : WIN_P};
 }
 ADY_HD int stage_a_sample(int l, int n16) {   // frame sample index lane l loads as DFT-16 input n16 (host-side table builder)
     const int r = (16 * l) % 75, cr = (16 - (3 * r) % 16) % 16;
@@ -289,7 +310,7 @@ ADY_HD void stage_a(const unsigned char* __restrict__ samp, const float* __restr
 #else
         memcpy(&wy, sp + off, 4); memcpy(&zx, sp + off + 4, 4);
 #endif
-        const float w = win[n16 * 80 + l];
+        const float w = win[k.win_off + n16 * k.win_step - (n16 >= k.thr ? 16 * k.win_step : 0)];
 #if defined(__CUDA_ARCH__)
         // int16 -> float without the XU pipe (64 I2F.S16 per task kept it busy for 8 cycles each and made it the
         // bottleneck of this stage): flip the sign bit (offset binary u = x + 32768), plant u in the mantissa of

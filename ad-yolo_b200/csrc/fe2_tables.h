@@ -194,9 +194,9 @@ inline bool build_col_perm(uint8_t perm[80]) {
 inline void fill_tables(const float* mel, Tables& t, MelPlan& plan, bool& ok) {
     memset(&t, 0, sizeof(t));
     if (!build_col_perm(t.col_perm)) { ok = false; return; }
-    for (int n16 = 0; n16 < 16; ++n16)
-        for (int l = 0; l < 75; ++l)
-            t.win[n16 * 80 + l] = (float)((0.5 - 0.5 * cos(2.0 * M_PI * (double)stage_a_sample(l, n16) / 1200.0)) / 65536.0);
+    for (int m = 0; m < 16; ++m)                  // half a table: lanes l >= 38 read the mirror image (stage_a_const)
+        for (int l = 0; l < 38; ++l)
+            t.win[m * WIN_P + l] = (float)((0.5 - 0.5 * cos(2.0 * M_PI * (double)((16 * l) % 75 + 75 * m) / 1200.0)) / 65536.0);
     for (int c = 0; c < 15; ++c)
         for (int b = 1; b < 5; ++b) {
             const double ang = -2.0 * M_PI * (double)(b * c) / 75.0;
