@@ -31,10 +31,16 @@ namespace fe2 {
 constexpr int CTAS_PER_SM = ADY_FE2_CTAS;   // x GROUPS tile pipelines each (fe2_core.cuh)
 constexpr int NTB = GROUPS * NT;            // threads per CTA
 
-// barrier of one group (bar 0 = __syncthreads is the whole CTA)
-__device__ __forceinline__ void group_sync(int g) {
+// barrier of one group (bar 0 = __syncthreads is the whole CTA).  The barrier number is re-derived from %tid.x at every
+// use: kept live across the tile loop it is the first value ptxas spills, and with all of L1 carved out as shared memory
+// a spill reload is an L2 round trip in front of the barrier.
+__device__ __forceinline__ void group_sync() {
     if (GROUPS == 1) __syncthreads();
-    else asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(NT) : "memory");
+    else {
+        unsigned t;
+        asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+        asm volatile("bar.sync %0, %1;" ::"r"(t / NT + 1), "n"(NT) : "memory");
+    }
 }
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
@@ -126,18 +132,18 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
         const int b = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * TFR, nf = min(TFR, T - t0);
         const unsigned rb = ROT ? rot_bits_rt(rot[b]) : 0u;
         cp_async_wait_all();
-        group_sync(g);                                   // samples landed; previous tile's epilogue is done with X
+        group_sync();                                   // samples landed; previous tile's epilogue is done with X
 
         // ---- stage A
         {
             // the 32 per-sample offsets of stage A depend on loop-invariant lane constants only; left alone, ptxas computes
             // them once and keeps them in local memory across the tile loop (33 spill loads per task).  An opaque copy of
-            // the wrap threshold per tile keeps the two selects per sample in the loop instead.
+            // the row rotation per tile keeps the four integer instructions per sample in the loop instead.
             StageAConst kt = ka;
-            asm volatile("" : "+r"(kt.thr), "+r"(kt.win_step));
+            asm volatile("" : "+r"(kt.cr));
             if (ab && lA < 75 && fA < nf) stage_a(s_samp, TABLES_IN_SMEM ? s_win : tab->win, s_x, fA, lA, kt);
         }
-        group_sync(g);
+        group_sync();
 
         // samples are consumed: prefetch the next tile while the rest of this one runs
         {
@@ -151,7 +157,7 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
 
         // ---- stage B (in place)
         if (ab && fA < nf) stage_b(s_x, fA, lA);
-        group_sync(g);
+        group_sync();
 
         // ---- stage C (in place): 224 regular pair-tasks + 18 c = 0 pair-tasks over two rounds of NT threads; the
         // c = 0 tasks run in round 1 on the last warp, next to the tail of the regular tasks on the first warps
@@ -172,12 +178,12 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
                 }
             }
         }
-        group_sync(g);
+        group_sync();
 
         // ---- mel projection: lane-job tid, both frames
         f2 acc[TFR][4];
         if (tid < NJOBS) mel_job<!MIC>(s_x, (TABLES_IN_SMEM ? s_ent : tab->ent) + tid, acc);
-        group_sync(g);                                   // every V read is done -> records may overwrite the frame buffers
+        group_sync();                                   // every V read is done -> records may overwrite the frame buffers
         if (tid < NJOBS) {
 #pragma unroll
             for (int f = 0; f < TFR; ++f) {
@@ -185,7 +191,7 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
                 if (!MIC) st_f4(s_x + (2 * f + 1) * REC_PLANE + rec_off, lo2(acc[f][2]), hi2(acc[f][2]), lo2(acc[f][3]), hi2(acc[f][3]));
             }
         }
-        group_sync(g);
+        group_sync();
 
         // ---- epilogue: thread = (frame, mel)
         if (tid < TFR * NMEL && (tid >> 6) < nf) {

@@ -163,7 +163,7 @@ constexpr int TFR = 2;                       // frames per tile
 constexpr int NT = ADY_FE2_NT;               // threads per CTA: 160 (5 warps) or 192 (6 warps: shorter mel jobs, 18 warps / SM)
 constexpr int NT_AB = 160;                   // stages A and B and the staging copy: 80 lanes per frame
 constexpr int ROWP = 80;                     // pitch of a 75-sample row of the staged audio, in samples (8 bytes each)
-constexpr int WIN_P = 40;                    // pitch of a window-table row (38 lanes used)
+constexpr int WIN_P = 41;                    // pitch of a window-table row (38 lanes used)
 constexpr int NROWS = 8 * (TFR + 1);         // 3 hops = 24 rows
 constexpr int SAMP_BYTES = NROWS * ROWP * 8; // 15 360
 constexpr int XSLOTS = 1210;                 // 16-byte slots per frame: 1200 points + 2 x 5 (Vb of the self-mirror tasks)
@@ -280,16 +280,16 @@ ADY_HD constexpr int stage_col(int rem) { return (61 * rem) % 75; }   // the sta
 // (cos, sin) pair costs two FMAs instead of one LDS but leaves a fixed ~2^-41 error pattern in the window whose
 // leakage shows up in the 'harsh' fixture: 2.4e-3 instead of 1.5e-3 on the standardised intensity channels.)
 struct StageAConst {
-    int col_off;     // byte offset of (row c_r, column col_perm[l]) in the staged buffer
-    int thr;         // n16 >= thr wraps to the row 16 below
-    int win_off;     // window table index of n16 = 0; n16 adds win_step (and wraps by 16 rows like the samples)
+    int col_off;     // byte offset of column col_perm[l] in a row of the staged buffer
+    int cr;          // DFT input n16 is sample m = (n16 + cr) & 15 of the lane, staged in row m of the frame
+    int win_off;     // window table index of sample m = 0; sample m adds m * win_step
     int win_step;    // + WIN_P for the lanes l <= 37, - WIN_P for the mirrored lanes
 };
 ADY_HD StageAConst stage_a_const(int l, int col /* col_perm[l] */) {
     const int r = (16 * l) % 75, cr = (16 - (3 * r) % 16) % 16;
-    // sample m = (n16 + c_r) & 15 of lane l is n = r + 75 m; w[n] = w[1200 - n] = sample 15 - m of lane 75 - l
+    // sample m of lane l is n = r + 75 m; w[n] = w[1200 - n] = sample 15 - m of lane 75 - l
     const bool mir = l > 37;
-    return {(cr * ROWP + col) * 8, 16 - cr, mir ? (15 - cr) * WIN_P + (75 - l) : cr * WIN_P + l, mir ? -WIN_P : WIN_P};
+    return {col * 8, cr, mir ? 15 * WIN_P + (75 - l) : l, mir ? -WIN_P : WIN_P};
 }
 ADY_HD int stage_a_sample(int l, int n16) {   // frame sample index lane l loads as DFT-16 input n16 (host-side table builder)
     const int r = (16 * l) % 75, cr = (16 - (3 * r) % 16) % 16;
@@ -302,7 +302,8 @@ ADY_HD void stage_a(const unsigned char* __restrict__ samp, const float* __restr
     c2 x[16];
 #pragma unroll
     for (int n16 = 0; n16 < 16; ++n16) {
-        const int off = n16 * (ROWP * 8) - (n16 >= k.thr ? 16 * ROWP * 8 : 0);
+        const int m = (n16 + k.cr) & 15;                  // one wrapped row index serves the sample and the window address
+        const int off = m * (ROWP * 8);
         uint32_t wy, zx;
 #if defined(__CUDA_ARCH__)
         const uint2 v = *reinterpret_cast<const uint2*>(sp + off);
@@ -310,7 +311,7 @@ ADY_HD void stage_a(const unsigned char* __restrict__ samp, const float* __restr
 #else
         memcpy(&wy, sp + off, 4); memcpy(&zx, sp + off + 4, 4);
 #endif
-        const float w = win[k.win_off + n16 * k.win_step - (n16 >= k.thr ? 16 * k.win_step : 0)];
+        const float w = win[k.win_off + m * k.win_step];
 #if defined(__CUDA_ARCH__)
         // int16 -> float without the XU pipe (64 I2F.S16 per task kept it busy for 8 cycles each and made it the
         // bottleneck of this stage): flip the sign bit (offset binary u = x + 32768), plant u in the mantissa of
