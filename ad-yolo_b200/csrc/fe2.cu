@@ -70,6 +70,15 @@ __device__ __forceinline__ void issue_tile_copy(unsigned char* samp, const int16
     }
 }
 
+// tile -> (clip, first frame) without an integer division per tile and thread: magic = min(floor(2^32 / tiles_per_clip),
+// 2^32 - 1) undershoots the quotient by at most one for tile < 2^31
+__device__ __forceinline__ void tile_coords(int tile, int tiles_per_clip, unsigned magic, int& b, int& t0) {
+    int q = (int)__umulhi((unsigned)tile, magic), r = tile - q * tiles_per_clip;
+    if (r >= tiles_per_clip) { ++q; r -= tiles_per_clip; }
+    b = q;
+    t0 = r * TFR;
+}
+
 // ROT : fused rotation augmentation (utils/augmentations.py:46-111), one combination per clip.
 // VIEW: clip b starts at sample clip_off[b] of one resident buffer (on-the-fly chunking, preprocess.py:13-48).
 // MIC : microphone-array format (no counterpart in the reference): the 4 log-mel channels go into a
@@ -77,7 +86,7 @@ __device__ __forceinline__ void issue_tile_copy(unsigned char* samp, const int16
 //       (B, T, 608) x 16 bytes for the GCC-PHAT lag transform (gcc_tc.cu); no intensity vectors (ROT must be false).
 template <bool ROT, bool VIEW, bool MIC>
 __global__ void __launch_bounds__(NTB, CTAS_PER_SM)
-fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_per_clip, int ntiles,
+fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_per_clip, unsigned tile_magic, int ntiles,
                const Tables* __restrict__ tab, const float* __restrict__ mean, const float* __restrict__ istd,
                float dc0, float dc1, const int8_t* __restrict__ rot, const long long* __restrict__ clip_off,
                float* __restrict__ out, uint4* __restrict__ phasor, int* __restrict__ flags, uint32_t* __restrict__ kext, int B) {
@@ -102,7 +111,8 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
     const int tile_step = (int)gridDim.x * GROUPS;
     int tile = (int)blockIdx.x * GROUPS + g;
     if (tile < ntiles) {
-        const int b = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * TFR;
+        int b, t0;
+        tile_coords(tile, tiles_per_clip, tile_magic, b, t0);
         issue_tile_copy(s_samp, audio, VIEW ? clip_off[b] : (long long)b * N, t0, min(TFR, T - t0), tid, copy_dst);
     }
     cp_async_commit();
@@ -129,7 +139,9 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
     const int rec_off = tid * 16;                                                   // this lane-job's record slot
 
     for (; tile < ntiles; tile += tile_step) {
-        const int b = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * TFR, nf = min(TFR, T - t0);
+        int b, t0;
+        tile_coords(tile, tiles_per_clip, tile_magic, b, t0);
+        const int nf = min(TFR, T - t0);
         const unsigned rb = ROT ? rot_bits_rt(rot[b]) : 0u;
         cp_async_wait_all();
         group_sync();                                   // samples landed; previous tile's epilogue is done with X
@@ -149,7 +161,8 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
         {
             const int nt = tile + tile_step;
             if (nt < ntiles) {
-                const int nb = nt / tiles_per_clip, nt0 = (nt % tiles_per_clip) * TFR;
+                int nb, nt0;
+                tile_coords(nt, tiles_per_clip, tile_magic, nb, nt0);
                 issue_tile_copy(s_samp, audio, VIEW ? clip_off[nb] : (long long)nb * N, nt0, min(TFR, T - nt0), tid, copy_dst);
             }
             cp_async_commit();
@@ -285,7 +298,9 @@ static int launch_inst(int grid, cudaStream_t stream, const int16_t* audio, long
         ADY_CUDA_CHECK(cudaFuncSetAttribute(fe2_foa_kernel<ROT, VIEW, MIC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
-    fe2_foa_kernel<ROT, VIEW, MIC><<<grid, NTB, SmemLayout::total, stream>>>(audio, N, T, tpc, ntiles, tab, mean, istd, dc0, dc1, rot,
+    const unsigned long long m64 = 0x100000000ull / (unsigned long long)tpc;
+    const unsigned magic = m64 > 0xffffffffull ? 0xffffffffu : (unsigned)m64;
+    fe2_foa_kernel<ROT, VIEW, MIC><<<grid, NTB, SmemLayout::total, stream>>>(audio, N, T, tpc, magic, ntiles, tab, mean, istd, dc0, dc1, rot,
                                                                           clip_off, out, phasor, flags,
                                                                           reinterpret_cast<uint32_t*>(flags) + 16, B);
     ADY_LAUNCH_CHECK("fe2_foa_kernel");
