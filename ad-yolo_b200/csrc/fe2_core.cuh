@@ -189,7 +189,7 @@ struct Tables {            // device-resident constants of the fe2 kernel (built
     float win[16 * WIN_P];         // stage A: 2^-16 x periodic Hann at sample r + 75 m of lane l <= 37 (r = 16 l mod 75), [m][l]; lanes
                                    // l >= 38 read the mirror image w[n] = w[1200 - n]: entry [15 - m][75 - l]  (stage_a_const)
     float tw75[15 * 4 * 2];        // stage C: W75^{b c} as (wr, wi) for c = 0..14, b = 1..4
-    MelEnt ent[MEL_L * NJOBS];     // [row][job]
+    alignas(16) MelEnt ent[MEL_L * NJOBS];     // [row][job]  (copied / read as 8-byte words)
     // lane-jobs, chunk-major: the i-th job of mel j (i < mel_njobs[j]) is lane / record slot j + rec_off[i] -- filters with
     // more than i jobs form a suffix of the mel axis, so the 8 epilogue threads of a quarter-warp read 8 consecutive records
     int16_t rec_off[REC_MAXJOBS + 1];
@@ -282,14 +282,14 @@ ADY_HD constexpr int stage_col(int rem) { return (61 * rem) % 75; }   // the sta
 struct StageAConst {
     int col_off;     // byte offset of column col_perm[l] in a row of the staged buffer
     int cr;          // DFT input n16 is sample m = (n16 + cr) & 15 of the lane, staged in row m of the frame
-    int win_off;     // window table index of sample m = 0; sample m adds m * win_step
-    int win_step;    // + WIN_P for the lanes l <= 37, - WIN_P for the mirrored lanes
+    int win_off;     // byte offset into the window table of sample m = 0; sample m adds m * win_step
+    int win_step;    // + 4 WIN_P for the lanes l <= 37, - 4 WIN_P for the mirrored lanes
 };
 ADY_HD StageAConst stage_a_const(int l, int col /* col_perm[l] */) {
     const int r = (16 * l) % 75, cr = (16 - (3 * r) % 16) % 16;
     // sample m of lane l is n = r + 75 m; w[n] = w[1200 - n] = sample 15 - m of lane 75 - l
     const bool mir = l > 37;
-    return {col * 8, cr, mir ? 15 * WIN_P + (75 - l) : l, mir ? -WIN_P : WIN_P};
+    return {col * 8, cr, 4 * (mir ? 15 * WIN_P + (75 - l) : l), mir ? -4 * WIN_P : 4 * WIN_P};
 }
 ADY_HD int stage_a_sample(int l, int n16) {   // frame sample index lane l loads as DFT-16 input n16 (host-side table builder)
     const int r = (16 * l) % 75, cr = (16 - (3 * r) % 16) % 16;
@@ -311,7 +311,7 @@ ADY_HD void stage_a(const unsigned char* __restrict__ samp, const float* __restr
 #else
         memcpy(&wy, sp + off, 4); memcpy(&zx, sp + off + 4, 4);
 #endif
-        const float w = win[k.win_off + m * k.win_step];
+        const float w = *reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(win) + (k.win_off + m * k.win_step));
 #if defined(__CUDA_ARCH__)
         // int16 -> float without the XU pipe (64 I2F.S16 per task kept it busy for 8 cycles each and made it the
         // bottleneck of this stage): flip the sign bit (offset binary u = x + 32768), plant u in the mantissa of
