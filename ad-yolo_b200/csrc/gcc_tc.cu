@@ -192,13 +192,23 @@ __device__ __forceinline__ void gcc_epilogue(uint32_t tmem, unsigned char* smem,
         float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);      // 32 rows, 144-byte pitch: conflict-free
         // vec: this lane's 8 (row, 16-byte column) targets, row = 4 it + lane / 8; otherwise row = lane
         const int pp = vec ? (lane >> 3) & 1 : lane & 1;                       // pair parity of the lane's row(s)
+        // frame of target `it`: f0 + 16 q + lane / 16 + 2 it (vec) or f0 + 16 q + lane / 2 (all eight the same).  One
+        // division for the first target, then (clip, frame-in-clip) advance by two frames with a carry (eight 64-bit
+        // divisions per lane were 19 % of the kernel's instructions)
         long long off[8];
+        {
+            const long long fr0 = f0 + 16 * q + (vec ? lane >> 4 : lane >> 1);
+            long long b = fr0 / T;
+            long long t = fr0 - b * T;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int row = vec ? 4 * it + (lane >> 3) : lane;
-            const long long fr = f0 + 16 * q + (row >> 1);
-            const long long b = fr / T;
-            off[it] = fr < n_frames ? b * os.sb + (fr - b * T) * os.st + pp * os.sc + (vec ? h * 32 + (lane & 7) * 4 : 0) : -1;
+            for (int it = 0; it < 8; ++it) {
+                const long long fr = fr0 + (vec ? 2 * it : 0);
+                off[it] = fr < n_frames ? b * os.sb + t * os.st + pp * os.sc + (vec ? h * 32 + (lane & 7) * 4 : 0) : -1;
+                if (vec) {
+                    t += 2;
+                    while (t >= T) { t -= T; ++b; }      // T = 1 moves two clips on
+                }
+            }
         }
 #pragma unroll 1
         for (int mt = 0; mt < 3; ++mt) {
