@@ -295,6 +295,7 @@ static int get_fe2_tables(const Tables** dev_tables) {
         Tables* d = nullptr;
         ADY_CUDA_CHECK(cudaMalloc(&d, sizeof(Tables)));
         ADY_CUDA_CHECK(cudaMemcpy(d, &host, sizeof(Tables), cudaMemcpyHostToDevice));
+        ADY_CUDA_CHECK(cudaMemcpyToSymbol(c_tw75, host.tw75, sizeof(host.tw75)));     // this translation unit's copy, per device
         cache[dev] = d;
     }
     *dev_tables = cache[dev];

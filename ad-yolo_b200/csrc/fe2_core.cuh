@@ -351,6 +351,12 @@ ADY_HD void stage_b(unsigned char* __restrict__ xf, int f, int u) {
     for (int c = 0; c < 15; ++c) st_c2(p + pi15(c) * 80, x[c]);
 }
 
+#if defined(__CUDACC__)
+// Stage-C twiddles in constant memory (filled by fe2.cu::get_fe2_tables): a warp's 32 pair-tasks span two values of c,
+// so an indexed LDC replays twice -- and stays off the shared-memory pipe that bounds the kernel (8 LDS.64 per task).
+static __constant__ float2 c_tw75[15 * 4];
+#endif
+
 // ---------------------------------------------------------------- stage C: twiddle W75^{b c}, DFT-5 over b, channel split, |X|^2, intensity
 // Pair-task = row (k16, c) ("P") with its mirror row ((16 - k16) & 15, (15 - c) % 15) ("Q"): the thread owns
 // bin k and bin 1200 - k of both packed FFTs, i.e. the four channel spectra of 5 bins.
@@ -423,8 +429,9 @@ ADY_HD void stage_c_load(const unsigned char* __restrict__ xb, const unsigned ch
         for (int b = 1; b < 5; ++b) {
             float2 tp, tq;                               // (wr, wi): the packed operations broadcast the scalar
 #if defined(__CUDA_ARCH__)
-            tp = *reinterpret_cast<const float2*>(tw + (c * 4 + (b - 1)) * 8);
-            tq = *reinterpret_cast<const float2*>(tw + (cq * 4 + (b - 1)) * 8);
+            (void)tw;
+            tp = c_tw75[c * 4 + (b - 1)];
+            tq = c_tw75[cq * 4 + (b - 1)];
 #else
             memcpy(&tp, tw + (c * 4 + (b - 1)) * 8, 8);
             memcpy(&tq, tw + (cq * 4 + (b - 1)) * 8, 8);
