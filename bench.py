@@ -537,6 +537,13 @@ if __name__ == "__main__":
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side-configs", action="store_true", help="skip config[0]/[2]/[3] and the reference-default shape")
     a = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Native libraries write there too (torch's ProcessGroupNCCL prints "NCCL
+    # version ..." on the first collective), so file descriptor 1 points at stderr while the benchmark runs and the JSON
+    # line goes to the saved descriptor.
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
     if a.impl == "reference":
         main_reference(a)
     else:
