@@ -475,9 +475,11 @@ ADY_HD void stage_c_foa(unsigned char* __restrict__ xb, const unsigned char* __r
 // The GCC-PHAT cross spectrum of a microphone pair is R / |R| = conj(u_m) u_n with u_c = X_c / |X_c|, so the front end
 // hands the lag-transform kernel one unit phasor per channel and bin as half2 (16 bytes per bin instead of the 32 bytes of
 // four complex64 spectra; a vanishing channel is sent as (0, 0): every pair it takes part in has R = 0, phase 0).
-// Phasor position of (pair-task, d): regular task tau -> 5 tau + d, c = 0 task i -> 560 + 5 i + d  (605 positions, K = 608).
+// Phasor position of (pair-task, d), d-major: regular task tau -> 112 d + tau, c = 0 task i -> 560 + 9 d + i (605 positions,
+// K = 608): the lanes of a warp hold consecutive tasks, so each of the five 16-byte stores of a task covers 512 contiguous
+// bytes per warp (task-major positions put the lanes 80 bytes apart: every store touched twice the sectors).
 constexpr int PH_K = 608;
-ADY_HD int phasor_pos(bool c0, int task, int d) { return (c0 ? 5 * NREG + 5 * task : 5 * task) + d; }
+ADY_HD int phasor_pos(bool c0, int task, int d) { return c0 ? 5 * NREG + d * NC0 + task : d * NREG + task; }
 ADY_HD int raw_bin_of(int k16, int c, int d) { return (225 * k16 + 976 * (c + 15 * d)) % 1200; }
 
 #if defined(__CUDA_ARCH__)
