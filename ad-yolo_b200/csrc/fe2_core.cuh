@@ -488,10 +488,14 @@ __device__ __forceinline__ uint32_t pack_half2(float re, float im) {
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(im), "f"(re));   // upper half <- first source
     return r;
 }
-__device__ __forceinline__ float rsqrt_or_zero(float p) {
+// unit phasor (re, im) / sqrt(p) of one channel as a half2 word, p = re^2 + im^2.  A vanishing channel (p below the
+// smallest normal: rsqrt.ftz would return inf) is sent as the word 0 = (+0, +0) EXACTLY -- the lag-transform kernel
+// recognises a vanishing channel by that word, and (-0) * 0 products would otherwise leave sign bits in it.
+__device__ __forceinline__ uint32_t phasor_word(float re, float im, float p) {
     float r;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
-    return p > 0.f ? r : 0.f;
+    const uint32_t w = pack_half2(re * r, im * r);
+    return p >= 1.17549435e-38f ? w : 0u;
 }
 #endif
 
@@ -514,12 +518,11 @@ ADY_HD void stage_c_mic(unsigned char* __restrict__ xb, const unsigned char* __r
         // channel spectra at raw bin k_d; k_d > 600 holds the conjugate of bin 1200 - k_d
         const float sg = raw_bin_of(k16, c, d) > 600 ? -1.f : 1.f;
 #if defined(__CUDA_ARCH__)
-        const float r0 = rsqrt_or_zero(va[0]), r2 = rsqrt_or_zero(va[1]), r1 = rsqrt_or_zero(va[2]), r3 = rsqrt_or_zero(va[3]);
-        uint4 rec;
-        rec.x = pack_half2(lo2(s0.re) * r0, sg * lo2(s0.im) * r0);      // channel 0 (W)
-        rec.y = pack_half2(lo2(s1.re) * r1, sg * lo2(s1.im) * r1);      // channel 1 (Y)
-        rec.z = pack_half2(hi2(s0.re) * r2, sg * hi2(s0.im) * r2);      // channel 2 (Z)
-        rec.w = pack_half2(hi2(s1.re) * r3, sg * hi2(s1.im) * r3);      // channel 3 (X)
+        uint4 rec;                                                     // va = (|W|^2, |Z|^2, |Y|^2, |X|^2)
+        rec.x = phasor_word(lo2(s0.re), sg * lo2(s0.im), va[0]);        // channel 0 (W)
+        rec.y = phasor_word(lo2(s1.re), sg * lo2(s1.im), va[2]);        // channel 1 (Y)
+        rec.z = phasor_word(hi2(s0.re), sg * hi2(s0.im), va[1]);        // channel 2 (Z)
+        rec.w = phasor_word(hi2(s1.re), sg * hi2(s1.im), va[3]);        // channel 3 (X)
         ph_frame[phasor_pos(C0, task, d)] = rec;
 #else
         float* o = reinterpret_cast<float*>(ph_frame) + phasor_pos(C0, task, d) * 8;   // emulation: 8 floats per position

@@ -186,6 +186,32 @@ def test_mic_gcc_path_selfconsistent(A):
         assert (out[b, 4, 5:35].argmax(-1) == 32 + 7).all()
 
 
+def test_mic_product_path_silence_and_vanishing_channel(A):
+    """fe2<MIC> -> gcc_ph16 (FP16 lag transform) on the cases the phasor hand-off treats specially: a vanishing channel
+    spectrum is sent as the zero phasor (+0, +0) and every pair it takes part in becomes (1, 0), like upstream's
+    np.angle(0) = 0.  Digital silence: all four channels carry only the 1e-8 DC offset (bins 0, +-1; every other bin is
+    exactly zero in FP32), so every cross spectrum is (1, 0) and cc = delta at lag 0 -- exactly 1 with FP16 operands
+    (the sum of 600 ones and two halves is exact).  The float64 oracle has rounding noise instead of exact zeros in
+    those bins, so this case is a property test, not a parity test.  A clip that is silent for its first half checks
+    that the zero handling is per (frame, position) and leaves the live frames within the usual gate."""
+    from adyolo_b200.features import features_mic_batched
+    rng = np.random.default_rng(5)
+    N = 24000
+    z = np.zeros((N, 4), np.int16)
+    half = np.clip(rng.standard_normal((N, 4)) * 2000, -32768, 32767).astype(np.int16)
+    half[:, 1] = np.roll(half[:, 0], 5)
+    half[: N // 2] = 0
+    out = features_mic_batched(torch.from_numpy(np.stack([z, half])).cuda()).cpu().numpy()
+    assert out.shape == (2, 10, 40, 64) and np.isfinite(out).all()
+    assert (out[0, 4:, :, 32] == 1.0).all()                                  # cc[0] of every pair and frame
+    other = np.delete(out[0, 4:], 32, axis=-1)
+    assert np.abs(other).max() < 1e-4                                        # FP16-rounded twiddles cancel to ~1e-5
+    assert (out[1, 4:, :18, 32] == 1.0).all()                                # the silent half of the second clip
+    ref = F.features_mic_stack(half)
+    assert np.abs(out[1, 4:, 22:] - ref[4:, 22:]).max() < 1e-3               # live frames (frame 20 +- 1 straddles the edge)
+    assert (out[1, 4, 22:38].argmax(-1) == 32 + 5).all()
+
+
 def test_gcc_tensor_core_kernel_against_oracle(A):
     """adyolo_gcc_from_stft (tcgen05 TF32 lag transform) straight through the C ABI on synthetic
     spectra: random phases, a dead microphone, digital silence, magnitudes far outside the range
