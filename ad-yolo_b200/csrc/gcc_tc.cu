@@ -484,6 +484,7 @@ static int launch_gcc(const void* in, int B, long long T, const float* mean, con
 //            operand, which with the 16-byte k-chunk skew makes the 16 stores of a half-warp hit 16 distinct slots
 // The pieces a warp consumes are the ones it copied: cp.async.wait_group + __syncwarp, no block barrier for the input.
 constexpr int H_POS = 16;                               // positions per chunk
+constexpr int H_THREADS = GT_THREADS + 32;              // 8 producer warps + the MMA warp
 constexpr int H_CHUNKS = fe2::PH_K / H_POS;             // 38
 constexpr int H_A_LBO = (GT_ITEMS / 8) * 128 + 16;      // 6160
 constexpr int H_A_BYTES = GT_KCH * H_A_LBO;             // 24 640
@@ -518,18 +519,21 @@ __device__ __forceinline__ uint32_t h2_mul(uint32_t a, uint32_t b) { uint32_t r;
 __device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 __device__ __forceinline__ uint32_t h2_neg(uint32_t a) { uint32_t r; asm("neg.f16x2 %0, %1;" : "=r"(r) : "r"(a)); return r; }
 
-__global__ void __launch_bounds__(GT_THREADS, 2)
+__global__ void __launch_bounds__(H_THREADS, 2)
 gcc_ph16_kernel(const uint4* __restrict__ ph, long long n_frames, int T, const uint4* __restrict__ btab,
                 const float* __restrict__ mean, const float* __restrict__ istd, float* __restrict__ out, OutStrides os) {
     extern __shared__ __align__(128) unsigned char smem[];      // A x2 | B x4 | raw x3
-    __shared__ __align__(8) unsigned long long mbar[GT_STAGES];
+    __shared__ __align__(8) unsigned long long mbar[GT_STAGES];        // "empty": the MMAs that read A stage s (and its B slot) are done
+    __shared__ __align__(8) unsigned long long mfull[GT_STAGES];       // "full" : the 8 producer warps have written their rows of A stage s
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long f0 = (long long)blockIdx.x * GT_FRAMES;
 
-    h_issue_chunk_copy(smem, ph, btab, f0, n_frames, 0, tid);
-    h_issue_chunk_copy(smem, ph, btab, f0, n_frames, 1, tid);
+    if (tid < GT_THREADS) {                                            // producer warps only (the MMA warp copies nothing)
+        h_issue_chunk_copy(smem, ph, btab, f0, n_frames, 0, tid);
+        h_issue_chunk_copy(smem, ph, btab, f0, n_frames, 1, tid);
+    }
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(GT_TMEM_COLS));
@@ -537,7 +541,10 @@ gcc_ph16_kernel(const uint4* __restrict__ ph, long long n_frames, int T, const u
     }
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < GT_STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[s])));
+        for (int s = 0; s < GT_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mfull[s])), "n"(GT_THREADS / 32));
+        }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -550,6 +557,34 @@ gcc_ph16_kernel(const uint4* __restrict__ ph, long long n_frames, int T, const u
     const int raw_off = (8 * warp + fsub) * 256 + i * 16;                                     // + jj * 4 * 256; position i + 8: + 128
     const int a_off = (i >> 1) * H_A_LBO + (i & 1) * 8 + (2 * warp) * 128 + (2 * fsub) * 16;  // + jj * 128, + (p & 1) * 16 + (p >> 1) * 2048
 
+    if (warp == GT_THREADS / 32) {
+        // ---- MMA warp: waits for a stage to be full, issues the chunk's six MMAs and commits them to the stage's "empty"
+        // barrier.  The 8 producer warps never wait for each other or for the issue (a __syncthreads per chunk with
+        // thread 0 issuing made every warp wait for warp 0 in every chunk: 16 % of the stall samples).
+        for (int ch = 0; ch < H_CHUNKS; ++ch) {
+            const int stg = ch & (GT_STAGES - 1);
+            mbar_wait(smem_u32(&mfull[stg]), (uint32_t)((ch / GT_STAGES) & 1));
+            if (lane == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t a0 = smem_u32(smem + stg * H_A_BYTES), b0 = smem_u32(smem + H_OFF_B + (ch % GT_B_SLOTS) * GT_B_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < GT_KCH / 2; ++ks) {                   // K = 16 halves per MMA = 2 k-chunks
+                    const uint64_t bd = umma_desc(b0 + ks * 2 * GT_B_LBO, GT_B_LBO, 128);
+#pragma unroll
+                    for (int mt = 0; mt < 3; ++mt) {
+                        const uint64_t ad = umma_desc(a0 + ks * 2 * H_A_LBO + mt * 16 * 128, H_A_LBO, 128);
+                        const uint32_t acc = (ch | ks) ? 1u : 0u;           // first MMA overwrites the accumulator
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                            ::"r"(tmem + mt * 64), "l"(ad), "l"(bd), "r"(H_IDESC), "r"(acc) : "memory");
+                    }
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar[stg])) : "memory");
+            }
+            __syncwarp();
+        }
+    } else {
     for (int ch = 0; ch < H_CHUNKS; ++ch) {
         const int stg = ch & (GT_STAGES - 1);
         unsigned char* sA = smem + stg * H_A_BYTES + a_off;
@@ -598,31 +633,15 @@ gcc_ph16_kernel(const uint4* __restrict__ ph, long long n_frames, int T, const u
             for (int p = 0; p < 6; ++p) *reinterpret_cast<uint2*>(dst + (p & 1) * 16 + (p >> 1) * 2048) = make_uint2(pr[p], pi[p]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy / cp.async writes -> async proxy (UMMA)
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t a0 = smem_u32(smem + stg * H_A_BYTES), b0 = smem_u32(smem + H_OFF_B + (ch % GT_B_SLOTS) * GT_B_BYTES);
-#pragma unroll
-            for (int ks = 0; ks < GT_KCH / 2; ++ks) {                   // K = 16 halves per MMA = 2 k-chunks
-                const uint64_t bd = umma_desc(b0 + ks * 2 * GT_B_LBO, GT_B_LBO, 128);
-#pragma unroll
-                for (int mt = 0; mt < 3; ++mt) {
-                    const uint64_t ad = umma_desc(a0 + ks * 2 * H_A_LBO + mt * 16 * 128, H_A_LBO, 128);
-                    const uint32_t acc = (ch | ks) ? 1u : 0u;           // first MMA overwrites the accumulator
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                        ::"r"(tmem + mt * 64), "l"(ad), "l"(bd), "r"(H_IDESC), "r"(acc) : "memory");
-                }
-            }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar[stg])) : "memory");
-        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&mfull[stg])) : "memory");
+    }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     mbar_wait(smem_u32(&mbar[(H_CHUNKS - 1) & (GT_STAGES - 1)]), (uint32_t)(((H_CHUNKS - 1) / GT_STAGES) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;");
 
-    gcc_epilogue(tmem, smem, warp, lane, f0, n_frames, T, mean, istd, out, os);
+    if (warp < GT_THREADS / 32) gcc_epilogue(tmem, smem, warp, lane, f0, n_frames, T, mean, istd, out, os);
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(GT_TMEM_COLS));
@@ -680,7 +699,7 @@ static int launch_gcc_ph16(const void* in, int B, long long T, const float* mean
         ADY_CUDA_CHECK(cudaFuncSetAttribute(gcc_ph16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
         configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
-    gcc_ph16_kernel<<<(unsigned)blocks, GT_THREADS, H_SMEM, stream>>>(reinterpret_cast<const uint4*>(in), n_frames, (int)T, btab, mean,
+    gcc_ph16_kernel<<<(unsigned)blocks, H_THREADS, H_SMEM, stream>>>(reinterpret_cast<const uint4*>(in), n_frames, (int)T, btab, mean,
                                                                        istd, out, os);
     ADY_LAUNCH_CHECK("gcc_ph16_kernel");
     return ADY_OK;
