@@ -594,7 +594,18 @@ ADY_HD void mel_job(const unsigned char* __restrict__ x0, const MelEnt* __restri
         for (int i = 0; i < 4; ++i) acc[f][i] = ADY_K2(0.0);
     MelEnt e[MEL_L];
 #pragma unroll
-    for (int it = 0; it < MEL_L; ++it) e[it] = ent_col[it * NJOBS];
+    for (int it = 0; it < MEL_L; ++it) {
+#if defined(__CUDA_ARCH__)
+        // one 8-byte load per entry in every instantiation: without the intensity records (MIC) the compiler would
+        // otherwise fetch offa and w with two narrow loads of two wavefronts each
+        const uint2 raw = *reinterpret_cast<const uint2*>(&ent_col[it * NJOBS]);
+        e[it].offa = (uint16_t)(raw.x & 0xffffu);
+        e[it].offb = (uint16_t)(raw.x >> 16);
+        e[it].w = __uint_as_float(raw.y);
+#else
+        e[it] = ent_col[it * NJOBS];
+#endif
+    }
 #pragma unroll
     for (int it = 0; it < MEL_L; ++it) {
         const f2 w = dup2(e[it].w);
