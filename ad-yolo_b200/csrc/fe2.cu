@@ -113,7 +113,7 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
     unsigned char* s_samp = smem + SmemLayout::off_group + g * SmemLayout::group_bytes;
     unsigned char* s_x = s_samp + SAMP_BYTES;
     MelEnt* s_ent = reinterpret_cast<MelEnt*>(smem + SmemLayout::off_ent);           // (only with TABLES_IN_SMEM)
-    unsigned char* s_tw = smem + SmemLayout::off_tw;
+    const unsigned char* s_tw = nullptr;                                             // stage-C twiddles: constant memory on the device (c_tw75)
     float* s_win = reinterpret_cast<float*>(smem + SmemLayout::off_win);
     float2* s_scale = reinterpret_cast<float2*>(smem + SmemLayout::off_scale);       // (only with scale_in_smem)
     uint8_t* s_meljobs = smem + SmemLayout::off_meljobs;
@@ -135,7 +135,6 @@ fe2_foa_kernel(const int16_t* __restrict__ audio, long long N, int T, int tiles_
     // constant tables -> smem (once per persistent CTA, by all its groups)
     {
         const int t = (int)threadIdx.x;
-        for (int i = t; i < 15 * 4 * 2; i += NTB) reinterpret_cast<float*>(s_tw)[i] = tab->tw75[i];
         if (TABLES_IN_SMEM) {
             const uint2* src = reinterpret_cast<const uint2*>(tab->ent);
             uint2* dst = reinterpret_cast<uint2*>(s_ent);

@@ -163,7 +163,8 @@ constexpr int TFR = 2;                       // frames per tile
 constexpr int NT = ADY_FE2_NT;               // threads per CTA: 160 (5 warps) or 192 (6 warps: shorter mel jobs, 18 warps / SM)
 constexpr int NT_AB = 160;                   // stages A and B and the staging copy: 80 lanes per frame
 constexpr int ROWP = 80;                     // pitch of a 75-sample row of the staged audio, in samples (8 bytes each)
-constexpr int WIN_P = 41;                    // pitch of a window-table row (38 lanes used)
+constexpr int WIN_P = 64;                    // pitch of a window-table row: a multiple of 32, so the bank of an entry is its column
+constexpr int WIN_DIRECT = 44;               // lanes 0..43 own a column; lanes 44..74 read the mirror image (columns 31..1)
 constexpr int NROWS = 8 * (TFR + 1);         // 3 hops = 24 rows
 constexpr int SAMP_BYTES = NROWS * ROWP * 8; // 15 360
 constexpr int XSLOTS = 1210;                 // 16-byte slots per frame: 1200 points + 2 x 5 (Vb of the self-mirror tasks)
@@ -186,8 +187,8 @@ struct MelEnt {            // one non-zero: byte offsets of the bin's two V reco
 };
 
 struct Tables {            // device-resident constants of the fe2 kernel (built on the host, tables.cu)
-    float win[16 * WIN_P];         // stage A: 2^-16 x periodic Hann at sample r + 75 m of lane l <= 37 (r = 16 l mod 75), [m][l]; lanes
-                                   // l >= 38 read the mirror image w[n] = w[1200 - n]: entry [15 - m][75 - l]  (stage_a_const)
+    float win[16 * WIN_P];         // stage A: 2^-16 x periodic Hann at sample r + 75 m of lane l < 44 (r = 16 l mod 75), [m][l]; lanes
+                                   // l >= 44 read the mirror image w[n] = w[1200 - n]: entry [15 - m][75 - l]  (stage_a_const)
     float tw75[15 * 4 * 2];        // stage C: W75^{b c} as (wr, wi) for c = 0..14, b = 1..4
     alignas(16) MelEnt ent[MEL_L * NJOBS];     // [row][job]  (copied / read as 8-byte words)
     // lane-jobs, chunk-major: the i-th job of mel j (i < mel_njobs[j]) is lane / record slot j + rec_off[i] -- filters with
@@ -215,8 +216,7 @@ constexpr bool TABLES_IN_SMEM = GROUPS > 1 || ADY_FE2_CTAS < 4;
 struct SmemLayout {
     static constexpr int smem_max = 232448;                                // 227 KB opt-in limit per CTA
     // shared by the groups of a CTA
-    static constexpr int off_tw = 0;                                      // float2 [15][4]
-    static constexpr int off_meljobs = off_tw + 15 * 4 * 8;               // uint8 mel_njobs[64] | int32 record byte offset of chunk i [16]
+    static constexpr int off_meljobs = 0;                                 // uint8 mel_njobs[64] | int32 record byte offset of chunk i [16]
     static constexpr int off_ent = off_meljobs + 2 * NMEL;                // MelEnt [MEL_L][NJOBS]            (TABLES_IN_SMEM)
     static constexpr int off_win = off_ent + (TABLES_IN_SMEM ? MEL_L * NJOBS * 8 : 0);       // float [16][WIN_P]
     static constexpr int off_scale = off_win + (TABLES_IN_SMEM ? 16 * WIN_P * 4 : 0);        // float2 [7][64]: (istd, -mean*istd)
@@ -229,7 +229,7 @@ struct SmemLayout {
     static constexpr int total = off_group + GROUPS * group_bytes;
 };
 static_assert(4 * REC_PLANE <= TFR * X_BYTES, "partial records alias the frame buffers");
-static_assert(SmemLayout::off_group % 16 == 0 && SmemLayout::off_ent % 16 == 0 && SmemLayout::off_tw % 16 == 0 && SmemLayout::off_win % 16 == 0 &&
+static_assert(SmemLayout::off_group % 16 == 0 && SmemLayout::off_ent % 16 == 0 && SmemLayout::off_win % 16 == 0 &&
               SmemLayout::group_bytes % 16 == 0, "alignment");
 static_assert(SmemLayout::total <= SmemLayout::smem_max, "shared memory");
 
@@ -283,12 +283,14 @@ struct StageAConst {
     int col_off;     // byte offset of column col_perm[l] in a row of the staged buffer
     int cr;          // DFT input n16 is sample m = (n16 + cr) & 15 of the lane, staged in row m of the frame
     int win_off;     // byte offset into the window table of sample m = 0; sample m adds m * win_step
-    int win_step;    // + 4 WIN_P for the lanes l <= 37, - 4 WIN_P for the mirrored lanes
+    int win_step;    // + 4 WIN_P for the lanes that own a column, - 4 WIN_P for the mirrored lanes
 };
 ADY_HD StageAConst stage_a_const(int l, int col /* col_perm[l] */) {
     const int r = (16 * l) % 75, cr = (16 - (3 * r) % 16) % 16;
     // sample m of lane l is n = r + 75 m; w[n] = w[1200 - n] = sample 15 - m of lane 75 - l
-    const bool mir = l > 37;
+    // The split at 44 (not at 38) makes the columns of every warp distinct modulo 32 -- warp 1 reads columns 32..43 and
+    // 31..12 --, so the window loads are conflict-free although every lane reads its own row.
+    const bool mir = l >= WIN_DIRECT;
     return {col * 8, cr, 4 * (mir ? 15 * WIN_P + (75 - l) : l), mir ? -4 * WIN_P : 4 * WIN_P};
 }
 ADY_HD int stage_a_sample(int l, int n16) {   // frame sample index lane l loads as DFT-16 input n16 (host-side table builder)

@@ -194,8 +194,8 @@ inline bool build_col_perm(uint8_t perm[80]) {
 inline void fill_tables(const float* mel, Tables& t, MelPlan& plan, bool& ok) {
     memset(&t, 0, sizeof(t));
     if (!build_col_perm(t.col_perm)) { ok = false; return; }
-    for (int m = 0; m < 16; ++m)                  // half a table: lanes l >= 38 read the mirror image (stage_a_const)
-        for (int l = 0; l < 38; ++l)
+    for (int m = 0; m < 16; ++m)                  // 44 of 75 columns: the other lanes read the mirror image (stage_a_const)
+        for (int l = 0; l < WIN_DIRECT; ++l)
             t.win[m * WIN_P + l] = (float)((0.5 - 0.5 * cos(2.0 * M_PI * (double)((16 * l) % 75 + 75 * m) / 1200.0)) / 65536.0);
     for (int c = 0; c < 15; ++c)
         for (int b = 1; b < 5; ++b) {
