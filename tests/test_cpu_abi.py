@@ -216,3 +216,26 @@ def test_emulated_fe2_mic_phasors_give_the_oracle_gcc(built):
     ref = F.gcc_phat(F.audio2stft(audio, T, 1200, 600, 1200, "han"), 1200, 64)
     assert np.abs(got - ref).max() < 1e-4
     assert np.argmax(ref[2, :, 0]) == 32 + 3
+
+
+def test_tile_coordinate_magic_multiply():
+    """fe2.cu::tile_coords replaces `tile / tiles_per_clip` by __umulhi(tile, magic) + one correction, magic =
+    min(floor(2^32 / tpc), 2^32 - 1) (host side of launch_inst).  The estimate may undershoot the quotient by at most one
+    for every tile < 2^31: checked here on the arithmetic itself (edges of every quotient step for a spread of divisors)."""
+    rng = np.random.default_rng(0)
+    tpcs = [1, 2, 3, 5, 100, 125, 400, 1200, 65535, 65536, 65537, 720000, 2**20 + 1, 2**30, 2**31 - 1]
+    tpcs += [int(x) for x in rng.integers(1, 2**31 - 1, size=40)]
+    for tpc in tpcs:
+        magic = min((1 << 32) // tpc, (1 << 32) - 1)
+        tiles = {0, 1, tpc - 1, tpc, tpc + 1, 2**31 - 1, 2**31 - 2}
+        for k in [int(x) for x in rng.integers(0, max((2**31 - 1) // tpc, 1), size=30)]:
+            tiles.update((k * tpc - 1, k * tpc, k * tpc + tpc - 1))
+        for tile in tiles:
+            if not 0 <= tile < 2**31:
+                continue
+            q = (tile * magic) >> 32
+            r = tile - q * tpc
+            assert 0 <= r < 2 * tpc, (tpc, tile)
+            if r >= tpc:
+                q, r = q + 1, r - tpc
+            assert (q, r) == divmod(tile, tpc), (tpc, tile)
