@@ -98,8 +98,44 @@ __device__ __forceinline__ float anchor_grad_v(const AnchorEval& e, const ChainK
     return anchor_dD_ddist(e, cfg) * ddist_dov * (cfg.deg2rad * cfg.ovl_scale) * cfg.gs_v * vpass * (1.f - e.thv * e.thv);
 }
 
+// Block reduction of the few counters of the assignment kernels: warp shuffles, shared memory across the warps, then ONE
+// set of atomics per block (all blocks add to the same seven addresses; one set per warp queued 12 k - 80 k same-address
+// atomics in L2).
+__device__ __forceinline__ void flush_counters(double ang_sum, int ang_cnt, int (&newpos)[ADY_MAX_THR], int bad, int n_thr,
+                                               LossAccum* __restrict__ acc) {
+    __shared__ double s_sum[32];
+    __shared__ int s_cnt[32][2 + ADY_MAX_THR];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        ang_sum += __shfl_xor_sync(0xffffffffu, ang_sum, o);
+        ang_cnt += __shfl_xor_sync(0xffffffffu, ang_cnt, o);
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+#pragma unroll
+        for (int i = 0; i < ADY_MAX_THR; ++i) newpos[i] += __shfl_xor_sync(0xffffffffu, newpos[i], o);
+    }
+    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        s_sum[w] = ang_sum; s_cnt[w][0] = ang_cnt; s_cnt[w][1] = bad;
+#pragma unroll
+        for (int i = 0; i < ADY_MAX_THR; ++i) s_cnt[w][2 + i] = newpos[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < nw; ++k) {
+            ang_sum += s_sum[k]; ang_cnt += s_cnt[k][0]; bad += s_cnt[k][1];
+#pragma unroll
+            for (int i = 0; i < ADY_MAX_THR; ++i) newpos[i] += s_cnt[k][2 + i];
+        }
+        if (ang_cnt) { atomicAdd(&acc->ang_sum, ang_sum); atomicAdd(&acc->ang_cnt, (unsigned long long)ang_cnt); }
+        if (bad) atomicAdd(&acc->bad_rows, bad);
+        for (int i = 0; i < n_thr; ++i)
+            if (newpos[i]) atomicAdd(&acc->n_pos[i], (unsigned long long)newpos[i]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int AR_THREADS = 256;
+__global__ void __launch_bounds__(AR_THREADS)
 assign_rows_kernel(const float* __restrict__ logit, const float* __restrict__ target, long long M_host,
                    const long long* __restrict__ M_dev, int B, int T,
                    AssignCfg cfg, float* __restrict__ D_out, uint8_t* __restrict__ mask_out,
@@ -187,21 +223,18 @@ assign_rows_kernel(const float* __restrict__ logit, const float* __restrict__ ta
         }
     }
     if (!acc) return;
-    // block reduction of the few counters (warp shuffle, then one atomic per warp)
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        ang_sum += __shfl_xor_sync(0xffffffffu, ang_sum, o);
-        ang_cnt += __shfl_xor_sync(0xffffffffu, ang_cnt, o);
-        bad += __shfl_xor_sync(0xffffffffu, bad, o);
-#pragma unroll
-        for (int i = 0; i < ADY_MAX_THR; ++i) newpos[i] += __shfl_xor_sync(0xffffffffu, newpos[i], o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (ang_cnt) { atomicAdd(&acc->ang_sum, ang_sum); atomicAdd(&acc->ang_cnt, (unsigned long long)ang_cnt); }
-        if (bad) atomicAdd(&acc->bad_rows, bad);
-        for (int i = 0; i < cfg.n_thr; ++i)
-            if (newpos[i]) atomicAdd(&acc->n_pos[i], (unsigned long long)newpos[i]);
-    }
+    flush_counters(ang_sum, ang_cnt, newpos, bad, cfg.n_thr, acc);
+}
+
+// (Measured and rejected, round 2: one LANE per (row, anchor) -- groups of 8 lanes, the first-minimum scan replayed on the
+//  gathered distances, bit-identical results -- runs the five libdevice chains of a row side by side on 2.2 waves of
+//  threads instead of 0.45, but issues 60 % more warp-level chain evaluations (20 of 32 lanes active) and repeats the
+//  target-side sin / cos per lane: 30.6 us against 21.4 us for the kernel above.)
+static void launch_assign_kernel(const float* logit, const float* target, long long M, const long long* M_dev, int B, int T,
+                                 const AssignCfg& cfg, float* D, uint8_t* mask, int32_t* argmin, unsigned long long* state,
+                                 float2* ang, LossAccum* acc, cudaStream_t stream) {
+    const int blocks = (int)((M + AR_THREADS - 1) / AR_THREADS);
+    assign_rows_kernel<<<blocks, AR_THREADS, 0, stream>>>(logit, target, M, M_dev, B, T, cfg, D, mask, argmin, state, ang, acc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -557,8 +590,8 @@ int launch_assign(const float* logit, const float* target, long long M, int B, i
     int rc = check_cfg(cfg);
     if (rc) return rc;
     if (M <= 0) return ADY_OK;
-    const int blocks = (int)((M + 127) / 128);
-    assign_rows_kernel<<<blocks, 128, 0, stream>>>(logit, target, M, nullptr, B, T, cfg, D, mask, argmin, nullptr, nullptr, nullptr);
+    if (M / AR_THREADS + 1 > 0x7fffffffLL) return set_error(ADY_ERR_INVALID, "adyolo_assign: too many rows");
+    launch_assign_kernel(logit, target, M, nullptr, B, T, cfg, D, mask, argmin, nullptr, nullptr, nullptr, stream);
     ADY_LAUNCH_CHECK("assign_rows_kernel");
     return ADY_OK;
 }
@@ -575,8 +608,8 @@ int launch_loss(const float* logit, const float* target, long long M, const long
     float2* ang = reinterpret_cast<float2*>(state + n_anchor);
     ADY_CUDA_CHECK(cudaMemsetAsync(ws, 0, loss_workspace_bytes(B, T, cfg), stream));
     if (M > 0) {
-        const int blocks = (int)((M + 127) / 128);
-        assign_rows_kernel<<<blocks, 128, 0, stream>>>(logit, target, M, M_dev, B, T, cfg, D, mask, argmin, state, ang, acc);
+        if (M / AR_THREADS + 1 > 0x7fffffffLL) return set_error(ADY_ERR_INVALID, "adyolo_loss: too many rows");
+        launch_assign_kernel(logit, target, M, M_dev, B, T, cfg, D, mask, argmin, state, ang, acc, stream);
         ADY_LAUNCH_CHECK("assign_rows_kernel");
     }
     int blocks = 0;
