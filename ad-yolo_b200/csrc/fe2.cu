@@ -13,8 +13,8 @@
 //                                                  bank-conflict free (3 hops, shared by the 2 frames)
 //   stage A  75 tasks / frame : window + DFT-16 of both packed FFTs (f32x2)          -> X1 (16 B / point)
 //   stage B  80 tasks / frame : DFT-15, in place                                      -> X2
-//   stage C 121 tasks / frame : twiddle + 2 x DFT-5, channel split, |X|^2, I / E, in place -> V  (224 + 18 threads, one round)
-//   mel     191 lane-jobs     : <= 7 non-zeros each, both frames per entry            -> 64-byte partial records
+//   stage C 121 tasks / frame : twiddle + 2 x DFT-5, channel split, |X|^2, I / E, in place -> V  (242 pair-tasks over two rounds)
+//   mel     156 lane-jobs     : <= 9 non-zeros each, both frames per entry            -> 64-byte partial records
 //   epilogue 128 threads      : (frame, mel): add the filter's records, 10 log10, standardise, coalesced store
 // The copy of the next tile is issued right after stage A and overlaps everything else.
 #include <atomic>
@@ -32,8 +32,8 @@ constexpr int CTAS_PER_SM = ADY_FE2_CTAS;   // x GROUPS tile pipelines each (fe2
 constexpr int NTB = GROUPS * NT;            // threads per CTA
 
 // barrier of one group (bar 0 = __syncthreads is the whole CTA).  The barrier number is re-derived from %tid.x at every
-// use: kept live across the tile loop it is the first value ptxas spills, and with all of L1 carved out as shared memory
-// a spill reload is an L2 round trip in front of the barrier.
+// use: kept live across the tile loop it is the first value ptxas spills, and with 227 KB of the SM's unified storage
+// carved out as shared memory a spill reload is mostly an L2 round trip in front of the barrier.
 __device__ __forceinline__ void group_sync() {
     if (GROUPS == 1) __syncthreads();
     else {

@@ -16,8 +16,8 @@
 //   * the exchange buffer holds one 16-byte element {re(A), re(B), im(A), im(B)} per point: every
 //     shared-memory access of the FFT stages is a 128-bit one, all conflict-free by construction;
 //   * stages B and C work in place, so one 19 KB buffer per frame serves X1, X2 and V;
-//   * the mel projection handles both frames of a tile per schedule entry and is balanced as 191
-//     lane-jobs of <= 7 non-zeros (one per thread) instead of 4 warp-tasks of 3..31 iterations.
+//   * the mel projection handles both frames of a tile per schedule entry and is balanced as 156
+//     lane-jobs of <= 9 non-zeros (one per thread) instead of 4 warp-tasks of 3..31 iterations.
 //
 // Everything is ADY_HD so that tests/emu runs the identical index logic on the CPU.
 #pragma once
