@@ -482,9 +482,10 @@ def main_ours(args):
                 #  against 148 SM x 128 lanes x 2 FLOP x the sampled SM clock
                 "fp32": {"achieved": BATCH * CLIP_S * 6.5e6 / (fe_ms / 1e3) / 1e12,
                          "peak": 148 * 128 * 2 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12, "unit": "TFLOP/s"},
-                "note": "bound by the shared-memory (L1 data) pipe, not HBM: three register-resident FFT stages exchange "
-                        "through shared memory and the sparse mel gather reads it again (ncu: l1tex data pipe ~69 % busy, "
-                        "FMA pipe ~41 %, DRAM ~8 %); see DESIGN.md section 4.1 / profiles/r02_*"}
+                "note": "not HBM-bound: three register-resident FFT stages exchange through shared memory, the sparse mel "
+                        "gather reads it again and every phase ends in a group barrier (ncu: L1 data pipe ~75 % busy, issue "
+                        "slots ~49 %, FMA pipe ~42 %, DRAM ~9 %; fewer instructions or more warps no longer move it); see "
+                        "DESIGN.md section 4.1 / profiles/r02_fe2_final4_*"}
         roof["fp32"]["frac"] = roof["fp32"]["achieved"] / roof["fp32"]["peak"]
     side = None
     if not args.no_side_configs:
