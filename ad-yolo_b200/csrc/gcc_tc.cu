@@ -640,6 +640,10 @@ gcc_ph16_kernel(const uint4* __restrict__ ph, long long n_frames, int T, const u
     asm volatile("cp.async.wait_all;" ::: "memory");
     mbar_wait(smem_u32(&mbar[(H_CHUNKS - 1) & (GT_STAGES - 1)]), (uint32_t)(((H_CHUNKS - 1) / GT_STAGES) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;");
+    // The epilogue stages its tiles in the A-operand memory.  The mbarrier chain already orders every warp's last operand
+    // stores before this point (full -> MMA -> commit -> the wait above); the block barrier states the same in a form
+    // that compute-sanitizer's racecheck models (it reported the two writes as a hazard without it).  Once per CTA.
+    __syncthreads();
 
     if (warp < GT_THREADS / 32) gcc_epilogue(tmem, smem, warp, lane, f0, n_frames, T, mean, istd, out, os);
     asm volatile("tcgen05.fence::before_thread_sync;");
