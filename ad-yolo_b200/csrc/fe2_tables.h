@@ -133,6 +133,15 @@ inline bool build_mel_plan(const float* mel, MelPlan& p) {
 // pair that is unique within both half-warps, and a colour class is a matching of <= 5 edges, so the lanes of one
 // colour take the columns colour, colour + 16, ... < 80.
 inline bool build_col_perm(uint8_t perm[80]) {
+#ifdef ADY_FE2_LINEAR_STAGING
+    // Measurement variant (tools/build_variant.py lin -DADY_FE2_LINEAR_STAGING): the layout a bulk / TMA copy would produce,
+    // sample N of the tile at row N / 75, column N mod 75.  Lane l then reads column 16 l mod 75, and because the row
+    // pitch is a multiple of 16 samples the lanes of a half-warp fall into bank pairs 0,0,0,0,0,5,5,5,5,5,10,... (5-way
+    // conflicts on every stage-A sample load); numbers in DESIGN.md section 4.1.
+    for (int i = 0; i < 80; ++i) perm[i] = 0;
+    for (int l = 0; l < 75; ++l) perm[l] = (uint8_t)((16 * l) % 75);
+    return true;
+#endif
     int colour[75], at_r[5][16], at_w[5][16];           // at_x[node][colour] = lane using that colour at the node, or -1
     for (int n = 0; n < 5; ++n)
         for (int c = 0; c < 16; ++c) at_r[n][c] = at_w[n][c] = -1;
