@@ -125,3 +125,44 @@ def test_rotation_on_the_host_equals_the_fused_device_rotation(A, scaler2021):
     rows_host = A.label_rows_batched(torch.from_numpy(np.concatenate(host_e)).cuda(), 10, grid)
     assert torch.equal(rows_fused, rows_host)
     assert (fused - plain).abs().max().item() < 2e-4
+
+
+def test_front_end_and_loss_on_two_streams_equal_the_single_stream_step(A):
+    """bench.py issues the two independent halves of a step (front end | label rows + loss) on two CUDA streams.  Every
+    entry point launches on torch's current stream and keeps its state (tables, launch counter, workspaces) per call or
+    behind a mutex, so the results must be those of the same calls on one stream: features bit-identical, the label rows
+    identical, loss and gradient identical up to the order of the floating-point atomics (<= 1e-6 relative)."""
+    from oracle.loss_torch import default_params
+    rng = np.random.default_rng(3)
+    B, T, C = 24, 50, 12
+    audio = torch.from_numpy(np.clip(rng.standard_normal((B, 120000, 4)) * 3000, -32768, 32767).astype(np.int16)).cuda()
+    ev = np.array([[b, t, rng.integers(0, C), rng.integers(-180, 181), rng.integers(-90, 91)]
+                   for b in range(B) for t in range(T) for _ in range(int(rng.integers(0, 3)))], dtype=np.float64)
+    ev = torch.from_numpy(ev).cuda()
+    grid = A.labels.GridSpec(C, 5, [45, 45], 0.5)
+    crit = A.ADYOLOloss(default_params(C, "cuda:0"))
+    logit = torch.randn((B, T, 2400), device="cuda", generator=torch.Generator(device="cuda").manual_seed(7)).requires_grad_(True)
+
+    def loss_side():
+        rows = A.label_rows_batched(ev, T, grid, max_rows=4 * ev.shape[0])
+        logit.grad = None
+        loss = crit(logit, rows)
+        loss.backward()
+        return rows.materialize() if hasattr(rows, "materialize") else rows, loss.detach().clone(), logit.grad.clone()
+
+    f0 = A.features_batched(audio, None)
+    r0, l0, g0 = loss_side()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for _ in range(4):                                   # several overlapping steps in flight
+        with torch.cuda.stream(s1):
+            f = A.features_batched(audio, None)
+        with torch.cuda.stream(s2):
+            outs.append((f,) + loss_side())
+    torch.cuda.synchronize()
+    for f, r, l, g in outs:
+        assert torch.equal(f, f0)
+        assert torch.equal(r, r0)
+        assert abs(l.item() - l0.item()) <= 1e-6 * abs(l0.item())
+        assert (g - g0).abs().max().item() <= 1e-6 * g0.abs().max().item() + 1e-12
