@@ -8,7 +8,8 @@ workload (N=1, config[1] of BASELINE.json): batch of 256 synthetic 5-s FOA chunk
   (256, 50, 2400).  The encoder itself is stock PyTorch and out of scope (not timed).
 A "step" = one pass of that hot path over one batch.  Weak scaling: every rank gets its own
 256-clip batch, no data-path collective (clips are independent).  `value` issues the two independent halves of the
-step (front end | label rows + loss) on two CUDA streams; `single_stream` reports the same step on one stream.
+step (front end | label rows + loss) on two CUDA streams, captured once and replayed as one CUDA graph per step (one host
+launch per step keeps 8 ranks on one host GPU-bound); `single_stream` reports the same step eagerly on one stream.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
@@ -359,7 +360,30 @@ def main_ours(args):
         A.features_batched(audio, scaler_dev, out=feat_buf, timing_events=fe_events if record else None)
         return loss_side(events)
 
-    def timed_steps(n, two_streams, record):
+    def capture_step_graph():
+        """The two-stream step as ONE CUDA graph (fork / join inside the capture): a replay costs the host one launch
+        instead of ~12 driver calls, which is what keeps 8 ranks on one host GPU-bound.  Returns None when the capture
+        is not possible (the eager two-stream step is used then)."""
+        try:
+            graph = torch.cuda.CUDAGraph()
+            n0 = L.adyolo_launch_count()
+            with torch.cuda.graph(graph):
+                cur = torch.cuda.current_stream()
+                s_fe.wait_stream(cur)
+                s_loss.wait_stream(cur)
+                step(audio_d, events_d, two_streams=True)
+                cur.wait_stream(s_fe)
+                cur.wait_stream(s_loss)
+            per_step = L.adyolo_launch_count() - n0
+            graph.replay()
+            torch.cuda.synchronize()
+            return graph, per_step
+        except Exception as e:                                    # pragma: no cover (depends on the driver / torch build)
+            print("bench: CUDA-graph capture of the step failed, using eager streams:", repr(e), file=sys.stderr)
+            torch.cuda.synchronize()
+            return None, 0
+
+    def timed_steps(n, two_streams, record, graph=None):
         """n steps between two events on the current stream; the side streams fork after the first and join before the second"""
         cur = torch.cuda.current_stream()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -367,6 +391,11 @@ def main_ours(args):
         if two_streams:
             s_fe.wait_event(t0)
             s_loss.wait_event(t0)
+        if graph is not None:
+            for _ in range(n):
+                graph.replay()
+            t1.record()
+            return t0, t1
         for _ in range(n):
             step(audio_d, events_d, record=record, two_streams=two_streams)
         if two_streams:
@@ -393,12 +422,19 @@ def main_ours(args):
     sampler = ClockSampler(local_rank, pci)
     sampler.start()
     L = A._lib.lib()
+    step_graph, graph_launches = (None, 0) if args.no_graph else capture_step_graph()
+    if step_graph is not None:
+        timed_steps(args.warmup, True, False, graph=step_graph)
+        barrier()
     launches0 = L.adyolo_launch_count()
-    e0, e1 = timed_steps(args.steps, True, True)
-    launches = L.adyolo_launch_count() - launches0       # counted by the library at every launch site
+    e0, e1 = timed_steps(args.steps, True, step_graph is None, graph=step_graph)
+    # counted by the library at every launch site; a graph replay runs the launches counted once at capture
+    launches = graph_launches * args.steps if step_graph is not None else L.adyolo_launch_count() - launches0
     barrier()
     ms = e0.elapsed_time(e1)
     n_fe = len(fe_events)
+    timed_steps(max(3, args.warmup), False, False)        # (eager steps again after the graph replays)
+    barrier()
     q0, q1 = timed_steps(args.steps, False, True)         # the same steps on one stream, for reference
     barrier()
     ms_single = q0.elapsed_time(q1)
@@ -499,9 +535,10 @@ def main_ours(args):
     except Exception:
         peak = 6650.0
     roof = None
-    if fe_ms:
+    if fe_ms or fe_single_ms:
         # roofline of the dominant kernel from its launches in the single-stream pass (the kernel has the GPU to itself
-        # there); in the two-stream pass its duration also contains the loss-side kernels that run next to it
+        # there); in the eager two-stream pass its duration also contains the loss-side kernels that run next to it
+        # (not available when the step is replayed as a graph: timing events cannot be recorded inside a capture)
         fe_overlapped_ms, fe_ms = fe_ms, (fe_single_ms or fe_ms)
         alg_bytes = BATCH * CLIP_S * BYTES_PER_AUDIO_S
         ach = alg_bytes / (fe_ms / 1e3) / 1e9
@@ -534,8 +571,9 @@ def main_ours(args):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_dict(world),
-                "streams": "front end on one CUDA stream, label rows + loss forward/backward on a second one (independent inputs); "
-                           "e2e and the side configs run on a single stream",
+                "streams": "front end on one CUDA stream, label rows + loss forward/backward on a second one (independent inputs)"
+                           + (", captured once and replayed as one CUDA graph per step" if step_graph is not None else "")
+                           + "; e2e and the side configs run eagerly on a single stream",
                 "single_stream": {"value": hours_per_step * args.steps / (ms_single / 1e3), "unit": "audio-hours/s",
                                   "ms_per_step": ms_single / args.steps},
                 "e2e": {"value": e2e_value, "unit": "audio-hours/s", "ms_per_step": e2e_ms / args.steps,
@@ -579,6 +617,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager two-stream step instead of one CUDA graph per step")
     ap.add_argument("--no-side-configs", action="store_true", help="skip config[0]/[2]/[3] and the reference-default shape")
     a = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Native libraries write there too (torch's ProcessGroupNCCL prints "NCCL
