@@ -367,7 +367,9 @@ def main_ours(args):
         try:
             graph = torch.cuda.CUDAGraph()
             n0 = L.adyolo_launch_count()
-            with torch.cuda.graph(graph):
+            # thread_local: only this thread's calls are checked during the capture (the clock sampler and NCCL's watchdog
+            # run in other threads)
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 cur = torch.cuda.current_stream()
                 s_fe.wait_stream(cur)
                 s_loss.wait_stream(cur)
