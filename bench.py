@@ -560,7 +560,8 @@ def main_ours(args):
                 #  against 148 SM x 128 lanes x 2 FLOP x the sampled SM clock
                 "fp32": {"achieved": BATCH * CLIP_S * 6.5e6 / (fe_ms / 1e3) / 1e12,
                          "peak": 148 * 128 * 2 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12, "unit": "TFLOP/s"},
-                "note": "not HBM-bound: three register-resident FFT stages exchange through shared memory, the sparse mel "
+                "note": "kernel_ms: CUDA events around the front-end launches of the single-stream pass (inside a graph replay "
+                        "no timing events can be recorded). Not HBM-bound: three register-resident FFT stages exchange through shared memory, the sparse mel "
                         "gather reads it again and every phase ends in a group barrier (ncu: L1 data pipe ~75 % busy, issue "
                         "slots ~49 %, FMA pipe ~42 %, DRAM ~9 %; fewer instructions or more warps no longer move it); see "
                         "DESIGN.md section 4.1 / profiles/r02_fe2_final4_*"}
