@@ -84,6 +84,9 @@ class HostBatchPipeline:
         if self._slots[s] is None or any(d.shape != h.shape or d.dtype != h.dtype for d, h in zip(self._slots[s], host_tensors)) \
                 or len(self._slots[s]) != len(host_tensors):
             self._slots[s] = [torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in host_tensors]
+            # the caching allocator may hand out blocks whose previous tenant still has kernels queued on the
+            # allocating (current) stream: order the first copy into a fresh slot after them
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self._free[s])       # consumer of the previous use is done
             for d, h in zip(self._slots[s], host_tensors):

@@ -155,7 +155,9 @@ typedef struct adyolo_grid_cfg {
 
 /* FeatureLabelProcessor.get_yolo_label (datasets.py:457-482) + label half of collate_fn (:175-184)
  *   events   device float64 (E, 5) rows [batch, frame, class, azi, ele] in dataset order
- *   cellmask device uint32 (E): bit (Gi*Ge + Gj) set for every responsible cell
+ *   cellmask device uint32 (E): bit (Gi*Ge + Gj) set for every responsible cell -- hence grids of at most
+ *            32 cells (the reference's 45-degree grid is 8 x 4 = 32; 60 / 90 degrees are smaller); a finer grid
+ *            returns ADYOLO_ERR_UNSUPPORTED here (the loss entries take up to 16 x 16 cells)
  *   total_rows device int64[1]: M = total number of rows
  * then adyolo_label_rows writes rows device float32 (M, 7) [batch, frame, Gi, Gj, class, U, V].  */
 size_t adyolo_label_workspace_bytes(int64_t E);
