@@ -52,6 +52,27 @@ def test_unsupported_geometry_is_refused(built):
     assert b"1200" in _lib.lib().adyolo_last_error()
 
 
+def test_grids_beyond_the_compiled_limits_are_refused(built):
+    """one 32-bit cell mask per event (label path), 16 x 16 cells (loss).  A finer grid than the
+    reference's 45 degrees is refused with ADYOLO_ERR_UNSUPPORTED before anything is launched (host-side check: runs
+    without a GPU), never truncated."""
+    from adyolo_b200 import _lib
+    from adyolo_b200.labels import GridSpec
+    L = _lib.lib()
+    total = ctypes.c_int64(-1)
+    g30 = GridSpec(12, 5, [30, 30], 0.5)                       # 12 x 6 = 72 cells
+    assert g30.nb_grids == [12, 6]
+    rc = L.adyolo_label_cells(None, 0, 50, ctypes.byref(g30.c), None, 0, None, ctypes.byref(total), None, None)
+    assert rc == -3 and b"32-cell" in L.adyolo_last_error()
+    rc = L.adyolo_label_cells_rows(None, 0, 50, ctypes.byref(g30.c), None, 0, None, ctypes.byref(total), None, None, 0, None)
+    assert rc == -3 and b"32-cell" in L.adyolo_last_error()
+    g20 = GridSpec(12, 5, [20, 20], 0.5)                       # 18 x 9: beyond the loss kernels' 16 x 16 too
+    rc = L.adyolo_label_cells(None, 0, 50, ctypes.byref(g20.c), None, 0, None, ctypes.byref(total), None, None)
+    assert rc == -3 and b"too large" in L.adyolo_last_error()
+    assert L.adyolo_loss_workspace_bytes(1, 1, ctypes.byref(g20.c)) == 0
+    assert total.value == -1                                   # nothing was written
+
+
 def test_no_cpu_fallback(built):
     import torch
     if torch.cuda.is_available():
